@@ -1,0 +1,154 @@
+/* trs.h -- C ABI of libtrs_b200.so: the B200 (sm_100a) hot path of TorchRecSys.
+ *
+ * The reference (FrancescoI/torchrecsys) is pure Python on stock torch and has no FFI of its
+ * own; every entry point below replaces a span of reference Python (cited per function,
+ * paths relative to the reference root) and is what a binding for that span would call.
+ * INTEGRATION.md shows the ctypes stubs.
+ *
+ * Rules of the boundary
+ *  - plain C: pointers, sizes, PODs.  No torch / C++ types.
+ *  - every pointer is a DEVICE pointer unless the name ends in _host.
+ *  - the caller owns and allocates every buffer, including workspaces (the *_bytes functions
+ *    size them).  The library never allocates, frees or retains a pointer.
+ *  - every call is asynchronous on `stream` and never synchronises.
+ *  - return value: 0 on success, negative trs_status otherwise; the message of the last failure
+ *    on the calling thread is available from trs_last_error().  No exception crosses the ABI.
+ *  - ids are int64 ("LongTensor", dataset/dataset.py:268-272), parameters are fp32 row-major
+ *    [n_rows, dim] exactly as nn.Embedding stores them; the kernels update them in place.
+ */
+#ifndef TRS_H_
+#define TRS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRS_ABI_VERSION 1
+#define TRS_MAX_META 8 /* metadata features (columns) per model */
+
+typedef struct CUstream_st* trs_stream_t; /* == cudaStream_t */
+
+typedef enum {
+    TRS_OK = 0,
+    TRS_ERR_ARG = -1,     /* bad argument (null pointer, unsupported dim, ...) */
+    TRS_ERR_CUDA = -2,    /* a CUDA runtime call failed */
+    TRS_ERR_WORKSPACE = -3 /* caller workspace too small */
+} trs_status;
+
+typedef enum { TRS_NET_LINEAR = 0, TRS_NET_FM = 1 } trs_net;
+typedef enum { TRS_OPT_SGD = 0, TRS_OPT_ADAGRAD = 1, TRS_OPT_SPARSE_ADAM = 2 } trs_opt;
+
+/* One id space = an embedding table [n_rows, dim] plus (optionally) the width-1 table that is
+ * always looked up with the same ids (Linear: user_bias/item_bias, linear.py:45-51; FM:
+ * linear_user/linear_item/linear_metadata, fm.py:42-56).  s0/s1 are the optimizer state tensors
+ * of the same shape as their parameter: Adagrad `sum` -> s0; SparseAdam `exp_avg` -> s0,
+ * `exp_avg_sq` -> s1; unused ones are NULL. */
+typedef struct {
+    float* emb;
+    float* emb_s0;
+    float* emb_s1;
+    float* lin; /* [n_rows, 1] or NULL */
+    float* lin_s0;
+    float* lin_s1;
+    int64_t n_rows;
+} trs_table;
+
+typedef struct {
+    int32_t net;    /* trs_net */
+    int32_t dim;    /* n_factors */
+    int32_t n_meta; /* F: metadata features, 0..TRS_MAX_META */
+    int32_t reserved;
+    trs_table user;
+    trs_table item;
+    trs_table meta[TRS_MAX_META];
+} trs_model;
+
+/* The (already shuffled) samples of one epoch, as the reference loader would emit them batch
+ * after batch (dataset/dataset.py:414-458): step s covers samples [s*batch, min((s+1)*batch, n)).
+ * Metadata ids are one id per feature, row-major [n_samples, n_meta]. */
+typedef struct {
+    const int64_t* user;
+    const int64_t* pos;
+    const int64_t* neg;
+    const int64_t* pos_meta; /* NULL when n_meta == 0 */
+    const int64_t* neg_meta;
+    int64_t n_samples;
+    int32_t batch;
+    int32_t reserved;
+} trs_epoch;
+
+/* Row-wise optimizer (torch.optim.{SGD,Adagrad,SparseAdam} on sparse gradients;
+ * torch: optim/_functional.py:24-84, optim/adagrad.py:363-373, optim/sgd.py).
+ * step_scale[s] is the scalar the update of step s is multiplied by, computed by the host in
+ * double exactly as torch does and rounded to fp32: SGD lr; Adagrad clr = lr/(1+(t-1)*lr_decay);
+ * SparseAdam lr*sqrt(1-beta2^t)/(1-beta1^t). */
+typedef struct {
+    int32_t kind; /* trs_opt */
+    int32_t reserved;
+    double beta1; /* python floats of the torch optimizer; (1-beta) is rounded to fp32 inside */
+    double beta2;
+    double eps;
+    const float* step_scale; /* device, [>= first_step + n_steps] */
+} trs_optim;
+
+/* ---- library ------------------------------------------------------------------------- */
+int trs_abi_version(void);
+const char* trs_last_error(void);
+/* SM count and the persistent grid the training kernel would use on the current device. */
+int trs_device_info(int* sm_count_host, int* train_grid_host, int* train_block_host);
+
+/* ---- a1: embedding rows (embeddings/init_embeddings.py:5,53 -> aten::embedding) -------- */
+/* out[b,:] = table[idx[b],:] (+ sum_f meta_emb[f][meta_idx[b,f],:]) -- 128-bit row gather that
+ * sum-pools the metadata rows into the item row (linear.py:67-75).  Bit-exact. */
+int trs_embed_gather_sum(const float* table, int dim, const int64_t* idx, int64_t n,
+                         const float* const* meta_tables_host, const int64_t* meta_idx, int n_meta,
+                         float* out, trs_stream_t stream);
+
+/* ---- a2/a3: scorer forward (linear.py:54-80 -> (B,1); fm.py:60-101 -> (B,)) ------------- */
+int trs_scores(const trs_model* model, const int64_t* user, const int64_t* item,
+               const int64_t* meta, int64_t n, float* out, trs_stream_t stream);
+
+/* ---- a9: dynamic negatives (dataset/dataset.py:435-447) on device, Philox4x32-10 --------- */
+/* neg[j] ~ U[0, n_items) redrawn while == pos[j]; counter = first_index + j, key = seed.
+ * If item_meta ([n_items, n_meta]) is given, also emits neg_meta[j,:] = item_meta[neg[j],:]
+ * (dataset.py:375-411).  Bit-exact against oracle/cf_oracle.py:philox_negatives. */
+int trs_philox_negatives(uint64_t seed, uint64_t first_index, const int64_t* pos, int64_t n,
+                         int64_t n_items, const int64_t* item_meta, int n_meta, int64_t* neg,
+                         int64_t* neg_meta, trs_stream_t stream);
+
+/* ids in [0, n_rows)?  Adds the number of offenders to *bad_count (device int32). */
+int trs_validate_ids(const int64_t* ids, int64_t n, int64_t n_rows, int32_t* bad_count,
+                     trs_stream_t stream);
+
+/* ---- a7 (K5): the sort half of coalesce(), for a whole epoch at once ---------------------- */
+/* For every step and every id space, a stable sort of that step's lookups by row id (what
+ * grad.coalesce() does per step, torch: optim/_functional.py:44).  `plan` receives the sorted
+ * (row, lookup) pairs; `tmp` is scratch of trs_plan_tmp_bytes(). */
+size_t trs_plan_bytes(const trs_model* model, const trs_epoch* epoch);
+size_t trs_plan_tmp_bytes(const trs_model* model, const trs_epoch* epoch);
+int trs_plan_build(const trs_model* model, const trs_epoch* epoch, void* plan, size_t plan_bytes,
+                   void* tmp, size_t tmp_bytes, trs_stream_t stream);
+
+/* ---- a6+a5+a7: fused fwd + hinge + bwd + segmented reduce + row-wise optimizer ------------ */
+/* Runs steps [first_step, first_step+n_steps) of the epoch in ONE persistent cooperative
+ * launch (model.py:274-284 per step: forward x2, hinge_loss, backward, optimizer.step()).
+ * loss[s] receives the batch-mean hinge of step first_step+s (the value loss.item() returns at
+ * model.py:200), without a host sync. */
+size_t trs_train_workspace_bytes(const trs_model* model, const trs_epoch* epoch);
+int trs_train_steps(const trs_model* model, const trs_epoch* epoch, const trs_optim* optim,
+                    const void* plan, void* workspace, size_t workspace_bytes, int first_step,
+                    int n_steps, float* loss, trs_stream_t stream);
+
+/* ---- a10: evaluate (model.py:292-338, evaluate/metrics.py:23-31) -------------------------- */
+/* Per batch b of `epoch`: loss[b] = mean hinge, auc[b] = #(pos > neg)/len.  pos_out/neg_out
+ * (nullable) receive the raw scores. */
+int trs_eval_pairwise(const trs_model* model, const trs_epoch* epoch, float* loss, float* auc,
+                      float* pos_out, float* neg_out, trs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRS_H_ */

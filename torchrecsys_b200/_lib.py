@@ -1,0 +1,192 @@
+"""ctypes binding of include/trs.h (libtrs_b200.so).
+
+There is no CPU fallback: if the library is missing or a call fails this module raises.  torch is
+used only for device memory (``data_ptr()``) and the current CUDA stream."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+MAX_META = 8
+NET_LINEAR, NET_FM = 0, 1
+OPT_SGD, OPT_ADAGRAD, OPT_SPARSE_ADAM = 0, 1, 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtrs_b200.so")
+
+# every symbol include/trs.h declares (tests/test_abi.py checks the .so exports them all)
+SYMBOLS = [
+    "trs_abi_version", "trs_last_error", "trs_device_info", "trs_embed_gather_sum", "trs_scores",
+    "trs_philox_negatives", "trs_validate_ids", "trs_plan_bytes", "trs_plan_tmp_bytes",
+    "trs_plan_build", "trs_train_workspace_bytes", "trs_train_steps", "trs_eval_pairwise",
+]
+
+
+class Table(C.Structure):
+    _fields_ = [("emb", C.c_void_p), ("emb_s0", C.c_void_p), ("emb_s1", C.c_void_p),
+                ("lin", C.c_void_p), ("lin_s0", C.c_void_p), ("lin_s1", C.c_void_p),
+                ("n_rows", C.c_int64)]
+
+
+class Model(C.Structure):
+    _fields_ = [("net", C.c_int32), ("dim", C.c_int32), ("n_meta", C.c_int32), ("reserved", C.c_int32),
+                ("user", Table), ("item", Table), ("meta", Table * MAX_META)]
+
+
+class Epoch(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("pos", C.c_void_p), ("neg", C.c_void_p),
+                ("pos_meta", C.c_void_p), ("neg_meta", C.c_void_p),
+                ("n_samples", C.c_int64), ("batch", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Optim(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("beta1", C.c_double),
+                ("beta2", C.c_double), ("eps", C.c_double), ("step_scale", C.c_void_p)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m torchrecsys_b200.build` "
+                "(there is no CPU / eager fallback for the hot path)")
+        L = C.CDLL(LIB_PATH)
+        L.trs_last_error.restype = C.c_char_p
+        for name in ("trs_plan_bytes", "trs_plan_tmp_bytes", "trs_train_workspace_bytes"):
+            getattr(L, name).restype = C.c_size_t
+        if L.trs_abi_version() != 1:
+            raise RuntimeError("libtrs_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError(f"libtrs_b200: {lib().trs_last_error().decode()} (status {rc})")
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=None) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("libtrs_b200 takes CUDA tensors only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("tensor must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"expected {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def make_table(emb, emb_s0=None, emb_s1=None, lin=None, lin_s0=None, lin_s1=None) -> Table:
+    f32 = torch.float32
+    return Table(_ptr(emb, f32), _ptr(emb_s0, f32), _ptr(emb_s1, f32), _ptr(lin, f32),
+                 _ptr(lin_s0, f32), _ptr(lin_s1, f32), emb.shape[0])
+
+
+def make_model(net: int, dim: int, user: Table, item: Table, metas: Sequence[Table]) -> Model:
+    if len(metas) > MAX_META:
+        raise RuntimeError(f"at most {MAX_META} metadata features are supported")
+    m = Model(net, dim, len(metas), 0, user, item)
+    for f, t in enumerate(metas):
+        m.meta[f] = t
+    return m
+
+
+def make_epoch(user, pos, neg, pos_meta=None, neg_meta=None, batch: int = 512) -> Epoch:
+    i64 = torch.int64
+    return Epoch(_ptr(user, i64), _ptr(pos, i64), _ptr(neg, i64), _ptr(pos_meta, i64),
+                 _ptr(neg_meta, i64), user.shape[0], batch, 0)
+
+
+def device_info():
+    sm, grid, block = C.c_int(), C.c_int(), C.c_int()
+    _check(lib().trs_device_info(C.byref(sm), C.byref(grid), C.byref(block)))
+    return sm.value, grid.value, block.value
+
+
+def embed_gather_sum(table, idx, meta_tables=(), meta_idx=None) -> torch.Tensor:
+    n, dim = idx.shape[0], table.shape[1]
+    out = torch.empty((n, dim), dtype=torch.float32, device=table.device)
+    ptrs = (C.c_void_p * max(len(meta_tables), 1))(*[_ptr(t, torch.float32) for t in meta_tables])
+    _check(lib().trs_embed_gather_sum(C.c_void_p(_ptr(table, torch.float32)), dim,
+                                      C.c_void_p(_ptr(idx, torch.int64)), C.c_int64(n), ptrs,
+                                      C.c_void_p(_ptr(meta_idx, torch.int64)), len(meta_tables),
+                                      C.c_void_p(_ptr(out)), _stream()))
+    return out
+
+
+def scores(model: Model, user, item, meta=None) -> torch.Tensor:
+    n = user.shape[0]
+    out = torch.empty(n, dtype=torch.float32, device=user.device)
+    _check(lib().trs_scores(C.byref(model), C.c_void_p(_ptr(user, torch.int64)),
+                            C.c_void_p(_ptr(item, torch.int64)), C.c_void_p(_ptr(meta, torch.int64)),
+                            C.c_int64(n), C.c_void_p(_ptr(out)), _stream()))
+    return out
+
+
+def philox_negatives(seed: int, first_index: int, pos, n_items: int, item_meta=None):
+    n = pos.shape[0]
+    neg = torch.empty_like(pos)
+    n_meta = 0 if item_meta is None else item_meta.shape[1]
+    neg_meta = None if item_meta is None else torch.empty((n, n_meta), dtype=torch.int64, device=pos.device)
+    _check(lib().trs_philox_negatives(C.c_uint64(seed), C.c_uint64(first_index),
+                                      C.c_void_p(_ptr(pos, torch.int64)), C.c_int64(n),
+                                      C.c_int64(n_items), C.c_void_p(_ptr(item_meta, torch.int64)),
+                                      n_meta, C.c_void_p(_ptr(neg)), C.c_void_p(_ptr(neg_meta)), _stream()))
+    return neg, neg_meta
+
+
+def count_bad_ids(ids, n_rows: int, counter: torch.Tensor) -> None:
+    _check(lib().trs_validate_ids(C.c_void_p(_ptr(ids, torch.int64)), C.c_int64(ids.numel()),
+                                  C.c_int64(n_rows), C.c_void_p(_ptr(counter, torch.int32)), _stream()))
+
+
+def plan_build(model: Model, epoch: Epoch, device) -> torch.Tensor:
+    L = lib()
+    nbytes = L.trs_plan_bytes(C.byref(model), C.byref(epoch))
+    tbytes = L.trs_plan_tmp_bytes(C.byref(model), C.byref(epoch))
+    plan = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+    tmp = torch.empty(max(tbytes, 1), dtype=torch.uint8, device=device)
+    _check(L.trs_plan_build(C.byref(model), C.byref(epoch), C.c_void_p(plan.data_ptr()),
+                            C.c_size_t(nbytes), C.c_void_p(tmp.data_ptr()), C.c_size_t(tbytes), _stream()))
+    return plan
+
+
+def train_workspace(model: Model, epoch: Epoch, device) -> torch.Tensor:
+    nbytes = lib().trs_train_workspace_bytes(C.byref(model), C.byref(epoch))
+    if nbytes == 0:
+        raise RuntimeError(f"libtrs_b200: {lib().trs_last_error().decode()}")
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+def train_steps(model: Model, epoch: Epoch, optim: Optim, plan, workspace, first_step: int,
+                n_steps: int, loss_out: torch.Tensor) -> None:
+    _check(lib().trs_train_steps(C.byref(model), C.byref(epoch), C.byref(optim),
+                                 C.c_void_p(plan.data_ptr()), C.c_void_p(workspace.data_ptr()),
+                                 C.c_size_t(workspace.numel()), first_step, n_steps,
+                                 C.c_void_p(_ptr(loss_out, torch.float32)), _stream()))
+
+
+def eval_pairwise(model: Model, epoch: Epoch, want_scores: bool = False):
+    n = epoch.n_samples
+    nb = (n + epoch.batch - 1) // epoch.batch
+    dev = torch.device("cuda", torch.cuda.current_device())
+    loss = torch.empty(nb, dtype=torch.float32, device=dev)
+    auc = torch.empty(nb, dtype=torch.float32, device=dev)
+    pos = torch.empty(n, dtype=torch.float32, device=dev) if want_scores else None
+    neg = torch.empty(n, dtype=torch.float32, device=dev) if want_scores else None
+    _check(lib().trs_eval_pairwise(C.byref(model), C.byref(epoch), C.c_void_p(_ptr(loss)),
+                                   C.c_void_p(_ptr(auc)), C.c_void_p(_ptr(pos)), C.c_void_p(_ptr(neg)),
+                                   _stream()))
+    return loss, auc, pos, neg

@@ -1,0 +1,247 @@
+// plan.cu -- the sort half of coalesce() (torch: optim/_functional.py:44) for a whole epoch:
+// for every step and id space, a STABLE sort of that step's lookups by row id, so the training
+// kernel can reduce duplicate rows deterministically (in lookup order) before the non-linear
+// optimizer update.  Batched LSD radix sort, 8-bit digits, one segment per step.
+//
+// Lookups of a step with B_s samples:   user space: j in [0,B_s)      -> user[j]
+//                                       item space: j in [0,2B_s)     -> j<B_s ? pos[j] : neg[j-B_s]
+//                                       meta f    : j in [0,2B_s)     -> pos_meta[j,f] / neg_meta[j-B_s,f]
+#include "plan.cuh"
+
+namespace trs {
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ROWS = 8;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ROWS;
+
+struct SortSrc {
+    // first pass: ids
+    const int64_t* a;
+    const int64_t* b;
+    int stride, off;
+    // later passes: pairs
+    const uint32_t* key;
+    const uint32_t* val;
+};
+
+template <bool FIRST>
+__device__ __forceinline__ void load_pair(const SortSrc& s, int64_t step, int B, int Bs, int mult,
+                                          int j, uint32_t& key, uint32_t& val) {
+    if (FIRST) {
+        const int64_t sample0 = step * (int64_t)B;
+        const int64_t id = (j < Bs) ? s.a[(sample0 + j) * s.stride + s.off]
+                                    : s.b[(sample0 + j - Bs) * s.stride + s.off];
+        key = (uint32_t)id;
+        val = (uint32_t)j;
+    } else {
+        const int64_t base = (int64_t)mult * step * B;
+        key = s.key[base + j];
+        val = s.val[base + j];
+    }
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_hist_kernel(SortSrc src, uint32_t* __restrict__ hist, int tiles, int64_t n_samples, int B,
+                 int mult, int shift) {
+    __shared__ uint32_t s_hist[256];
+    const int64_t step = blockIdx.y;
+    const int tile = blockIdx.x;
+    const int Bs = (int)min((int64_t)B, n_samples - step * B);
+    const int len = mult * Bs;
+    s_hist[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SORT_ROWS; ++r) {
+        int j = tile * SORT_TILE + r * SORT_THREADS + threadIdx.x;
+        if (j < len) {
+            uint32_t key, val;
+            load_pair<FIRST>(src, step, B, Bs, mult, j, key, val);
+            atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+        }
+    }
+    __syncthreads();
+    hist[((size_t)step * 256 + threadIdx.x) * tiles + tile] = s_hist[threadIdx.x];
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_scatter_kernel(SortSrc src, uint32_t* __restrict__ dst_key, uint32_t* __restrict__ dst_val,
+                    const uint32_t* __restrict__ hist, int tiles, int64_t n_samples, int B, int mult,
+                    int shift) {
+    __shared__ uint32_t s_base[256];
+    __shared__ uint32_t s_run[256];
+    __shared__ uint32_t s_wcnt[SORT_THREADS / 32][256];
+    __shared__ uint32_t s_wtot[SORT_THREADS / 32];
+    const int64_t step = blockIdx.y;
+    const int tile = blockIdx.x;
+    const int Bs = (int)min((int64_t)B, n_samples - step * B);
+    const int len = mult * Bs;
+    const int64_t base = (int64_t)mult * step * B;
+    const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
+
+    // global base of digit d for this tile: sum_{d'<d} total[d'] + sum_{t<tile} hist[d][t]
+    {
+        const uint32_t* h = hist + ((size_t)step * 256 + d) * tiles;
+        uint32_t total = 0, before = 0;
+        for (int t = 0; t < tiles; ++t) {
+            uint32_t c = h[t];
+            total += c;
+            if (t < tile) before += c;
+        }
+        uint32_t inc = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) s_wtot[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += s_wtot[w];
+        s_base[d] = wbase + inc - total + before;
+        s_run[d] = 0;
+    }
+    __syncthreads();
+
+    for (int r = 0; r < SORT_ROWS; ++r) {
+        const int j = tile * SORT_TILE + r * SORT_THREADS + d;
+        const bool valid = j < len;
+        uint32_t key = 0, val = 0;
+        if (valid) load_pair<FIRST>(src, step, B, Bs, mult, j, key, val);
+        const uint32_t dg = valid ? ((key >> shift) & 255u) : 256u;
+#pragma unroll
+        for (int w = 0; w < SORT_THREADS / 32; ++w) s_wcnt[w][d] = 0;
+        __syncthreads();
+        const uint32_t peers = __match_any_sync(0xffffffffu, dg);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank == 0) s_wcnt[warp][dg] = __popc(peers);
+        __syncthreads();
+        {
+            uint32_t run = s_run[d];
+#pragma unroll
+            for (int w = 0; w < SORT_THREADS / 32; ++w) {
+                uint32_t c = s_wcnt[w][d];
+                s_wcnt[w][d] = run;
+                run += c;
+            }
+            s_run[d] = run;
+        }
+        __syncthreads();
+        if (valid) {
+            const uint32_t p = s_base[dg] + s_wcnt[warp][dg] + rank;
+            dst_key[base + p] = key;
+            dst_val[base + p] = val;
+        }
+        __syncthreads();
+    }
+}
+
+static int bits_for(int64_t n_rows) {
+    int b = 1;
+    while (((int64_t)1 << b) < n_rows) ++b;
+    return b;
+}
+
+// Sort one id space for all steps.  Final (key, perm) land in out_key/out_val.
+static int sort_space(const int64_t* a, const int64_t* b, int stride, int off, int mult,
+                      int64_t n_rows, const trs_epoch* ep, uint32_t* out_key, uint32_t* out_val,
+                      uint32_t* tmp_key, uint32_t* tmp_val, uint32_t* hist, cudaStream_t st) {
+    const int64_t steps = n_steps_of(ep);
+    const int tiles = (int)(((int64_t)mult * ep->batch + SORT_TILE - 1) / SORT_TILE);
+    const int npass = (bits_for(n_rows) + 7) / 8;
+    dim3 grid(tiles, (unsigned)steps);
+    for (int p = 0; p < npass; ++p) {
+        const bool to_out = ((npass - 1 - p) % 2) == 0;
+        uint32_t* dk = to_out ? out_key : tmp_key;
+        uint32_t* dv = to_out ? out_val : tmp_val;
+        SortSrc src = {a, b, stride, off, to_out ? tmp_key : out_key, to_out ? tmp_val : out_val};
+        if (p == 0) {
+            sort_hist_kernel<true><<<grid, SORT_THREADS, 0, st>>>(src, hist, tiles, ep->n_samples, ep->batch, mult, 0);
+            sort_scatter_kernel<true><<<grid, SORT_THREADS, 0, st>>>(src, dk, dv, hist, tiles, ep->n_samples, ep->batch, mult, 0);
+        } else {
+            sort_hist_kernel<false><<<grid, SORT_THREADS, 0, st>>>(src, hist, tiles, ep->n_samples, ep->batch, mult, 8 * p);
+            sort_scatter_kernel<false><<<grid, SORT_THREADS, 0, st>>>(src, dk, dv, hist, tiles, ep->n_samples, ep->batch, mult, 8 * p);
+        }
+    }
+    TRS_CUDA(cudaGetLastError());
+    return TRS_OK;
+}
+
+PlanLayout plan_layout(int64_t n_samples, int n_meta) {
+    PlanLayout L;
+    size_t off = 0;
+    auto take = [&](size_t n_elems) {
+        size_t o = off;
+        off += (n_elems * sizeof(uint32_t) + 255) / 256 * 256;
+        return o;
+    };
+    L.user_key = take(n_samples);
+    L.user_perm = take(n_samples);
+    L.item_key = take(2 * n_samples);
+    L.item_perm = take(2 * n_samples);
+    for (int f = 0; f < TRS_MAX_META; ++f) {
+        L.meta_key[f] = f < n_meta ? take(2 * n_samples) : 0;
+        L.meta_perm[f] = f < n_meta ? take(2 * n_samples) : 0;
+    }
+    L.total = off;
+    return L;
+}
+
+static size_t hist_bytes(const trs_epoch* ep) {
+    const int tiles = (int)((2ll * ep->batch + SORT_TILE - 1) / SORT_TILE);
+    return (size_t)n_steps_of(ep) * 256 * tiles * sizeof(uint32_t);
+}
+
+}  // namespace trs
+
+using namespace trs;
+
+extern "C" size_t trs_plan_bytes(const trs_model* model, const trs_epoch* epoch) {
+    if (!model || !epoch) return 0;
+    return plan_layout(epoch->n_samples, model->n_meta).total;
+}
+
+extern "C" size_t trs_plan_tmp_bytes(const trs_model* model, const trs_epoch* epoch) {
+    if (!model || !epoch || epoch->batch <= 0) return 0;
+    // one (key, perm) pair buffer of the widest id space + the per-tile digit histograms
+    return ((size_t)4 * epoch->n_samples * sizeof(uint32_t) + 511) / 256 * 256 + hist_bytes(epoch);
+}
+
+extern "C" int trs_plan_build(const trs_model* model, const trs_epoch* ep, void* plan,
+                              size_t plan_bytes, void* tmp, size_t tmp_bytes, trs_stream_t stream) {
+    RowShape shape;
+    int rc = check_model(model, &shape);
+    if (rc) return rc;
+    TRS_REQUIRE(ep && ep->user && ep->pos && ep->neg, "epoch ids are NULL");
+    TRS_REQUIRE(ep->batch > 0 && ep->batch <= (1 << 30), "batch out of range");
+    TRS_REQUIRE(model->n_meta == 0 || (ep->pos_meta && ep->neg_meta), "metadata ids are NULL");
+    TRS_REQUIRE(plan && tmp, "plan/tmp is NULL");
+    TRS_REQUIRE(model->user.n_rows > 0 && model->user.n_rows <= 0xFFFFFFFFll &&
+                model->item.n_rows > 0 && model->item.n_rows <= 0xFFFFFFFFll, "n_rows out of range");
+    if (ep->n_samples == 0) return TRS_OK;
+    const PlanLayout L = plan_layout(ep->n_samples, model->n_meta);
+    if (plan_bytes < L.total || tmp_bytes < trs_plan_tmp_bytes(model, ep)) {
+        set_error("plan workspace too small: plan %zu < %zu or tmp %zu < %zu", plan_bytes, L.total,
+                  tmp_bytes, trs_plan_tmp_bytes(model, ep));
+        return TRS_ERR_WORKSPACE;
+    }
+    char* P = (char*)plan;
+    uint32_t* tmp_key = (uint32_t*)tmp;
+    uint32_t* tmp_val = tmp_key + 2 * ep->n_samples;
+    uint32_t* hist = (uint32_t*)((char*)tmp + ((size_t)4 * ep->n_samples * sizeof(uint32_t) + 511) / 256 * 256);
+    rc = sort_space(ep->user, ep->user, 1, 0, 1, model->user.n_rows, ep, (uint32_t*)(P + L.user_key),
+                    (uint32_t*)(P + L.user_perm), tmp_key, tmp_val, hist, stream);
+    if (rc) return rc;
+    rc = sort_space(ep->pos, ep->neg, 1, 0, 2, model->item.n_rows, ep, (uint32_t*)(P + L.item_key),
+                    (uint32_t*)(P + L.item_perm), tmp_key, tmp_val, hist, stream);
+    if (rc) return rc;
+    for (int f = 0; f < model->n_meta; ++f) {
+        TRS_REQUIRE(model->meta[f].n_rows > 0 && model->meta[f].n_rows <= 0xFFFFFFFFll, "meta n_rows out of range");
+        rc = sort_space(ep->pos_meta, ep->neg_meta, model->n_meta, f, 2, model->meta[f].n_rows, ep,
+                        (uint32_t*)(P + L.meta_key[f]), (uint32_t*)(P + L.meta_perm[f]), tmp_key,
+                        tmp_val, hist, stream);
+        if (rc) return rc;
+    }
+    return TRS_OK;
+}

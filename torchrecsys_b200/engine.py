@@ -1,0 +1,151 @@
+"""Host driver of the fused training path: binds a torch optimizer to the row-wise CUDA update and
+runs whole epochs through libtrs_b200 without a per-step host sync.
+
+Replaces, per step, the reference's ``forward x2 -> hinge_loss -> zero_grad -> backward ->
+optimizer.step() -> loss.item()`` (model.py:274-284, 188-200)."""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib
+
+
+@dataclass
+class OptBinding:
+    kind: int                 # _lib.OPT_*
+    keys: tuple               # names of (s0, s1) in optimizer.state[p]
+    lr: float
+    beta1: float = 0.0
+    beta2: float = 0.0
+    eps: float = 0.0
+    lr_decay: float = 0.0
+    step0: int = 0            # steps already taken (per-parameter `step`, identical for all tables)
+
+
+def _same_hparams(groups: List[dict], names) -> dict:
+    first = {n: groups[0].get(n) for n in names}
+    for g in groups[1:]:
+        if any(g.get(n) != first[n] for n in names):
+            raise NotImplementedError(
+                "the fused path needs identical hyper-parameters in every param group; got differing "
+                + ", ".join(names))
+    return first
+
+
+def _get_step(state: dict) -> int:
+    s = state.get("step", 0)
+    return int(s.item()) if torch.is_tensor(s) else int(s)
+
+
+def bind_optimizer(optimizer: torch.optim.Optimizer, params: List[torch.nn.Parameter]) -> OptBinding:
+    """Recognise the optimizer and make sure ``optimizer.state[p]`` holds torch-compatible state
+    tensors for every sparse table (created lazily exactly as torch's own ``step()`` would)."""
+    groups = optimizer.param_groups
+    name = type(optimizer).__name__
+    if name in ("SparseAdam", "Adam"):
+        hp = _same_hparams(groups, ("lr", "betas", "eps", "maximize", "weight_decay", "amsgrad"))
+        if hp.get("weight_decay") or hp.get("amsgrad") or hp.get("maximize"):
+            raise NotImplementedError(f"{name}: weight_decay / amsgrad / maximize are not supported on sparse tables")
+        for p in params:
+            st = optimizer.state[p]
+            if "exp_avg" not in st:
+                st["step"] = 0 if name == "SparseAdam" else torch.tensor(0.0)
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        b = OptBinding(_lib.OPT_SPARSE_ADAM, ("exp_avg", "exp_avg_sq"), float(hp["lr"]),
+                       float(hp["betas"][0]), float(hp["betas"][1]), float(hp["eps"]))
+    elif name == "Adagrad":
+        hp = _same_hparams(groups, ("lr", "lr_decay", "eps", "weight_decay", "maximize"))
+        if hp.get("weight_decay") or hp.get("maximize"):
+            raise NotImplementedError("Adagrad: weight_decay is not compatible with sparse gradients (as in torch)")
+        for p in params:
+            st = optimizer.state[p]
+            if "sum" not in st:  # torch creates it in __init__, keep for safety
+                st["step"] = torch.tensor(0.0)
+                st["sum"] = torch.full_like(p, groups[0].get("initial_accumulator_value", 0.0))
+        b = OptBinding(_lib.OPT_ADAGRAD, ("sum", None), float(hp["lr"]), eps=float(hp["eps"]),
+                       lr_decay=float(hp["lr_decay"]))
+    elif name == "SGD":
+        hp = _same_hparams(groups, ("lr", "momentum", "weight_decay", "nesterov", "maximize", "dampening"))
+        if hp.get("momentum") or hp.get("weight_decay") or hp.get("nesterov") or hp.get("maximize"):
+            raise NotImplementedError("SGD: momentum / weight_decay / nesterov are not row-sparse; "
+                                      "only plain SGD takes the fused path")
+        b = OptBinding(_lib.OPT_SGD, (None, None), float(hp["lr"]))
+    else:
+        raise NotImplementedError(
+            f"optimizer {name} has no fused row-wise update; use SparseAdam, Adagrad, SGD (or Adam, "
+            "which is applied row-wise to the sparse tables)")
+    for p in params:
+        if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+            raise RuntimeError("parameters must be contiguous fp32 CUDA tensors")
+        for k in b.keys:
+            if k is not None and optimizer.state[p][k].device != p.device:
+                optimizer.state[p][k] = optimizer.state[p][k].to(p.device)
+    steps = {_get_step(optimizer.state[p]) for p in params} if b.kind != _lib.OPT_SGD else {0}
+    b.step0 = max(steps)
+    return b
+
+
+def step_scales(b: OptBinding, n_steps: int) -> List[float]:
+    """The per-step scalar of trs_optim.step_scale, in python doubles as torch computes it."""
+    out = []
+    for i in range(n_steps):
+        t = b.step0 + i + 1
+        if b.kind == _lib.OPT_SPARSE_ADAM:
+            out.append(b.lr * math.sqrt(1 - b.beta2 ** t) / (1 - b.beta1 ** t))
+        elif b.kind == _lib.OPT_ADAGRAD:
+            out.append(b.lr / (1 + (t - 1) * b.lr_decay))
+        else:
+            out.append(b.lr)
+    return out
+
+
+def advance_steps(optimizer, params, b: OptBinding, n_steps: int) -> None:
+    if b.kind == _lib.OPT_SGD:
+        return
+    for p in params:
+        st = optimizer.state[p]
+        if torch.is_tensor(st["step"]):
+            st["step"] += n_steps
+        else:
+            st["step"] = st["step"] + n_steps
+    b.step0 += n_steps
+
+
+class EpochRunner:
+    """Runs the steps of one epoch's (already ordered) samples through the fused kernel."""
+
+    def __init__(self, net, optimizer):
+        self.net = net
+        self.optimizer = optimizer
+        self.params = [p for p in net.parameters()]
+        self.binding = bind_optimizer(optimizer, self.params)
+        self.launches = 0  # CUDA kernels launched by this runner (bench.py reports it)
+
+    def run(self, samples: Dict[str, torch.Tensor], batch_size: int) -> torch.Tensor:
+        """samples: device tensors user/pos/neg[/pos_meta/neg_meta] of one epoch.  Returns the
+        per-step batch-mean hinge losses (device, [n_steps]); nothing here syncs with the host."""
+        b = self.binding
+        dev = samples["user"].device
+        model = self.net.abi_model(self.optimizer.state, b.keys)
+        epoch = _lib.make_epoch(samples["user"], samples["pos"], samples["neg"],
+                                samples.get("pos_meta"), samples.get("neg_meta"), batch_size)
+        n = samples["user"].shape[0]
+        n_steps = -(-n // batch_size)
+        scales = torch.tensor(step_scales(b, n_steps), dtype=torch.float64).to(torch.float32)
+        scales = scales.to(dev, non_blocking=True)
+        optim = _lib.Optim(b.kind, 0, b.beta1, b.beta2, b.eps, scales.data_ptr())
+        plan = _lib.plan_build(model, epoch, dev)
+        ws = _lib.train_workspace(model, epoch, dev)
+        loss = torch.empty(n_steps, dtype=torch.float32, device=dev)
+        _lib.train_steps(model, epoch, optim, plan, ws, 0, n_steps, loss)
+        n_meta = model.n_meta
+        passes = lambda rows: max(1, -(-max(1, (rows - 1).bit_length()) // 8))
+        self.launches += 1 + 2 * (passes(model.user.n_rows) + passes(model.item.n_rows)
+                                  + sum(passes(model.meta[f].n_rows) for f in range(n_meta)))
+        advance_steps(self.optimizer, self.params, b, n_steps)
+        return loss

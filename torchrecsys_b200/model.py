@@ -1,0 +1,233 @@
+"""``TorchRecSys`` -- the reference's orchestrator API (model.py:18-452) on the B200 hot path.
+
+Same constructor, ``fit`` / ``evaluate`` / ``predict`` / ``forward`` / ``backward`` signatures,
+prints and ``parameters()`` / ``state_dict()`` surface.  What changes underneath:
+
+* ``fit`` keeps the training split on the device, shuffles there, draws dynamic negatives with the
+  Philox kernel and runs each epoch as ONE persistent fused kernel (engine.py); the only host
+  sync is the end-of-epoch loss read-back for the reference's progress line.
+* ``evaluate`` runs the fused scorer+hinge+pairwise-AUC kernel; ``predict`` scores one user
+  against all items on the device.
+* there is no CPU path: ``use_cuda=False`` still builds the host objects (data processing,
+  parameters) but every compute entry point raises.
+
+Supersets of the reference: ``hidden_layers`` / ``use_batch_norm`` reach the MLP,
+``seed`` fixes the Philox key, ``Adam`` is accepted and applied row-wise (D2)."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import pandas as pd
+import torch
+import torch.profiler
+
+from . import _lib
+from .collaborative.fm import FM
+from .collaborative.linear import Linear
+from .collaborative.mlp import MLP
+from .dataset.dataset import FastDataLoader, ProcessData
+from .engine import EpochRunner
+from .evaluate.metrics import Metrics
+from .helper.cuda import gpu
+from .helper.loss import hinge_loss
+
+_NO_CPU = ("torchrecsys_b200 has no CPU fallback: construct TorchRecSys(..., use_cuda=True) on a "
+           "machine with a CUDA device (the reference's use_cuda=False path is the CPU oracle)")
+
+
+class TorchRecSys(torch.nn.Module):
+    def __init__(self, dataset: pd.DataFrame, user_id_col: str, item_id_col: str,
+                 n_factors: int = 80, net_type: str = "linear",
+                 metadata_id_col: Optional[List[str]] = None, split_ratio: float = 0.8,
+                 dynamic_neg_sampling: bool = False, use_amp: bool = False, use_cuda: bool = False,
+                 debug: bool = False, path: str = "./",
+                 hidden_layers: Optional[List[int]] = None, use_batch_norm: bool = True,
+                 seed: int = 1234):
+        super().__init__()
+        self.path, self.debug = path, debug
+        self.dynamic_neg_sampling = dynamic_neg_sampling
+        self.use_amp, self.use_cuda = use_amp, use_cuda
+        self.grad_scaler = None  # bf16 tensor-core path needs no loss scaling
+        self.seed = int(seed)
+        self._epochs_seen = 0
+
+        self.data_processor = ProcessData(dataset=dataset, user_id_col=user_id_col,
+                                          item_id_col=item_id_col, metadata_id_col=metadata_id_col,
+                                          split_ratio=split_ratio,
+                                          dynamic_neg_sampling=dynamic_neg_sampling)
+        self.data_processor.prepare_data()
+        self.config = self.data_processor.config
+        self.n_users = self.config.get("num_users")
+        self.n_items = self.config.get("num_items")
+        self.metadata_size = self.config.get("num_metadata")
+        self.metadata_name = metadata_id_col if hasattr(self.data_processor, "metadata_id_col") else None
+        self.n_factors, self.net_type = n_factors, net_type
+        self.use_metadata = bool(self.metadata_name)
+        self.hidden_layers, self.use_batch_norm = hidden_layers, use_batch_norm
+        self._dev_cache = {}
+        self._init_net(net_type)
+        if use_cuda:
+            self._validate_ids()
+
+    # ------------------------------------------------------------------------------------
+    def _init_net(self, net_type: str = "linear") -> None:
+        assert net_type in ("linear", "mlp", "neucf", "fm", "lstm"), \
+            'Net type must be one of "linear", "mlp", "neu", "ease" or "lstm"'
+        common = dict(n_users=self.n_users, n_items=self.n_items, n_metadata=self.metadata_size,
+                      n_factors=self.n_factors, use_metadata=self.use_metadata, use_cuda=self.use_cuda)
+        if net_type == "linear":
+            print("Linear Collaborative Filtering")
+            self.net = Linear(**common)
+        elif net_type == "mlp":
+            print("Multi Layer Perceptron")
+            self.net = MLP(hidden_layers=self.hidden_layers, use_batch_norm=self.use_batch_norm, **common)
+        elif net_type == "fm":
+            print("Factorization Machine")
+            self.net = FM(**common)
+        else:
+            raise NotImplementedError(f"{net_type} is not implemented (nor is it in the reference)")
+        self.net = gpu(self.net, self.use_cuda)
+
+    def _require_cuda(self) -> torch.device:
+        if not self.use_cuda or not torch.cuda.is_available():
+            raise RuntimeError(_NO_CPU)
+        return next(self.net.parameters()).device
+
+    def _device_split(self, which: str) -> dict:
+        """The train / test split as device tensors with the kernels' key names (cached)."""
+        if which not in self._dev_cache:
+            dev = self._require_cuda()
+            src = getattr(self.data_processor, which)
+            names = {"user_id": "user", "pos_item_id": "pos", "neg_item_id": "neg",
+                     "pos_metadata_id": "pos_meta", "neg_metadata_id": "neg_meta"}
+            self._dev_cache[which] = {names[k]: v.to(dev).contiguous() for k, v in src.items() if k in names}
+            if self.data_processor.item_meta is not None and "item_meta" not in self._dev_cache:
+                self._dev_cache["item_meta"] = torch.from_numpy(self.data_processor.item_meta).to(dev)
+        return self._dev_cache[which]
+
+    def _validate_ids(self) -> None:
+        """ids must be dense 0-based; the reference dies with IndexError inside
+        aten::embedding, here one kernel checks every split once, up front."""
+        dev = self._require_cuda()
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        for which in ("train_data", "test_data"):
+            d = self._device_split(which)
+            if not d or d["user"].numel() == 0:
+                continue
+            _lib.count_bad_ids(d["user"], self.n_users, bad)
+            _lib.count_bad_ids(d["pos"], self.n_items, bad)
+            if "neg" in d:
+                _lib.count_bad_ids(d["neg"], self.n_items, bad)
+            if "pos_meta" in d:
+                for f, size in enumerate(self.metadata_size.values()):
+                    _lib.count_bad_ids(d["pos_meta"][:, f].contiguous(), size, bad)
+        if int(bad.item()):
+            raise IndexError(f"{int(bad.item())} user/item/metadata ids fall outside [0, n): ids must "
+                             "be dense 0-based integers, as the reference requires")
+
+    def _with_negatives(self, d: dict, first_index: int) -> dict:
+        """Dynamic negatives (dataset.py:435-447) drawn on the device: Philox counter = position
+        in the stream of samples this model has consumed."""
+        if not self.dynamic_neg_sampling:
+            return d
+        item_meta = self._dev_cache.get("item_meta") if self.use_metadata else None
+        neg, neg_meta = _lib.philox_negatives(self.seed, first_index, d["pos"], self.n_items, item_meta)
+        out = dict(d, neg=neg)
+        if neg_meta is not None:
+            out["neg_meta"] = neg_meta
+        return out
+
+    # ------------------------------------------------------------------------------------
+    def forward(self, net, batch):
+        positive = gpu(net.forward(batch, user_key="user_id", item_key="pos_item_id",
+                                   metadata_key="pos_metadata_id"), self.use_cuda)
+        negative = gpu(net.forward(batch, user_key="user_id", item_key="neg_item_id",
+                                   metadata_key="neg_metadata_id"), self.use_cuda)
+        return positive, negative
+
+    def backward(self, loss_value, optimizer):
+        optimizer.zero_grad()
+        loss_value.backward()
+        optimizer.step()
+        return loss_value.item()
+
+    # ------------------------------------------------------------------------------------
+    def fit(self, optimizer, epochs=10, batch_size=512, profile_epochs: int = 0):
+        dev = self._require_cuda()
+        if self.net_type == "mlp":
+            return self._fit_mlp(optimizer, epochs, batch_size, profile_epochs)
+        base = self._device_split("train_data")
+        n = base["user"].shape[0] if base else 0
+        runner = EpochRunner(self.net, optimizer)
+        self._last_runner = runner
+        # the reference loader shuffles once when constructed and again at every __iter__
+        # (dataset.py:359-373); consuming the CPU generator the same way keeps seeded runs comparable
+        if n:
+            torch.randperm(n)
+        for epoch in range(epochs):
+            self.net = self.net.train()
+
+            def one_epoch():
+                if n == 0:
+                    return 0.0
+                perm = torch.randperm(n).to(dev, non_blocking=True)
+                samples = {k: v[perm] for k, v in base.items()}
+                samples = self._with_negatives(samples, self._epochs_seen * n)
+                losses = runner.run(samples, batch_size)
+                self._epochs_seen += 1
+                return float(losses.mean().item())  # unweighted mean over batches (model.py:287)
+
+            if profile_epochs > 0 and epoch == 0:
+                print(f"\n--- Starting Profiling for Epoch {epoch + 1} ---")
+                acts = [torch.profiler.ProfilerActivity.CPU, torch.profiler.ProfilerActivity.CUDA]
+                with torch.profiler.profile(activities=acts, record_shapes=True, profile_memory=True,
+                                            with_stack=True) as prof:
+                    avg_loss = one_epoch()
+                print("--- Profiler Results (First Epoch) ---")
+                print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=20))
+            else:
+                avg_loss = one_epoch()
+            print(f"|--- Epoch {epoch + 1}/{epochs} --- Training Loss: {avg_loss:.4f}")
+
+    def _fit_mlp(self, optimizer, epochs, batch_size, profile_epochs):
+        raise NotImplementedError("the MLP tower's tcgen05 path is not wired into fit yet")
+
+    # ------------------------------------------------------------------------------------
+    def evaluate(self, batch_size=512, eval_metrics=["loss", "auc"]):
+        self._require_cuda()
+        self.net = self.net.eval()
+        test = self._device_split("test_data")
+        self.last_eval = {}
+        if not test or test["user"].numel() == 0:
+            print("|--- No test data to evaluate.")
+            return
+        if self.net_type == "mlp":
+            raise NotImplementedError("MLP evaluate is not wired yet")
+        test = self._with_negatives(test, (1 << 40) + self._epochs_seen * test["user"].shape[0])
+        epoch = _lib.make_epoch(test["user"], test["pos"], test["neg"], test.get("pos_meta"),
+                                test.get("neg_meta"), batch_size)
+        loss, auc, _, _ = _lib.eval_pairwise(self.net.abi_model(), epoch)
+        results = {"loss": loss, "auc": auc}
+        for metric in eval_metrics:
+            if metric in results:
+                value = float(results[metric].mean().item())  # unweighted mean over batches
+            else:
+                value = 0
+            self.last_eval[metric] = value
+            print(f"|--- Testing {metric}: {value:.4f}")
+
+    # ------------------------------------------------------------------------------------
+    def predict(self, user_id: int, top_k: int = 10, prediction_batch_size: int = 4096):
+        """Top-k item ids for one user, best first, as a CPU int64 tensor (model.py:341-452).
+        Ties are broken towards the lower item id (the reference's sort is unstable, D10).
+        ``prediction_batch_size`` is accepted for compatibility; all items are scored in one pass."""
+        dev = self._require_cuda()
+        self.net = self.net.eval()
+        if self.net_type == "mlp":
+            raise NotImplementedError("MLP predict is not wired yet")
+        items = torch.arange(self.n_items, device=dev)
+        users = torch.full_like(items, int(user_id))
+        meta = self._dev_cache.get("item_meta") if self.use_metadata else None
+        scores = _lib.scores(self.net.abi_model(), users, items, meta)
+        order = torch.sort(scores, descending=True, stable=True)[1]
+        return order[:top_k].cpu()
