@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the TorchRecSys hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2_fm|c1_linear|c4_linear]
+
+A "step" is one training step of the named workload: forward x2 + hinge + backward + sparse
+optimizer update over one batch (reference model.py:274-284).  Default workload = BASELINE.json
+configs[1] ("C2"): FM + 1 metadata feature (100 categories), dynamic negatives, 1M users x 200k
+items, dim 64, batch 8192, SparseAdam, synthetic uniform ids.
+
+  value      whole-job samples/s over K steps, every input already resident in HBM, timed with CUDA
+             events; the timed region contains EVERYTHING a step needs: Philox negatives, the sort
+             plan (coalesce's sort), and the persistent fused kernel.
+  e2e        the same K steps with the ids starting in pinned HOST memory (H2D inside the timed
+             region) and the per-step losses read back to the host (D2H inside).
+  roofline   the fused train kernel alone: algorithmic HBM bytes (ids + each unique
+             touched row's param+state read once and written once) / its CUDA-event duration,
+             against the measured HBM peak of MEASURED_PEAKS.json.
+  cpu_baseline  the reference's CPU op stream (oracle/torch_port.py, kind "port": /root/reference
+             is not on the GPU box) on a bounded sample of the same workload on the host cores.
+
+--impl reference runs only that CPU arm and prints it as the main line.
+Multi-GPU (N>1, under torchrun): table rows are sharded by `row mod N`... see DESIGN.md (e);
+each rank trains its own sample shard, weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: net, users, items, dim, n_categories (0 = no metadata), batch, optimizer, dynamic negs
+    "c2_fm": dict(net="fm", n_users=1_000_000, n_items=200_000, dim=64, n_cat=100, batch=8192,
+                  opt="sparse_adam", lr=1e-3, desc="BASELINE configs[1]: FM + product_category(100), "
+                  "dynamic negatives, 1M users x 200k items, dim 64, batch 8192, SparseAdam"),
+    "c1_linear": dict(net="linear", n_users=3000, n_items=1000, dim=80, n_cat=0, batch=1024,
+                      opt="sparse_adam", lr=1e-3, desc="BASELINE configs[0] shape: linear 3k x 1k, dim 80, batch 1024"),
+    "c4_linear": dict(net="linear", n_users=50_000_000, n_items=5_000_000, dim=128, n_cat=0, batch=16384,
+                      opt="sparse_adam", lr=1e-3, desc="BASELINE configs[3]: linear 50M x 5M, dim 128, batch 16384/GPU"),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2_fm", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the workload's batch size")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data: uniform ids, rng seed 1234, category(item) = item mod n_cat
+# ------------------------------------------------------------------------------------------------
+def synth_ids(wl, n, seed=1234):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    user = rng.integers(0, wl["n_users"], n, dtype=np.int64)
+    pos = rng.integers(0, wl["n_items"], n, dtype=np.int64)
+    return user, pos
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's op stream on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(wl, steps, warmup, budget_s):
+    """Times oracle/torch_port.py (same ATen CPU ops as the reference's use_cuda=False path) on a
+    bounded sample: `steps` steps of the workload's batch size, thread count swept, best kept."""
+    import numpy as np
+    import torch
+    from oracle import cf_oracle as O
+    from oracle import torch_port as TP
+    B = wl["batch"]
+    n = (steps + warmup) * B
+    user, pos = synth_ids(wl, n)
+    neg = O.philox_negatives(1234, 0, pos, wl["n_items"])
+    batch_of = lambda s: {"user": torch.from_numpy(user[s * B:(s + 1) * B]),
+                          "pos": torch.from_numpy(pos[s * B:(s + 1) * B]),
+                          "neg": torch.from_numpy(neg[s * B:(s + 1) * B])}
+    metas = [wl["n_cat"]] if wl["n_cat"] else []
+    ncores = len(os.sched_getaffinity(0))
+    best = None
+    t_start = time.time()
+    threads = sorted({1, 2, 4, 8, 16, 32, ncores} & set(range(1, ncores + 1)))
+    tried = {}
+    for nt in threads:
+        if time.time() - t_start > budget_s:
+            break
+        torch.set_num_threads(nt)
+        torch.manual_seed(1234)
+        net = TP.make_net(wl["net"], wl["n_users"], wl["n_items"], metas, wl["dim"])
+        net.train()
+        opt = TP.make_optimizer(wl["opt"], net, wl["lr"])
+
+        def run(s):
+            b = batch_of(s)
+            if metas:
+                b["pos_meta"] = (b["pos"] % wl["n_cat"]).view(-1, 1)
+                b["neg_meta"] = (b["neg"] % wl["n_cat"]).view(-1, 1)
+            return TP.train_step(net, opt, b)
+
+        for s in range(warmup):
+            run(s)
+        t0 = time.perf_counter()
+        done = 0
+        for s in range(warmup, warmup + steps):
+            run(s)
+            done += 1
+            if time.perf_counter() - t0 > budget_s / max(len(threads), 1) and done >= 2:
+                break
+        dt = time.perf_counter() - t0
+        tried[nt] = done * B / dt
+        if best is None or tried[nt] > best[0]:
+            best = (tried[nt], nt, done, dt)
+        del net, opt
+    value, nt, done, dt = best
+    return {"value": value, "unit": "samples/s", "cores": nt, "kind": "port",
+            "sample": f"{done} steps of batch {B} ({done * B} samples) of the same workload after "
+                      f"{warmup} warm-up steps, torch {torch.__version__} CPU, threads swept "
+                      f"{ {k: round(v) for k, v in tried.items()} } on {ncores} cores, best kept",
+            "ms_per_step": dt / done * 1e3, "steps": done}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region (NVML, ~2 ms period)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(wl, user, pos, neg, n_steps, B, S):
+    """8 B per id consumed + per unique touched row (param + S state tensors) read once
+    and written once, embedding row (dim floats) and its width-1 companion.  From the actual batches."""
+    import torch
+    D, F = wl["dim"], 1 if wl["n_cat"] else 0
+    row_bytes = 4 * (D + 1) * (2 + 2 * S)
+    total = 0
+    for s in range(n_steps):
+        sl = slice(s * B, (s + 1) * B)
+        uu = torch.unique(user[sl]).numel()
+        items = torch.cat([pos[sl], neg[sl]])
+        ui = torch.unique(items).numel()
+        um = torch.unique(items % wl["n_cat"]).numel() if F else 0
+        meta_row = row_bytes if wl["net"] == "fm" else 4 * D * (2 + 2 * S)
+        total += 8 * (3 * B + 2 * B * F) + (uu + ui) * row_bytes + um * meta_row
+    return total
+
+
+def gpu_bench(args, wl):
+    import torch
+    import torch.distributed as dist
+    from torchrecsys_b200 import _lib
+    from torchrecsys_b200.collaborative.fm import FM
+    from torchrecsys_b200.collaborative.linear import Linear
+    from torchrecsys_b200.engine import EpochRunner
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W, B = args.steps, max(args.warmup, 3), args.batch or wl["batch"]
+    F = 1 if wl["n_cat"] else 0
+
+    torch.manual_seed(1234 + rank)
+    cls = FM if wl["net"] == "fm" else Linear
+    net = cls(wl["n_users"], wl["n_items"], {"product_category": wl["n_cat"]} if F else {}, wl["dim"],
+              use_metadata=bool(F), use_cuda=True).to(dev)
+    if wl["opt"] == "sparse_adam":
+        opt = torch.optim.SparseAdam(list(net.parameters()), lr=wl["lr"])
+        S = 2
+    else:
+        opt = torch.optim.Adagrad(net.parameters(), lr=wl["lr"])
+        S = 1
+    runner = EpochRunner(net, opt)
+
+    n = (K + W) * B
+    user_h, pos_h = synth_ids(wl, n, seed=1234 + rank)
+    user_h, pos_h = torch.from_numpy(user_h).pin_memory(), torch.from_numpy(pos_h).pin_memory()
+    user, pos = user_h.to(dev), pos_h.to(dev)
+    item_meta = (torch.arange(wl["n_items"], device=dev) % wl["n_cat"]).view(-1, 1).contiguous() if F else None
+
+    def step_block(u, p, first):
+        """Everything the steps need, device side: negatives -> plan -> fused kernel."""
+        neg, neg_meta = _lib.philox_negatives(1234, first, p, wl["n_items"], item_meta)
+        smp = {"user": u, "pos": p, "neg": neg}
+        if F:
+            smp["pos_meta"] = item_meta[p]  # category of the positive (torch gather: loader-side plumbing)
+            smp["neg_meta"] = neg_meta
+        return runner.run(smp, B)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    sync_all = (lambda: (torch.cuda.synchronize(), dist.barrier(), torch.cuda.synchronize())) if world > 1 \
+        else torch.cuda.synchronize
+
+    # clock ramp (not steps): keep the GPU busy ~0.3 s so the timed region does not start at idle clocks
+    scratch = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    t0 = time.time()
+    while time.time() - t0 < 0.3:
+        scratch.copy_(scratch.flip(0))
+        torch.cuda.synchronize()
+    del scratch
+
+    # W warm-up steps
+    step_block(user[:W * B], pos[:W * B], 0)
+    sync_all()
+
+    # ---- timed: K steps, inputs resident in HBM ----
+    uK, pK = user[W * B:], pos[W * B:]
+    launches0 = runner.launches
+    e0, e1 = ev(), ev()
+    with ClockSampler(local) as clocks:
+        sync_all()
+        e0.record()
+        loss = step_block(uK, pK, W * B)
+        e1.record()
+        sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = runner.launches - launches0 + 1  # + the Philox kernel
+    mean_loss = float(loss.mean().item())
+
+    # ---- the fused kernel alone (roofline): same K steps again on the now-further-trained model ----
+    neg, neg_meta = _lib.philox_negatives(1234, W * B, pK, wl["n_items"], item_meta)
+    smp = {"user": uK, "pos": pK, "neg": neg}
+    if F:
+        smp["pos_meta"], smp["neg_meta"] = item_meta[pK], neg_meta
+    b = runner.binding
+    model = net.abi_model(opt.state, b.keys)
+    epoch = _lib.make_epoch(smp["user"], smp["pos"], smp["neg"], smp.get("pos_meta"), smp.get("neg_meta"), B)
+    from torchrecsys_b200.engine import step_scales, advance_steps
+    scales = torch.tensor(step_scales(b, K), dtype=torch.float64).float().to(dev)
+    optim_c = _lib.Optim(b.kind, 0, b.beta1, b.beta2, b.eps, scales.data_ptr())
+    p0, p1, k0, k1 = ev(), ev(), ev(), ev()
+    torch.cuda.synchronize()
+    p0.record()
+    plan = _lib.plan_build(model, epoch, dev)
+    p1.record()
+    ws = _lib.train_workspace(model, epoch, dev)
+    loss2 = torch.empty(K, device=dev)
+    k0.record()
+    _lib.train_steps(model, epoch, optim_c, plan, ws, 0, K, loss2)
+    k1.record()
+    torch.cuda.synchronize()
+    advance_steps(opt, runner.params, b, K)
+    kernel_ms, plan_ms = k0.elapsed_time(k1), p0.elapsed_time(p1)
+    alg_bytes = algorithmic_bytes(wl, uK, pK, neg, K, B, S)
+
+    # ---- e2e: ids start in pinned host memory, losses end on the host ----
+    x0, x1 = ev(), ev()
+    sync_all()
+    x0.record()
+    u_d = user_h[W * B:].to(dev, non_blocking=True)
+    p_d = pos_h[W * B:].to(dev, non_blocking=True)
+    loss3 = step_block(u_d, p_d, (W + K) * B)
+    loss_host = loss3.to("cpu", non_blocking=True)
+    x1.record()
+    sync_all()
+    e2e_ms = x0.elapsed_time(x1)
+    assert loss_host.numel() == K
+
+    times = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, kernel_ms = (float(x) for x in times.cpu())
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+    out = {
+        "metric": "train samples/sec (fwd+bwd+sparse update)", "value": world * K * B / (ms * 1e-3),
+        "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": wl["desc"], "name": args.workload, "batch_per_gpu": B, "global_batch": B * world,
+                   "optimizer": wl["opt"], "l2": "inputs larger than L2: tables+optimizer state "
+                   f"{(wl['n_users'] + wl['n_items']) * (wl['dim'] + 1) * 4 * (1 + S) / 1e9:.2f} GB, rows hit at random",
+                   "timed_region": "Philox negatives + sort plan + persistent fused train kernel, K steps in one launch",
+                   "parallelism": f"dp{world} (independent replicas)" if world > 1 else "single GPU",
+                   "clock_ramp": "0.3 s of device copies before the warm-up steps", "mean_loss": mean_loss},
+        "e2e": {"value": world * K * B / (e2e_ms * 1e-3), "unit": "samples/s",
+                "h2d_bytes_per_step": 16 * B, "d2h_bytes_per_step": 4,
+                "note": "user+positive ids from pinned host memory; metadata ids and negatives are derived on the device"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "trs::train_kernel (one persistent launch, K steps)",
+                     "kernel_ms_per_step": kernel_ms / K, "plan_ms_per_step": plan_ms / K,
+                     "algorithmic_bytes_per_step": alg_bytes / K,
+                     "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650"},
+        "clocks": clocks.summary(),
+    }
+    if world > 1:
+        dist.destroy_process_group()
+    return out, rank
+
+
+def main():
+    args = parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl["batch"] = args.batch
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, args.steps)
+        r = cpu_reference(wl, steps, max(1, min(args.warmup, 3)), budget_s=max(args.cpu_seconds, 20.0) * 3)
+        line = {"impl": "reference", "metric": "train samples/sec (fwd+bwd+sparse update)", "value": r["value"],
+                "unit": "samples/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(1, min(args.warmup, 3)),
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["desc"], "name": args.workload, "batch_per_gpu": wl["batch"]},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+    out, rank = gpu_bench(args, wl)
+    if rank == 0:
+        if args.gpus == 1 and not args.no_cpu_baseline:
+            r = cpu_reference(wl, steps=8, warmup=1, budget_s=args.cpu_seconds)
+            out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

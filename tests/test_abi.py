@@ -36,6 +36,6 @@ def test_struct_sizes_match_header():
 def test_argument_errors_are_reported_not_raised_across_the_abi():
     from torchrecsys_b200 import _lib
     L = _lib.lib()
-    rc = L.trs_scores(None, None, None, None, ctypes.c_int64(0), None, None)
+    rc = L.trs_scores(None, None, None, None, ctypes.c_int64(4), None, None)
     assert rc == -1
     assert b"NULL" in L.trs_last_error()

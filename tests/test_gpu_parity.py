@@ -191,8 +191,18 @@ def test_train_steps_match_reference(dev, name):
         torch.cuda.synchronize()
         np.testing.assert_allclose(loss.cpu().numpy(), g["loss"][:n_steps], rtol=1e-4, atol=1e-5)
         sd = {k: v.cpu().numpy() for k, v in net.state_dict().items()}
+        init = G.section(g, "init")
         for k, v in G.section(g, section).items():
-            np.testing.assert_allclose(sd[k], v, err_msg=f"{k} after {n_steps} steps", **tol)
+            ok = np.ones(v.shape[0], dtype=bool)
+            if n_steps == 1 and opt != "sgd":
+                # Adagrad/Adam first step is lr * g/(|g|+eps): where the true gradient is ~eps (a
+                # saturated sigmoid) its rounding noise decides the step.  Leave those rows out.
+                _, grads = (O.linear_grads if net_type == "linear" else O.fm_grads)(init, G.batch_at(g, 0))
+                rows, gsum = O.coalesce(*grads[k])
+                ok[rows[np.abs(gsum).max(axis=1) < 1e-6]] = False
+                if net_type == "linear" and k == "user_bias.weight":
+                    ok[:] = True
+            np.testing.assert_allclose(sd[k][ok], v[ok], err_msg=f"{k} after {n_steps} steps", **tol)
         if n_steps == steps:
             named = dict(net.named_parameters())
             for k, v in G.section(g, "state").items():
@@ -332,8 +342,8 @@ def test_c2_full_size_invariants(dev):
     want_loss = O.train_step("fm", p0, state, batch, spec, 1)
     np.testing.assert_allclose(float(loss[0]), want_loss, rtol=1e-5)
     got = {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}
-    for k in p0:
-        np.testing.assert_allclose(got[k], p0[k], rtol=1e-5, atol=2e-6, err_msg=k)
+    for k in p0:  # Adagrad's first step is lr*g/(|g|+eps) with lr = 1e-2: a few ulp of g -> ~3e-6
+        np.testing.assert_allclose(got[k], p0[k], rtol=1e-5, atol=1e-5, err_msg=k)
 
 
 def test_fit_evaluate_predict_end_to_end_against_cpu_port(dev):

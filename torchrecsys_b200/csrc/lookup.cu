@@ -222,11 +222,11 @@ extern "C" int trs_embed_gather_sum(const float* table, int dim, const int64_t* 
                                     const float* const* meta_tables_host, const int64_t* meta_idx,
                                     int n_meta, float* out, trs_stream_t stream) {
     RowShape shape;
+    if (n == 0) return TRS_OK;
     TRS_REQUIRE(table && idx && out, "NULL pointer");
     TRS_REQUIRE(n_meta >= 0 && n_meta <= TRS_MAX_META, "n_meta %d out of range", n_meta);
     TRS_REQUIRE(n_meta == 0 || (meta_tables_host && meta_idx), "metadata pointers missing");
     TRS_REQUIRE(pick_row_shape(dim, &shape), "unsupported dim %d", dim);
-    if (n == 0) return TRS_OK;
     MetaPtrs mp = {};
     for (int f = 0; f < n_meta; ++f) mp.t[f] = meta_tables_host[f];
     TRS_DISPATCH_ROW_SHAPE(shape, launch_gather, table, dim, idx, n, mp, meta_idx, n_meta, out, stream);
@@ -239,9 +239,9 @@ extern "C" int trs_scores(const trs_model* model, const int64_t* user, const int
     RowShape shape;
     int rc = check_model(model, &shape);
     if (rc) return rc;
+    if (n == 0) return TRS_OK;
     TRS_REQUIRE(user && item && out, "NULL pointer");
     TRS_REQUIRE(model->n_meta == 0 || meta, "model has metadata tables but meta ids are NULL");
-    if (n == 0) return TRS_OK;
     TRS_DISPATCH_ROW_SHAPE(shape, launch_scores, model, user, item, meta, n, out, stream);
     TRS_CUDA(cudaGetLastError());
     return TRS_OK;
@@ -252,10 +252,11 @@ extern "C" int trs_eval_pairwise(const trs_model* model, const trs_epoch* epoch,
     RowShape shape;
     int rc = check_model(model, &shape);
     if (rc) return rc;
-    TRS_REQUIRE(epoch && epoch->user && epoch->pos && epoch->neg, "epoch ids are NULL");
+    TRS_REQUIRE(epoch, "epoch is NULL");
+    if (epoch->n_samples == 0) return TRS_OK;
+    TRS_REQUIRE(epoch->user && epoch->pos && epoch->neg, "epoch ids are NULL");
     TRS_REQUIRE(epoch->batch > 0, "batch must be positive");
     TRS_REQUIRE(model->n_meta == 0 || (epoch->pos_meta && epoch->neg_meta), "metadata ids are NULL");
-    if (epoch->n_samples == 0) return TRS_OK;
     TRS_DISPATCH_ROW_SHAPE(shape, launch_eval, model, epoch, loss, auc, pos_out, neg_out, stream);
     TRS_CUDA(cudaGetLastError());
     return TRS_OK;
@@ -265,6 +266,7 @@ extern "C" int trs_philox_negatives(uint64_t seed, uint64_t first_index, const i
                                     int64_t n, int64_t n_items, const int64_t* item_meta,
                                     int n_meta, int64_t* neg, int64_t* neg_meta,
                                     trs_stream_t stream) {
+    if (n == 0) return TRS_OK;
     TRS_REQUIRE(pos && neg, "NULL pointer");
     TRS_REQUIRE(n_items >= 2 && n_items <= 0xFFFFFFFFll, "n_items must be in [2, 2^32)");
     TRS_REQUIRE(!neg_meta || (item_meta && n_meta > 0), "neg_meta needs item_meta");
@@ -278,8 +280,8 @@ extern "C" int trs_philox_negatives(uint64_t seed, uint64_t first_index, const i
 
 extern "C" int trs_validate_ids(const int64_t* ids, int64_t n, int64_t n_rows, int32_t* bad_count,
                                 trs_stream_t stream) {
-    TRS_REQUIRE(ids && bad_count, "NULL pointer");
     if (n == 0) return TRS_OK;
+    TRS_REQUIRE(ids && bad_count, "NULL pointer");
     int grid = grid_for(n, 256, device_props().sm_count * 8);
     validate_ids_kernel<<<grid, 256, 0, stream>>>(ids, n, n_rows, bad_count);
     TRS_CUDA(cudaGetLastError());
