@@ -186,9 +186,12 @@ def main():
     for net_type in ("linear", "fm"):
         for F in (0, 1):
             for opt in ("sgd", "adagrad", "sparse_adam"):
-                jobs.append((f"train_{net_type}_F{F}_{opt}", (net_type, F, opt, 0.5 if net_type == "linear" else 0.3)))
-    jobs.append(("train_fm_F2_sparse_adam", ("fm", 2, "sparse_adam", 0.3)))
+                jobs.append((f"train_{net_type}_F{F}_{opt}", (net_type, F, opt, 0.5 if net_type == "linear" else 0.15)))
+    jobs.append(("train_fm_F2_sparse_adam", ("fm", 2, "sparse_adam", 0.15)))
     jobs.append(("train_linear_F0_sparse_adam_refinit", ("linear", 0, "sparse_adam", None)))
+    # FM scale 0.15: with 0.3 the D=16 pairwise term saturates the sigmoid for some samples, their
+    # gradient drops to ~1e-10 and Adagrad/Adam's g/(|g|+eps) turns rounding noise into +-lr steps --
+    # a fixture no two implementations (nor the reference at two thread counts) agree on.
     for i, (name, (nt, F, opt, sc)) in enumerate(jobs):
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **train_fixture(nt, F, opt, sc, 100 + i))
         print("wrote", name)

