@@ -148,6 +148,35 @@ int trs_train_steps(const trs_model* model, const trs_epoch* epoch, const trs_op
 int trs_eval_pairwise(const trs_model* model, const trs_epoch* epoch, float* loss, float* auc,
                       float* pos_out, float* neg_out, trs_stream_t stream);
 
+/* ---- a4 (K7): dense layers of the MLP tower (collaborative/mlp.py:74-85, 107-113) ------------ */
+/* out[m, n] = sum_k a[m, k] * b[n, k] (+ bias[n]) on the tcgen05 tensor cores: bf16 operands, both
+ * contiguous along k, fp32 accumulation in TMEM.  nn.Linear forward is (a = activations, b = weight);
+ * dgrad and wgrad reach the same form through transposed operand copies.
+ *  - out is fp32 or bf16 (out_bf16), row-major with leading dimension ldc.
+ *  - splits > 1 cuts k into `splits` ranges; split z writes its raw fp32 partial at out + z*split_stride.
+ *  - col_sum / col_sumsq (nullable, [ceil(m/128), n]): per 128-row tile, the column sums of the stored
+ *    output and of its squares over the valid rows, for BatchNorm1d batch statistics (mlp.py:82, 109).
+ *    A row is valid iff (row % rows_per_half) < rows_valid (the positive and the negative pass of a
+ *    step are stacked, each padded to rows_per_half rows); rows_per_half == 0: every row is valid.
+ *  k, n and ldc must be multiples of 8; a and b 16-byte aligned. */
+typedef struct {
+    const void* a; /* bf16 [m, k], leading dimension lda */
+    const void* b; /* bf16 [n, k], leading dimension ldb */
+    int64_t lda, ldb;
+    int64_t m, n, k;
+    void* out;
+    int64_t ldc;
+    int64_t split_stride;
+    int32_t out_bf16;
+    int32_t splits;
+    const float* bias;
+    float* col_sum;
+    float* col_sumsq;
+    int64_t rows_per_half;
+    int64_t rows_valid;
+} trs_gemm_args;
+int trs_gemm_bf16_tn(const trs_gemm_args* args, trs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

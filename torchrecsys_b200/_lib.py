@@ -22,6 +22,7 @@ SYMBOLS = [
     "trs_abi_version", "trs_last_error", "trs_device_info", "trs_embed_gather_sum", "trs_scores",
     "trs_philox_negatives", "trs_validate_ids", "trs_plan_bytes", "trs_plan_tmp_bytes",
     "trs_plan_build", "trs_train_workspace_bytes", "trs_train_steps", "trs_eval_pairwise",
+    "trs_gemm_bf16_tn",
 ]
 
 
@@ -45,6 +46,14 @@ class Epoch(C.Structure):
 class Optim(C.Structure):
     _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("beta1", C.c_double),
                 ("beta2", C.c_double), ("eps", C.c_double), ("step_scale", C.c_void_p)]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("lda", C.c_int64), ("ldb", C.c_int64),
+                ("m", C.c_int64), ("n", C.c_int64), ("k", C.c_int64), ("out", C.c_void_p),
+                ("ldc", C.c_int64), ("split_stride", C.c_int64), ("out_bf16", C.c_int32),
+                ("splits", C.c_int32), ("bias", C.c_void_p), ("col_sum", C.c_void_p),
+                ("col_sumsq", C.c_void_p), ("rows_per_half", C.c_int64), ("rows_valid", C.c_int64)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -190,3 +199,25 @@ def eval_pairwise(model: Model, epoch: Epoch, want_scores: bool = False):
                                    C.c_void_p(_ptr(auc)), C.c_void_p(_ptr(pos)), C.c_void_p(_ptr(neg)),
                                    _stream()))
     return loss, auc, pos, neg
+
+
+def gemm_bf16_tn(a, b, out, bias=None, splits: int = 1, col_sum=None, col_sumsq=None,
+                 rows_per_half: int = 0, rows_valid: int = 0) -> None:
+    """out[m, n] = sum_k a[m, k] * b[n, k] (+ bias[n]); a, b bf16 row-major (last dim contiguous);
+    out fp32 or bf16 ([m, n], or [splits, m, n] fp32 partials when splits > 1)."""
+    bf = torch.bfloat16
+    for t in (a, b):
+        if t.dtype != bf or t.dim() != 2 or t.stride(1) != 1 or not t.is_cuda:
+            raise RuntimeError("gemm_bf16_tn takes 2-D bf16 CUDA operands contiguous along k")
+    m, k = a.shape
+    n = b.shape[0]
+    if b.shape[1] != k:
+        raise RuntimeError("gemm_bf16_tn: k mismatch")
+    o2 = out if splits == 1 else out[0]
+    if tuple(o2.shape) != (m, n) or o2.stride(1) != 1 or out.dtype not in (bf, torch.float32):
+        raise RuntimeError("gemm_bf16_tn: bad output")
+    args = GemmArgs(a.data_ptr(), b.data_ptr(), a.stride(0), b.stride(0), m, n, k, out.data_ptr(),
+                    o2.stride(0), out.stride(0) if splits > 1 else 0, int(out.dtype == bf), splits,
+                    _ptr(bias, torch.float32), _ptr(col_sum, torch.float32), _ptr(col_sumsq, torch.float32),
+                    rows_per_half, rows_valid)
+    _check(lib().trs_gemm_bf16_tn(C.byref(args), _stream()))
