@@ -158,6 +158,9 @@ int trs_eval_pairwise(const trs_model* model, const trs_epoch* epoch, float* los
  *    output and of its squares over the valid rows, for BatchNorm1d batch statistics (mlp.py:82, 109).
  *    A row is valid iff (row % rows_per_half) < rows_valid (the positive and the negative pass of a
  *    step are stacked, each padded to rows_per_half rows); rows_per_half == 0: every row is valid.
+ *  - a_mn / b_mn: the operand is given transposed in memory ([k, m] / [k, n]); the tensor cores read it
+ *    "MN-major", so dgrad (b = W as stored) and wgrad (a = dZ, b = activations, both as stored) need no
+ *    transposed copies.  Supported: (0,0), (0,1), (1,1); a_mn writes fp32 only.
  *  k, n and ldc must be multiples of 8; a and b 16-byte aligned. */
 typedef struct {
     const void* a; /* bf16 [m, k], leading dimension lda */
@@ -169,6 +172,8 @@ typedef struct {
     int64_t split_stride;
     int32_t out_bf16;
     int32_t splits;
+    int32_t a_mn; /* a is stored [k, m] (m contiguous, leading dimension lda) instead of [m, k] */
+    int32_t b_mn; /* b is stored [k, n] */
     const float* bias;
     float* col_sum;
     float* col_sumsq;

@@ -83,3 +83,22 @@ def test_gemm_strided_operands_and_column_statistics(dev):
     got_sq = css.view(2, Bpad // 128, n).sum(1)
     torch.testing.assert_close(got_sum, z.sum(1), rtol=1e-4, atol=1e-2)
     torch.testing.assert_close(got_sq, (z * z).sum(1), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("m,n,k,a_mn,b_mn", [
+    (256, 128, 128, False, True), (1000, 136, 200, False, True), (4096, 128, 512, False, True),
+    (4096, 32, 64, False, True), (128, 128, 128, True, True), (512, 128, 4096, True, True),
+    (256, 136, 1000, True, True), (32, 16, 640, True, True), (512, 512, 2048, True, True)])
+def test_gemm_mn_major_operands(dev, m, n, k, a_mn, b_mn):
+    """dgrad / wgrad operand layouts: the operand is handed over as stored ([k, m] / [k, n])."""
+    g = torch.Generator(device="cpu").manual_seed(m + n + k)
+    a = torch.randint(-4, 5, (m, k), generator=g).float()
+    b = torch.randint(-4, 5, (n, k), generator=g).float()
+    want = a @ b.t()
+    ad = (a.t().contiguous() if a_mn else a).to(dev).bfloat16()
+    bd = (b.t().contiguous() if b_mn else b).to(dev).bfloat16()
+    splits = 4 if k >= 1000 else 1
+    out = torch.empty((splits, m, n) if splits > 1 else (m, n), dtype=torch.float32, device=dev)
+    _L().gemm_bf16_tn(ad, bd, out, splits=splits, a_mn=a_mn, b_mn=b_mn)
+    got = out.sum(0) if splits > 1 else out
+    assert torch.equal(got.cpu(), want)

@@ -52,7 +52,7 @@ class GemmArgs(C.Structure):
     _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("lda", C.c_int64), ("ldb", C.c_int64),
                 ("m", C.c_int64), ("n", C.c_int64), ("k", C.c_int64), ("out", C.c_void_p),
                 ("ldc", C.c_int64), ("split_stride", C.c_int64), ("out_bf16", C.c_int32),
-                ("splits", C.c_int32), ("bias", C.c_void_p), ("col_sum", C.c_void_p),
+                ("splits", C.c_int32), ("a_mn", C.c_int32), ("b_mn", C.c_int32), ("bias", C.c_void_p), ("col_sum", C.c_void_p),
                 ("col_sumsq", C.c_void_p), ("rows_per_half", C.c_int64), ("rows_valid", C.c_int64)]
 
 
@@ -202,22 +202,23 @@ def eval_pairwise(model: Model, epoch: Epoch, want_scores: bool = False):
 
 
 def gemm_bf16_tn(a, b, out, bias=None, splits: int = 1, col_sum=None, col_sumsq=None,
-                 rows_per_half: int = 0, rows_valid: int = 0) -> None:
+                 rows_per_half: int = 0, rows_valid: int = 0, a_mn: bool = False, b_mn: bool = False) -> None:
     """out[m, n] = sum_k a[m, k] * b[n, k] (+ bias[n]); a, b bf16 row-major (last dim contiguous);
+    with a_mn / b_mn the operand is passed as stored [k, m] / [k, n].
     out fp32 or bf16 ([m, n], or [splits, m, n] fp32 partials when splits > 1)."""
     bf = torch.bfloat16
     for t in (a, b):
         if t.dtype != bf or t.dim() != 2 or t.stride(1) != 1 or not t.is_cuda:
-            raise RuntimeError("gemm_bf16_tn takes 2-D bf16 CUDA operands contiguous along k")
-    m, k = a.shape
-    n = b.shape[0]
-    if b.shape[1] != k:
+            raise RuntimeError("gemm_bf16_tn takes 2-D bf16 CUDA operands with a contiguous last dimension")
+    k, m = a.shape if a_mn else a.shape[::-1]
+    kb, n = b.shape if b_mn else b.shape[::-1]
+    if kb != k:
         raise RuntimeError("gemm_bf16_tn: k mismatch")
     o2 = out if splits == 1 else out[0]
     if tuple(o2.shape) != (m, n) or o2.stride(1) != 1 or out.dtype not in (bf, torch.float32):
         raise RuntimeError("gemm_bf16_tn: bad output")
     args = GemmArgs(a.data_ptr(), b.data_ptr(), a.stride(0), b.stride(0), m, n, k, out.data_ptr(),
                     o2.stride(0), out.stride(0) if splits > 1 else 0, int(out.dtype == bf), splits,
-                    _ptr(bias, torch.float32), _ptr(col_sum, torch.float32), _ptr(col_sumsq, torch.float32),
+                    int(a_mn), int(b_mn), _ptr(bias, torch.float32), _ptr(col_sum, torch.float32), _ptr(col_sumsq, torch.float32),
                     rows_per_half, rows_valid)
     _check(lib().trs_gemm_bf16_tn(C.byref(args), _stream()))

@@ -57,7 +57,11 @@ __device__ __forceinline__ void column_sums_32(float (&a)[32], int lane) {
     }
 }
 
-template <int BN, int STAGES, bool OUT_BF16>
+// A_MN / B_MN: the operand is stored [k, mn] (mn contiguous, "MN-major") instead of [mn, k].  Its tile
+// is then loaded as 64-column boxes of BK rows (row = one k, 128 bytes = 64 mn); boxes of consecutive
+// 64-mn blocks lie BK*128 bytes apart (the descriptor's leading byte offset), 8-k groups 1024 bytes
+// apart (stride byte offset), and a 16-wide K slice starts 16 rows = 2048 bytes further.
+template <int BN, int STAGES, bool OUT_BF16, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ GemmDev g) {
@@ -102,13 +106,25 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 tc::mbar_wait(&empty[s], ph ^ 1u);
                 tc::mbar_arrive_expect_tx(&full[s], S::A_BYTES + S::B_BYTES);
                 const int k = (kb0 + kb) * GEMM_BK;
-                tc::tma_load_2d(sA + s * S::A_BYTES, &tmap_a, &full[s], k, m0);
-                tc::tma_load_2d(sB + s * S::B_BYTES, &tmap_b, &full[s], k, n0);
+                if (A_MN) {
+#pragma unroll
+                    for (int b = 0; b < GEMM_BM / 64; ++b)
+                        tc::tma_load_2d(sA + s * S::A_BYTES + b * (GEMM_BK * 128), &tmap_a, &full[s], m0 + 64 * b, k);
+                } else {
+                    tc::tma_load_2d(sA + s * S::A_BYTES, &tmap_a, &full[s], k, m0);
+                }
+                if (B_MN) {
+#pragma unroll
+                    for (int b = 0; b < BN / 64; ++b)
+                        tc::tma_load_2d(sB + s * S::B_BYTES + b * (GEMM_BK * 128), &tmap_b, &full[s], n0 + 64 * b, k);
+                } else {
+                    tc::tma_load_2d(sB + s * S::B_BYTES, &tmap_b, &full[s], k, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = tc::idesc_bf16_f32(GEMM_BM, BN);
+            constexpr uint32_t idesc = tc::idesc_bf16_f32(GEMM_BM, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
@@ -116,8 +132,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 tc::tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < GEMM_BK / 16; ++k) {
-                    const uint64_t da = tc::smem_desc_sw128(sA + s * S::A_BYTES, k * 16);
-                    const uint64_t db = tc::smem_desc_sw128(sB + s * S::B_BYTES, k * 16);
+                    const uint64_t da = A_MN ? tc::smem_desc_sw128_mn(sA + s * S::A_BYTES + k * 2048, GEMM_BK * 128)
+                                             : tc::smem_desc_sw128(sA + s * S::A_BYTES, k * 16);
+                    const uint64_t db = B_MN ? tc::smem_desc_sw128_mn(sB + s * S::B_BYTES + k * 2048, GEMM_BK * 128)
+                                             : tc::smem_desc_sw128(sB + s * S::B_BYTES, k * 16);
                     tc::umma_bf16(tmem_acc, da, db, idesc, (kb | k) ? 1u : 0u);
                 }
                 tc::umma_commit(&empty[s]);  // frees the ring slot once these MMAs have read it
@@ -236,6 +254,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld_elems, int box_rows) {
+    // box = [box_rows, 64 columns]: K-major operands use box_rows = tile extent, MN-major ones box_rows = BK
     EncodeTiledFn fn = encode_fn();
     TRS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     TRS_REQUIRE(((uintptr_t)base & 15) == 0 && (ld_elems * 2) % 16 == 0,
@@ -255,13 +274,17 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t col
     return TRS_OK;
 }
 
-template <int BN, int STAGES, bool OUT_BF16>
+template <int BN, int STAGES, bool OUT_BF16, bool A_MN, bool B_MN>
 static int launch_gemm(const trs_gemm_args* a, const GemmDev& g, int splits, cudaStream_t stream) {
     CUtensorMap ta, tb;
     int rc;
-    if ((rc = make_tmap_bf16(&ta, a->a, a->m, a->k, a->lda, GEMM_BM))) return rc;
-    if ((rc = make_tmap_bf16(&tb, a->b, a->n, a->k, a->ldb, BN))) return rc;
-    auto kern = gemm_tn_kernel<BN, STAGES, OUT_BF16>;
+    if (A_MN) rc = make_tmap_bf16(&ta, a->a, a->k, a->m, a->lda, GEMM_BK);
+    else rc = make_tmap_bf16(&ta, a->a, a->m, a->k, a->lda, GEMM_BM);
+    if (rc) return rc;
+    if (B_MN) rc = make_tmap_bf16(&tb, a->b, a->k, a->n, a->ldb, GEMM_BK);
+    else rc = make_tmap_bf16(&tb, a->b, a->n, a->k, a->ldb, BN);
+    if (rc) return rc;
+    auto kern = gemm_tn_kernel<BN, STAGES, OUT_BF16, A_MN, B_MN>;
     constexpr int smem = GemmSmem<BN, STAGES>::TOTAL;
     TRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     dim3 grid((unsigned)((a->m + GEMM_BM - 1) / GEMM_BM), (unsigned)((a->n + BN - 1) / BN), (unsigned)splits);
@@ -301,8 +324,23 @@ extern "C" int trs_gemm_bf16_tn(const trs_gemm_args* a, trs_stream_t stream) {
     g.rows_per_half = a->rows_per_half > 0 ? (int)a->rows_per_half : (int)a->m;
     g.rows_valid = a->rows_per_half > 0 ? (int)a->rows_valid : (int)a->m;
     cudaStream_t s = (cudaStream_t)stream;
-    if (a->n > 64) {
-        return a->out_bf16 ? launch_gemm<128, 3, true>(a, g, splits, s) : launch_gemm<128, 3, false>(a, g, splits, s);
-    }
-    return a->out_bf16 ? launch_gemm<64, 4, true>(a, g, splits, s) : launch_gemm<64, 4, false>(a, g, splits, s);
+    TRS_REQUIRE(!(a->a_mn && !a->b_mn), "gemm: operand layout (a MN-major, b K-major) is not instantiated");
+    TRS_REQUIRE((!a->a_mn || a->m % 8 == 0), "gemm: MN-major a needs m %% 8 == 0");
+    const int layout = (a->a_mn ? 2 : 0) | (a->b_mn ? 1 : 0);
+#define TRS_GEMM_CASE(BN_, ST_, BF_, L_, AM_, BM_) \
+    if ((a->n > 64) == (BN_ == 128) && (a->out_bf16 != 0) == BF_ && layout == L_) \
+        return launch_gemm<BN_, ST_, BF_, AM_, BM_>(a, g, splits, s);
+    TRS_GEMM_CASE(128, 3, true, 0, false, false)
+    TRS_GEMM_CASE(128, 3, false, 0, false, false)
+    TRS_GEMM_CASE(64, 4, true, 0, false, false)
+    TRS_GEMM_CASE(64, 4, false, 0, false, false)
+    TRS_GEMM_CASE(128, 3, true, 1, false, true)
+    TRS_GEMM_CASE(128, 3, false, 1, false, true)
+    TRS_GEMM_CASE(64, 4, true, 1, false, true)
+    TRS_GEMM_CASE(64, 4, false, 1, false, true)
+    TRS_GEMM_CASE(128, 3, false, 3, true, true)
+    TRS_GEMM_CASE(64, 4, false, 3, true, true)
+#undef TRS_GEMM_CASE
+    set_error("gemm: no kernel for this combination (MN-major a writes fp32 only)");
+    return TRS_ERR_ARG;
 }

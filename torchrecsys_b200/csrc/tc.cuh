@@ -114,6 +114,18 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(const void* tile, int k_elem
     d |= (uint64_t)2 << 61;
     return d;
 }
+// MN-major bf16 tile: rows of 64 mn-elements (128 bytes, swizzled by TMA), one row per k.  `tile` points at
+// the first k row of the slice; lbo_bytes = distance between consecutive 64-mn blocks.
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(const void* tile, uint32_t lbo_bytes) {
+    const uint32_t addr = smem_u32(tile);
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // Instruction descriptor of kind::f16: D fp32 (bits 4-5 = 1), A and B bf16 (bits 7-9, 10-12 = 1), both
 // K-major (bits 15, 16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int m, int n) {
