@@ -38,7 +38,7 @@ typedef enum {
     TRS_ERR_WORKSPACE = -3 /* caller workspace too small */
 } trs_status;
 
-typedef enum { TRS_NET_LINEAR = 0, TRS_NET_FM = 1 } trs_net;
+typedef enum { TRS_NET_LINEAR = 0, TRS_NET_FM = 1, TRS_NET_MLP = 2 } trs_net;
 typedef enum { TRS_OPT_SGD = 0, TRS_OPT_ADAGRAD = 1, TRS_OPT_SPARSE_ADAM = 2 } trs_opt;
 
 /* One id space = an embedding table [n_rows, dim] plus (optionally) the width-1 table that is
@@ -181,6 +181,58 @@ typedef struct {
     int64_t rows_valid;
 } trs_gemm_args;
 int trs_gemm_bf16_tn(const trs_gemm_args* args, trs_stream_t stream);
+
+/* ---- a4 + a6 + a7 for net_type='mlp' (collaborative/mlp.py:88-115, model.py:171-200) --------- */
+/* The tower: concat[user, item, metadata_f...] -> (Linear -> BatchNorm1d -> ReLU) x n_layers ->
+ * Linear(-> 1).  Pointers are the fp32 parameters / buffers of the torch modules (fcs.l, bns.l,
+ * output_layer; collaborative/mlp.py:74-85), d* receive the dense gradients of one training step, and
+ * s0* are the dense optimizer state (Adagrad `sum`; NULL for SGD) updated in place together with the
+ * parameters.  The embedding tables travel in a trs_model with net = TRS_NET_MLP (lin pointers NULL). */
+#define TRS_MAX_LAYERS 8
+typedef struct {
+    int32_t n_layers; /* hidden layers, 1..TRS_MAX_LAYERS */
+    int32_t use_bn;
+    int32_t hidden[TRS_MAX_LAYERS];
+    float* W[TRS_MAX_LAYERS];     /* [hidden[l], in_l], in_0 = dim*(2+n_meta), in_l = hidden[l-1] */
+    float* b[TRS_MAX_LAYERS];     /* [hidden[l]] */
+    float* gamma[TRS_MAX_LAYERS]; /* BatchNorm1d weight / bias / running stats (use_bn) */
+    float* beta[TRS_MAX_LAYERS];
+    float* running_mean[TRS_MAX_LAYERS];
+    float* running_var[TRS_MAX_LAYERS];
+    float* w_out; /* [1, hidden[n_layers-1]] */
+    float* b_out; /* [1] */
+    /* training only */
+    float* dW[TRS_MAX_LAYERS];
+    float* db[TRS_MAX_LAYERS];
+    float* dgamma[TRS_MAX_LAYERS];
+    float* dbeta[TRS_MAX_LAYERS];
+    float* dw_out;
+    float* db_out;
+    float* s0W[TRS_MAX_LAYERS];
+    float* s0b[TRS_MAX_LAYERS];
+    float* s0gamma[TRS_MAX_LAYERS];
+    float* s0beta[TRS_MAX_LAYERS];
+    float* s0w_out;
+    float* s0b_out;
+} trs_mlp;
+
+/* Forward of n (user, item[, meta]) rows -> out[n] (net.forward, mlp.py:88-115).  batch_stats = 0: eval
+ * mode (BatchNorm uses running statistics); 1: train mode (this call's batch statistics, running
+ * statistics updated once, as one reference forward pass does). */
+size_t trs_mlp_forward_workspace_bytes(const trs_model* model, const trs_mlp* mlp, int64_t n);
+int trs_mlp_forward(const trs_model* model, const trs_mlp* mlp, const int64_t* user, const int64_t* item,
+                    const int64_t* meta, int64_t n, int batch_stats, float* out, void* workspace,
+                    size_t workspace_bytes, trs_stream_t stream);
+
+/* Steps [first_step, first_step+n_steps) of the epoch (model.py:274-284): both passes forward with
+ * per-pass BatchNorm statistics (running statistics updated twice per step), hinge, backward through the
+ * tcgen05 GEMMs, dense update (SGD / Adagrad) of the tower, deterministic segmented reduce + row-wise
+ * update of the embedding tables.  No host synchronisation; loss[s] as in trs_train_steps.
+ * `plan` comes from trs_plan_build on the same model / epoch. */
+size_t trs_mlp_train_workspace_bytes(const trs_model* model, const trs_mlp* mlp, const trs_epoch* epoch);
+int trs_mlp_train_steps(const trs_model* model, const trs_mlp* mlp, const trs_epoch* epoch,
+                        const trs_optim* optim, const void* plan, void* workspace, size_t workspace_bytes,
+                        int first_step, int n_steps, float* loss, trs_stream_t stream);
 
 #ifdef __cplusplus
 }

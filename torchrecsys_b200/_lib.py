@@ -22,7 +22,8 @@ SYMBOLS = [
     "trs_abi_version", "trs_last_error", "trs_device_info", "trs_embed_gather_sum", "trs_scores",
     "trs_philox_negatives", "trs_validate_ids", "trs_plan_bytes", "trs_plan_tmp_bytes",
     "trs_plan_build", "trs_train_workspace_bytes", "trs_train_steps", "trs_eval_pairwise",
-    "trs_gemm_bf16_tn",
+    "trs_gemm_bf16_tn", "trs_mlp_forward_workspace_bytes", "trs_mlp_forward",
+    "trs_mlp_train_workspace_bytes", "trs_mlp_train_steps",
 ]
 
 
@@ -222,3 +223,58 @@ def gemm_bf16_tn(a, b, out, bias=None, splits: int = 1, col_sum=None, col_sumsq=
                     int(a_mn), int(b_mn), _ptr(bias, torch.float32), _ptr(col_sum, torch.float32), _ptr(col_sumsq, torch.float32),
                     rows_per_half, rows_valid)
     _check(lib().trs_gemm_bf16_tn(C.byref(args), _stream()))
+
+
+# ---- MLP tower (include/trs.h: trs_mlp) -------------------------------------------------------------
+MAX_LAYERS = 8
+NET_MLP = 2
+_PL = C.c_void_p * MAX_LAYERS
+
+
+class Mlp(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("use_bn", C.c_int32), ("hidden", C.c_int32 * MAX_LAYERS),
+                ("W", _PL), ("b", _PL), ("gamma", _PL), ("beta", _PL), ("running_mean", _PL),
+                ("running_var", _PL), ("w_out", C.c_void_p), ("b_out", C.c_void_p),
+                ("dW", _PL), ("db", _PL), ("dgamma", _PL), ("dbeta", _PL), ("dw_out", C.c_void_p),
+                ("db_out", C.c_void_p), ("s0W", _PL), ("s0b", _PL), ("s0gamma", _PL), ("s0beta", _PL),
+                ("s0w_out", C.c_void_p), ("s0b_out", C.c_void_p)]
+
+
+def mlp_forward(model: Model, mlp: Mlp, user, item, meta=None, batch_stats: bool = False) -> torch.Tensor:
+    """Scores of n (user, item[, meta]) rows through the tower; eval-mode BatchNorm unless batch_stats."""
+    L = lib()
+    L.trs_mlp_forward_workspace_bytes.restype = C.c_size_t
+    n = user.shape[0]
+    out = torch.empty(n, dtype=torch.float32, device=user.device)
+    chunk = n if batch_stats else 1 << 16  # eval mode is row-independent: bound the activation workspace
+    ws = None
+    for lo in range(0, n, max(chunk, 1)):
+        hi = min(n, lo + chunk)
+        nbytes = L.trs_mlp_forward_workspace_bytes(C.byref(model), C.byref(mlp), C.c_int64(hi - lo))
+        if nbytes == 0:
+            raise RuntimeError(f"libtrs_b200: {L.trs_last_error().decode()}")
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=user.device)
+        m = None if meta is None else meta[lo:hi]
+        _check(L.trs_mlp_forward(C.byref(model), C.byref(mlp), C.c_void_p(_ptr(user[lo:hi], torch.int64)),
+                                 C.c_void_p(_ptr(item[lo:hi], torch.int64)), C.c_void_p(_ptr(m, torch.int64)),
+                                 C.c_int64(hi - lo), int(batch_stats), C.c_void_p(out[lo:hi].data_ptr()),
+                                 C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()), _stream()))
+    return out
+
+
+def mlp_train_workspace(model: Model, mlp: Mlp, epoch: Epoch, device) -> torch.Tensor:
+    L = lib()
+    L.trs_mlp_train_workspace_bytes.restype = C.c_size_t
+    nbytes = L.trs_mlp_train_workspace_bytes(C.byref(model), C.byref(mlp), C.byref(epoch))
+    if nbytes == 0:
+        raise RuntimeError(f"libtrs_b200: {L.trs_last_error().decode()}")
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+def mlp_train_steps(model: Model, mlp: Mlp, epoch: Epoch, optim: Optim, plan, workspace, first_step: int,
+                    n_steps: int, loss_out: torch.Tensor) -> None:
+    _check(lib().trs_mlp_train_steps(C.byref(model), C.byref(mlp), C.byref(epoch), C.byref(optim),
+                                     C.c_void_p(plan.data_ptr()), C.c_void_p(workspace.data_ptr()),
+                                     C.c_size_t(workspace.numel()), first_step, n_steps,
+                                     C.c_void_p(_ptr(loss_out, torch.float32)), _stream()))

@@ -3,12 +3,16 @@ concat[user, item, metadata_f...] -> (Linear -> BatchNorm1d -> ReLU) x n -> Line
 
 Parameter / buffer names match the reference (``user``, ``item``, ``metadata_embeddings.{f}``,
 ``fcs.{l}``, ``bns.{l}``, ``output_layer``).  The dense layers are real ``nn.Linear`` /
-``nn.BatchNorm1d`` modules so the weights bind to torch optimizers."""
-from typing import List, Optional
+``nn.BatchNorm1d`` modules so the weights bind to torch optimizers; the arithmetic runs in
+libtrs_b200: tcgen05 GEMMs (bf16 operands, fp32 accumulation) with BatchNorm / ReLU kernels around
+them (csrc/gemm.cu, csrc/mlp.cu)."""
+from typing import Dict, List, Optional
 
 import torch
 
+from .. import _lib
 from ..embeddings.init_embeddings import ScaledEmbedding
+from ._base import canonical_meta
 
 
 class MLP(torch.nn.Module):
@@ -44,5 +48,67 @@ class MLP(torch.nn.Module):
     def n_meta_features(self) -> int:
         return len(self.n_metadata) if (self.use_metadata and self.n_metadata) else 0
 
+    # ---- views handed to the C ABI -----------------------------------------------------------
+    def sparse_parameters(self) -> List[torch.nn.Parameter]:
+        out = [self.user.weight, self.item.weight]
+        if self.n_meta_features:
+            out += [e.weight for e in self.metadata_embeddings]
+        return out
+
+    def dense_parameters(self) -> List[torch.nn.Parameter]:
+        sparse = {id(p) for p in self.sparse_parameters()}
+        return [p for p in self.parameters() if id(p) not in sparse]
+
+    def abi_model(self, state: Optional[Dict[torch.Tensor, dict]] = None, keys=(None, None)) -> _lib.Model:
+        def table(p):
+            s0 = None if (state is None or keys[0] is None) else state[p][keys[0]]
+            s1 = None if (state is None or keys[1] is None) else state[p][keys[1]]
+            return _lib.make_table(p, s0, s1)
+
+        metas = [table(e.weight) for e in self.metadata_embeddings] if self.n_meta_features else []
+        return _lib.make_model(_lib.NET_MLP, self.n_factors, table(self.user.weight), table(self.item.weight), metas)
+
+    def abi_mlp(self, grads: Optional[Dict[torch.Tensor, torch.Tensor]] = None,
+                state: Optional[Dict[torch.Tensor, dict]] = None, key: Optional[str] = None) -> _lib.Mlp:
+        """``grads[p]``: fp32 buffer receiving p's gradient; ``state[p][key]``: dense optimizer state."""
+        if len(self.hidden_layers) > _lib.MAX_LAYERS:
+            raise RuntimeError(f"at most {_lib.MAX_LAYERS} hidden layers are supported")
+        m = _lib.Mlp()
+        m.n_layers, m.use_bn = len(self.hidden_layers), int(self.use_batch_norm)
+        ptr = lambda t: _lib._ptr(t, torch.float32)
+        g = (lambda p: ptr(grads[p])) if grads is not None else (lambda p: None)
+        s0 = (lambda p: ptr(state[p][key])) if (state is not None and key) else (lambda p: None)
+        for l, fc in enumerate(self.fcs):
+            m.hidden[l] = fc.out_features
+            m.W[l], m.b[l] = ptr(fc.weight), ptr(fc.bias)
+            m.dW[l], m.db[l] = g(fc.weight), g(fc.bias)
+            m.s0W[l], m.s0b[l] = s0(fc.weight), s0(fc.bias)
+            if self.use_batch_norm:
+                bn = self.bns[l]
+                m.gamma[l], m.beta[l] = ptr(bn.weight), ptr(bn.bias)
+                m.running_mean[l], m.running_var[l] = ptr(bn.running_mean), ptr(bn.running_var)
+                m.dgamma[l], m.dbeta[l] = g(bn.weight), g(bn.bias)
+                m.s0gamma[l], m.s0beta[l] = s0(bn.weight), s0(bn.bias)
+        o = self.output_layer
+        m.w_out, m.b_out = ptr(o.weight), ptr(o.bias)
+        m.dw_out, m.db_out = g(o.weight), g(o.bias)
+        m.s0w_out, m.s0b_out = s0(o.weight), s0(o.bias)
+        return m
+
     def forward(self, batch, user_key, item_key, metadata_key=None):
-        raise NotImplementedError("the MLP tower's tcgen05 forward is not wired yet")
+        """(B, 1) scores.  In ``train()`` mode BatchNorm uses this batch's statistics and updates the
+        running ones, as one reference forward pass does (mlp.py:107-111)."""
+        user, item = batch[user_key], batch[item_key]
+        if not user.is_cuda:
+            raise RuntimeError("torchrecsys_b200 has no CPU fallback: move the model and batch to a "
+                               "CUDA device (use_cuda=True)")
+        meta = canonical_meta(batch.get(metadata_key) if metadata_key else None, self.n_meta_features)
+        if self.n_meta_features and meta is None:
+            raise KeyError(f"model uses metadata but batch has no '{metadata_key}'")
+        stats = self.training and self.use_batch_norm
+        out = _lib.mlp_forward(self.abi_model(), self.abi_mlp(), user.long().contiguous(),
+                               item.long().contiguous(), meta, batch_stats=stats)
+        if stats:
+            for bn in self.bns:
+                bn.num_batches_tracked += 1
+        return out.view(-1, 1)

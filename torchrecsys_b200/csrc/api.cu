@@ -30,7 +30,7 @@ const DeviceProps& device_props() {
 
 int check_model(const trs_model* m, RowShape* shape) {
     TRS_REQUIRE(m != nullptr, "model is NULL");
-    TRS_REQUIRE(m->net == TRS_NET_LINEAR || m->net == TRS_NET_FM, "unknown net %d", m->net);
+    TRS_REQUIRE(m->net == TRS_NET_LINEAR || m->net == TRS_NET_FM || m->net == TRS_NET_MLP, "unknown net %d", m->net);
     TRS_REQUIRE(m->n_meta >= 0 && m->n_meta <= TRS_MAX_META, "n_meta %d out of range", m->n_meta);
     TRS_REQUIRE(pick_row_shape(m->dim, shape), "unsupported n_factors %d (need 1..512, or a multiple of 4)", m->dim);
     TRS_REQUIRE(m->user.emb && m->item.emb, "user/item embedding pointer is NULL");

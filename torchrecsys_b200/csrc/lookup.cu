@@ -239,6 +239,7 @@ extern "C" int trs_scores(const trs_model* model, const int64_t* user, const int
     RowShape shape;
     int rc = check_model(model, &shape);
     if (rc) return rc;
+    TRS_REQUIRE(model->net != TRS_NET_MLP, "trs_scores: use trs_mlp_forward for net_type mlp");
     if (n == 0) return TRS_OK;
     TRS_REQUIRE(user && item && out, "NULL pointer");
     TRS_REQUIRE(model->n_meta == 0 || meta, "model has metadata tables but meta ids are NULL");
@@ -252,6 +253,7 @@ extern "C" int trs_eval_pairwise(const trs_model* model, const trs_epoch* epoch,
     RowShape shape;
     int rc = check_model(model, &shape);
     if (rc) return rc;
+    TRS_REQUIRE(model->net != TRS_NET_MLP, "trs_eval_pairwise: score the tower with trs_mlp_forward");
     TRS_REQUIRE(epoch, "epoch is NULL");
     if (epoch->n_samples == 0) return TRS_OK;
     TRS_REQUIRE(epoch->user && epoch->pos && epoch->neg, "epoch ids are NULL");

@@ -20,6 +20,7 @@
 
 #include "plan.cuh"
 #include "scorer.cuh"
+#include "train.cuh"
 
 namespace trs {
 
@@ -74,7 +75,7 @@ static StageLayout stage_layout(const trs_model* m, const trs_epoch* ep, int gri
     const size_t B = (size_t)ep->batch, D = (size_t)m->dim;
     L.gU = take(B * D);
     L.gI = take(2 * B * D);
-    for (int f = 0; f < TRS_MAX_META; ++f) L.gM[f] = (m->net == TRS_NET_FM && f < m->n_meta) ? take(2 * B * D) : 0;
+    for (int f = 0; f < TRS_MAX_META; ++f) L.gM[f] = (m->net != TRS_NET_LINEAR && f < m->n_meta) ? take(2 * B * D) : 0;
     L.gbU = take(B);
     L.gbI = take(2 * B);
     L.loss_part = take((size_t)n_steps_of(ep) * grid);
@@ -194,7 +195,7 @@ __device__ __forceinline__ SpaceRef resolve_space(int space, const trs_model& m,
     } else {
         const int f = space - 2;
         r = {&m.meta[f], plan.meta_key[f] + 2 * lo, plan.meta_perm[f] + 2 * lo,
-             NET == TRS_NET_FM ? st.gM[f] : st.gI, NET == TRS_NET_FM ? st.gbI : nullptr};
+             NET != TRS_NET_LINEAR ? st.gM[f] : st.gI, NET == TRS_NET_FM ? st.gbI : nullptr};
     }
     if (!r.t->lin) r.stage_lin = nullptr;
     return r;
@@ -559,6 +560,9 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
         if (tracing) tr[0] = global_ns();
         // ------------------------------ phase A ------------------------------------------
         float hsum = 0.f;
+        // NET == TRS_NET_MLP: the gradient rows were staged by the tower's backward (mlp.cu); this
+        // kernel only runs the reduce + update phase
+        if constexpr (NET != TRS_NET_MLP)
         if (!(dbg & 1))
         for (int b0 = gid_warp0; b0 < Bs; b0 += ngroups) {   // warp-uniform trip count
             const int b_raw = b0 + (gid - gid_warp0);
@@ -855,7 +859,7 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
     cp_async_wait<0>();
 
     // batch-mean hinge per step, summed over CTAs in a fixed order (deterministic)
-    if (blockIdx.x == 0) {
+    if (NET != TRS_NET_MLP && blockIdx.x == 0) {
         for (int si = threadIdx.x; si < n_steps; si += NT) {
             const int64_t lo = (first_step + (int64_t)si) * ep.batch;
             const int Bs = (int)min((int64_t)ep.batch, ep.n_samples - lo);
@@ -874,8 +878,8 @@ static int train_grid_size() {
 
 template <int V, int G, int IT>
 static void query_grid(int net, int* grid) {
-    *grid = net == TRS_NET_LINEAR ? train_grid_size<TRS_NET_LINEAR, V, G, IT>()
-                                  : train_grid_size<TRS_NET_FM, V, G, IT>();
+    *grid = train_grid_size<TRS_NET_LINEAR, V, G, IT>();
+    (void)net;
 }
 
 template <int V, int G, int IT>
@@ -889,7 +893,8 @@ static void launch_train(const trs_model* m, const trs_epoch* ep, const OptScala
     void* args[] = {(void*)m, (void*)ep, (void*)opt, (void*)plan, (void*)st,
                     (void*)&first_step, (void*)&n_steps, (void*)&loss, (void*)&dbg};
     const void* fn = m->net == TRS_NET_LINEAR ? (const void*)train_kernel<TRS_NET_LINEAR, V, G, IT>
-                                              : (const void*)train_kernel<TRS_NET_FM, V, G, IT>;
+                     : m->net == TRS_NET_FM   ? (const void*)train_kernel<TRS_NET_FM, V, G, IT>
+                                              : (const void*)train_kernel<TRS_NET_MLP, V, G, IT>;
     const size_t smem = train_smem_bytes<V, IT>();
     if (smem > 48 * 1024) {
         *err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -936,9 +941,31 @@ extern "C" size_t trs_train_workspace_bytes(const trs_model* model, const trs_ep
     return stage_layout(model, epoch, train_grid_for(model, shape)).total;
 }
 
+namespace trs {
+StagePtrs stage_pointers(const trs_model* model, const trs_epoch* ep, void* workspace) {
+    RowShape shape;
+    StagePtrs r = {};
+    if (!pick_row_shape(model->dim, &shape)) return r;
+    const StageLayout SL = stage_layout(model, ep, train_grid_for(model, shape));
+    char* W = (char*)workspace;
+    r.gU = (float*)(W + SL.gU);
+    r.gI = (float*)(W + SL.gI);
+    for (int f = 0; f < model->n_meta; ++f) r.gM[f] = (float*)(W + SL.gM[f]);
+    return r;
+}
+}  // namespace trs
+
 extern "C" int trs_train_steps(const trs_model* model, const trs_epoch* ep, const trs_optim* optim,
                                const void* plan, void* workspace, size_t workspace_bytes,
                                int first_step, int n_steps, float* loss, trs_stream_t stream) {
+    TRS_REQUIRE(model && model->net != TRS_NET_MLP, "trs_train_steps: use trs_mlp_train_steps for net_type mlp");
+    return trs::run_train_steps(model, ep, optim, plan, workspace, workspace_bytes, first_step, n_steps, loss,
+                                (cudaStream_t)stream);
+}
+
+int trs::run_train_steps(const trs_model* model, const trs_epoch* ep, const trs_optim* optim,
+                         const void* plan, void* workspace, size_t workspace_bytes,
+                         int first_step, int n_steps, float* loss, cudaStream_t stream) {
     RowShape shape;
     int rc = check_model(model, &shape);
     if (rc) return rc;
@@ -947,7 +974,7 @@ extern "C" int trs_train_steps(const trs_model* model, const trs_epoch* ep, cons
     TRS_REQUIRE(model->n_meta == 0 || (ep->pos_meta && ep->neg_meta), "metadata ids are NULL");
     TRS_REQUIRE(optim && optim->step_scale, "optimizer / step_scale is NULL");
     TRS_REQUIRE(optim->kind >= TRS_OPT_SGD && optim->kind <= TRS_OPT_SPARSE_ADAM, "unknown optimizer kind %d", optim->kind);
-    TRS_REQUIRE(plan && workspace && loss, "plan / workspace / loss is NULL");
+    TRS_REQUIRE(plan && workspace && (loss || model->net == TRS_NET_MLP), "plan / workspace / loss is NULL");
     const int64_t steps = n_steps_of(ep);
     TRS_REQUIRE(first_step >= 0 && n_steps >= 0 && first_step + (int64_t)n_steps <= steps,
                 "steps [%d, %d) outside the epoch's %lld steps", first_step, first_step + n_steps, (long long)steps);

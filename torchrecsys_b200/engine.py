@@ -150,3 +150,52 @@ class EpochRunner:
                                   + sum(passes(model.meta[f].n_rows) for f in range(n_meta))) + 2 + n_meta
         advance_steps(self.optimizer, self.params, b, n_steps)
         return loss
+
+
+class MlpEpochRunner:
+    """EpochRunner for net_type='mlp': every step runs the tower forward/backward on the tcgen05 GEMMs,
+    the dense SGD / Adagrad update and the row-wise embedding update inside libtrs_b200
+    (trs_mlp_train_steps); the host only launches."""
+
+    def __init__(self, net, optimizer):
+        self.net = net
+        self.optimizer = optimizer
+        self.params = [p for p in net.parameters()]
+        self.binding = bind_optimizer(optimizer, self.params)
+        if self.binding.kind == _lib.OPT_SPARSE_ADAM:
+            raise NotImplementedError(
+                "net_type='mlp' has dense parameters: use Adagrad or SGD (torch's SparseAdam rejects dense "
+                "gradients and Adam rejects the sparse ones, SURVEY.md D2)")
+        self.grads = {p: torch.zeros_like(p) for p in net.dense_parameters()}
+        for p, g in self.grads.items():
+            p.grad = g  # the last step's dense gradient stays visible to user code
+        self.launches = 0
+
+    def run(self, samples: Dict[str, torch.Tensor], batch_size: int) -> torch.Tensor:
+        b = self.binding
+        dev = samples["user"].device
+        key = b.keys[0]
+        model = self.net.abi_model(self.optimizer.state, b.keys)
+        mlp = self.net.abi_mlp(self.grads, self.optimizer.state if key else None, key)
+        epoch = _lib.make_epoch(samples["user"], samples["pos"], samples["neg"],
+                                samples.get("pos_meta"), samples.get("neg_meta"), batch_size)
+        n = samples["user"].shape[0]
+        n_steps = -(-n // batch_size)
+        scales = torch.tensor(step_scales(b, n_steps), dtype=torch.float64).to(torch.float32)
+        scales = scales.to(dev, non_blocking=True)
+        optim = _lib.Optim(b.kind, 0, b.beta1, b.beta2, b.eps, scales.data_ptr())
+        plan = _lib.plan_build(model, epoch, dev)
+        ws = _lib.mlp_train_workspace(model, mlp, epoch, dev)
+        loss = torch.empty(n_steps, dtype=torch.float32, device=dev)
+        _lib.mlp_train_steps(model, mlp, epoch, optim, plan, ws, 0, n_steps, loss)
+        nl = len(self.net.hidden_layers)
+        bn = int(self.net.use_batch_norm)
+        # per step: gather, weight cast, per layer (gemm, bn finalize, bn+relu), hinge, loss; backward per
+        # layer (reduce, finalize, apply, db reduce, wgrad gemm, dW reduce, dgrad gemm); dense update, staging,
+        # row update
+        self.launches += n_steps * (2 + nl * (2 + bn) + 2 + nl * (5 + 2 * bn) + 3)
+        advance_steps(self.optimizer, self.params, b, n_steps)
+        if self.net.use_batch_norm:
+            for m in self.net.bns:
+                m.num_batches_tracked += 2 * n_steps  # two forward passes per step (model.py:173-183)
+        return loss

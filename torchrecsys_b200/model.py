@@ -26,7 +26,7 @@ from .collaborative.fm import FM
 from .collaborative.linear import Linear
 from .collaborative.mlp import MLP
 from .dataset.dataset import FastDataLoader, ProcessData
-from .engine import EpochRunner
+from .engine import EpochRunner, MlpEpochRunner
 from .evaluate.metrics import Metrics
 from .helper.cuda import gpu
 from .helper.loss import hinge_loss
@@ -154,11 +154,9 @@ class TorchRecSys(torch.nn.Module):
     # ------------------------------------------------------------------------------------
     def fit(self, optimizer, epochs=10, batch_size=512, profile_epochs: int = 0):
         dev = self._require_cuda()
-        if self.net_type == "mlp":
-            return self._fit_mlp(optimizer, epochs, batch_size, profile_epochs)
         base = self._device_split("train_data")
         n = base["user"].shape[0] if base else 0
-        runner = EpochRunner(self.net, optimizer)
+        runner = (MlpEpochRunner if self.net_type == "mlp" else EpochRunner)(self.net, optimizer)
         self._last_runner = runner
         # the reference loader shuffles once when constructed and again at every __iter__
         # (dataset.py:359-373); consuming the CPU generator the same way keeps seeded runs comparable
@@ -189,9 +187,6 @@ class TorchRecSys(torch.nn.Module):
                 avg_loss = one_epoch()
             print(f"|--- Epoch {epoch + 1}/{epochs} --- Training Loss: {avg_loss:.4f}")
 
-    def _fit_mlp(self, optimizer, epochs, batch_size, profile_epochs):
-        raise NotImplementedError("the MLP tower's tcgen05 path is not wired into fit yet")
-
     # ------------------------------------------------------------------------------------
     def evaluate(self, batch_size=512, eval_metrics=["loss", "auc"]):
         self._require_cuda()
@@ -201,12 +196,21 @@ class TorchRecSys(torch.nn.Module):
         if not test or test["user"].numel() == 0:
             print("|--- No test data to evaluate.")
             return
-        if self.net_type == "mlp":
-            raise NotImplementedError("MLP evaluate is not wired yet")
         test = self._with_negatives(test, (1 << 40) + self._epochs_seen * test["user"].shape[0])
-        epoch = _lib.make_epoch(test["user"], test["pos"], test["neg"], test.get("pos_meta"),
-                                test.get("neg_meta"), batch_size)
-        loss, auc, _, _ = _lib.eval_pairwise(self.net.abi_model(), epoch)
+        if self.net_type == "mlp":
+            # eval-mode BatchNorm is row-independent: score the whole split once, then the per-batch
+            # statistics of model.py:315-324
+            net = self.net
+            pos = _lib.mlp_forward(net.abi_model(), net.abi_mlp(), test["user"], test["pos"], test.get("pos_meta"))
+            neg = _lib.mlp_forward(net.abi_model(), net.abi_mlp(), test["user"], test["neg"], test.get("neg_meta"))
+            hinge = torch.clamp(neg - pos + 1.0, min=0.0).split(batch_size)
+            wins = (pos > neg).float().split(batch_size)
+            loss = torch.stack([h.mean() for h in hinge])
+            auc = torch.stack([w.mean() for w in wins])
+        else:
+            epoch = _lib.make_epoch(test["user"], test["pos"], test["neg"], test.get("pos_meta"),
+                                    test.get("neg_meta"), batch_size)
+            loss, auc, _, _ = _lib.eval_pairwise(self.net.abi_model(), epoch)
         results = {"loss": loss, "auc": auc}
         for metric in eval_metrics:
             if metric in results:
@@ -223,11 +227,12 @@ class TorchRecSys(torch.nn.Module):
         ``prediction_batch_size`` is accepted for compatibility; all items are scored in one pass."""
         dev = self._require_cuda()
         self.net = self.net.eval()
-        if self.net_type == "mlp":
-            raise NotImplementedError("MLP predict is not wired yet")
         items = torch.arange(self.n_items, device=dev)
         users = torch.full_like(items, int(user_id))
         meta = self._dev_cache.get("item_meta") if self.use_metadata else None
-        scores = _lib.scores(self.net.abi_model(), users, items, meta)
+        if self.net_type == "mlp":
+            scores = _lib.mlp_forward(self.net.abi_model(), self.net.abi_mlp(), users, items, meta)
+        else:
+            scores = _lib.scores(self.net.abi_model(), users, items, meta)
         order = torch.sort(scores, descending=True, stable=True)[1]
         return order[:top_k].cpu()
