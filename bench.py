@@ -42,6 +42,9 @@ WORKLOADS = {
                   "dynamic negatives, 1M users x 200k items, dim 64, batch 8192, SparseAdam"),
     "c1_linear": dict(net="linear", n_users=3000, n_items=1000, dim=80, n_cat=0, batch=1024,
                       opt="sparse_adam", lr=1e-3, desc="BASELINE configs[0] shape: linear 3k x 1k, dim 80, batch 1024"),
+    "c3_mlp": dict(net="mlp", n_users=1_000_000, n_items=200_000, dim=64, n_cat=0, batch=16384, opt="adagrad",
+                   lr=1e-2, hidden=[512, 256, 128], desc="BASELINE configs[2]: MLP [512,256,128] + batch norm, bf16 "
+                   "tensor-core GEMMs, 1M users x 200k items, dim 64, batch 16384, Adagrad"),
     "c4_linear": dict(net="linear", n_users=50_000_000, n_items=5_000_000, dim=128, n_cat=0, batch=16384,
                       opt="sparse_adam", lr=1e-3, desc="BASELINE configs[3]: linear 50M x 5M, dim 128, batch 16384/GPU"),
 }
@@ -54,6 +57,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2_fm", choices=sorted(WORKLOADS))
+    ap.add_argument("--users", type=int, default=0, help="override the workload's user count (memory-bound hosts)")
     ap.add_argument("--batch", type=int, default=0, help="override the workload's batch size")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -99,7 +103,8 @@ def cpu_reference(wl, steps, warmup, budget_s):
             break
         torch.set_num_threads(nt)
         torch.manual_seed(1234)
-        net = TP.make_net(wl["net"], wl["n_users"], wl["n_items"], metas, wl["dim"])
+        kw = dict(hidden=wl["hidden"], batch_norm=True) if wl["net"] == "mlp" else {}
+        net = TP.make_net(wl["net"], wl["n_users"], wl["n_items"], metas, wl["dim"], **kw)
         net.train()
         opt = TP.make_optimizer(wl["opt"], net, wl["lr"])
 
@@ -190,7 +195,7 @@ def algorithmic_bytes(wl, user, pos, neg, n_steps, B, S):
     and written once, embedding row (dim floats) and its width-1 companion.  From the actual batches."""
     import torch
     D, F = wl["dim"], 1 if wl["n_cat"] else 0
-    row_bytes = 4 * (D + 1) * (2 + 2 * S)
+    row_bytes = 4 * (D + (0 if wl["net"] == "mlp" else 1)) * (2 + 2 * S)  # MLP tables have no width-1 companion
     total = 0
     for s in range(n_steps):
         sl = slice(s * B, (s + 1) * B)
@@ -209,7 +214,8 @@ def gpu_bench(args, wl):
     from torchrecsys_b200 import _lib
     from torchrecsys_b200.collaborative.fm import FM
     from torchrecsys_b200.collaborative.linear import Linear
-    from torchrecsys_b200.engine import EpochRunner
+    from torchrecsys_b200.collaborative.mlp import MLP
+    from torchrecsys_b200.engine import EpochRunner, MlpEpochRunner
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -222,16 +228,21 @@ def gpu_bench(args, wl):
     F = 1 if wl["n_cat"] else 0
 
     torch.manual_seed(1234 + rank)
-    cls = FM if wl["net"] == "fm" else Linear
-    net = cls(wl["n_users"], wl["n_items"], {"product_category": wl["n_cat"]} if F else {}, wl["dim"],
-              use_metadata=bool(F), use_cuda=True).to(dev)
+    is_mlp = wl["net"] == "mlp"
+    if is_mlp:
+        net = MLP(wl["n_users"], wl["n_items"], {}, wl["dim"], use_metadata=False, use_batch_norm=True,
+                  hidden_layers=wl["hidden"], use_cuda=True).to(dev).train()
+    else:
+        cls = FM if wl["net"] == "fm" else Linear
+        net = cls(wl["n_users"], wl["n_items"], {"product_category": wl["n_cat"]} if F else {}, wl["dim"],
+                  use_metadata=bool(F), use_cuda=True).to(dev)
     if wl["opt"] == "sparse_adam":
         opt = torch.optim.SparseAdam(list(net.parameters()), lr=wl["lr"])
         S = 2
     else:
         opt = torch.optim.Adagrad(net.parameters(), lr=wl["lr"])
         S = 1
-    runner = EpochRunner(net, opt)
+    runner = (MlpEpochRunner if is_mlp else EpochRunner)(net, opt)
 
     n = (K + W) * B
     user_h, pos_h = synth_ids(wl, n, seed=1234 + rank)
@@ -294,11 +305,18 @@ def gpu_bench(args, wl):
     p0.record()
     plan = _lib.plan_build(model, epoch, dev)
     p1.record()
-    ws = _lib.train_workspace(model, epoch, dev)
     loss2 = torch.empty(K, device=dev)
-    k0.record()
-    _lib.train_steps(model, epoch, optim_c, plan, ws, 0, K, loss2)
-    k1.record()
+    if is_mlp:
+        mlp_c = net.abi_mlp(runner.grads, opt.state if b.keys[0] else None, b.keys[0])
+        ws = _lib.mlp_train_workspace(model, mlp_c, epoch, dev)
+        k0.record()
+        _lib.mlp_train_steps(model, mlp_c, epoch, optim_c, plan, ws, 0, K, loss2)
+        k1.record()
+    else:
+        ws = _lib.train_workspace(model, epoch, dev)
+        k0.record()
+        _lib.train_steps(model, epoch, optim_c, plan, ws, 0, K, loss2)
+        k1.record()
     torch.cuda.synchronize()
     advance_steps(opt, runner.params, b, K)
     kernel_ms, plan_ms = k0.elapsed_time(k1), p0.elapsed_time(p1)
@@ -329,6 +347,27 @@ def gpu_bench(args, wl):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "kernel": "trs::train_kernel (one persistent launch, K steps)",
+                "kernel_ms_per_step": kernel_ms / K, "plan_ms_per_step": plan_ms / K,
+                "algorithmic_bytes_per_step": alg_bytes / K,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650"}
+    if is_mlp:
+        # the tower's GEMMs bound this workload: 3 x 2 x MACs per row, 2 rows per sample
+        width, macs = wl["dim"] * 2, 0
+        for h in wl["hidden"]:
+            macs += width * h
+            width = h
+        flops_step = 3 * 2 * (macs + width) * 2 * B
+        tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        tach = flops_step * K / (kernel_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s", "frac": tach / tpeak,
+                    "kernel": "trs::gemm_tn_kernel (9 tcgen05 GEMMs per step) timed inside the whole fused step: "
+                              "every kernel of trs_mlp_train_steps is in the denominator",
+                    "kernel_ms_per_step": kernel_ms / K, "plan_ms_per_step": plan_ms / K,
+                    "algorithmic_flops_per_step": flops_step,
+                    "embedding_bytes_per_step": alg_bytes / K,
+                    "peak_source": "measured sustained bf16 (MEASURED_PEAKS.json)" if peaks else "fallback 1400"}
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
@@ -337,23 +376,21 @@ def gpu_bench(args, wl):
     out = {
         "metric": "train samples/sec (fwd+bwd+sparse update)", "value": world * K * B / (ms * 1e-3),
         "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if is_mlp else "f32", "data": "synthetic",
         "config": {"workload": wl["desc"], "name": args.workload, "batch_per_gpu": B, "global_batch": B * world,
                    "optimizer": wl["opt"], "l2": "inputs larger than L2: tables+optimizer state "
                    f"{(wl['n_users'] + wl['n_items']) * (wl['dim'] + 1) * 4 * (1 + S) / 1e9:.2f} GB, rows hit at random",
-                   "timed_region": "Philox negatives + sort plan + persistent fused train kernel, K steps in one launch",
+                   "timed_region": ("Philox negatives + sort plan + K fused MLP steps (one C call, ~40 kernels per step)"
+                                    if is_mlp else
+                                    "Philox negatives + sort plan + persistent fused train kernel, K steps in one launch"),
                    "parallelism": f"dp{world} (independent replicas)" if world > 1 else "single GPU",
                    "clock_ramp": "0.3 s of device copies before the warm-up steps", "mean_loss": mean_loss},
         "e2e": {"value": world * K * B / (e2e_ms * 1e-3), "unit": "samples/s",
                 "h2d_bytes_per_step": 16 * B, "d2h_bytes_per_step": 4,
                 "note": "user+positive ids from pinned host memory; metadata ids and negatives are derived on the device"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "trs::train_kernel (one persistent launch, K steps)",
-                     "kernel_ms_per_step": kernel_ms / K, "plan_ms_per_step": plan_ms / K,
-                     "algorithmic_bytes_per_step": alg_bytes / K,
-                     "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650"},
+        "roofline": dict(roofline, traffic=traffic),
         "clocks": clocks.summary(),
     }
     if world > 1:
@@ -366,6 +403,8 @@ def main():
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
         wl["batch"] = args.batch
+    if args.users:
+        wl["n_users"] = args.users
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
         if rank != 0:

@@ -167,9 +167,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float b = (g.bias && col0 + j < g.N) ? __ldg(g.bias + col0 + j) : 0.f;
-                v[j] = __uint_as_float(r[j]) + b;
+            for (int j = 0; j < 32; j += 4) {  // N % 8 == 0 and bias is a tensor base: 16-byte aligned
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g.bias && col0 + j < g.N) b = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + j));
+                v[j + 0] = __uint_as_float(r[j + 0]) + b.x;
+                v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
+                v[j + 2] = __uint_as_float(r[j + 2]) + b.z;
+                v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
             }
             if (row_in) {
                 if (OUT_BF16) {

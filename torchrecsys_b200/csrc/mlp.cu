@@ -59,6 +59,39 @@ __device__ __forceinline__ void st_bf8(bf16* p, const F8& x) {
     *reinterpret_cast<uint4*>(p) = u;
 }
 
+// the 8 per-column parameters a thread needs for its 16-byte chunk, as two 128-bit loads
+__device__ __forceinline__ F8 ld_f8(const float* p) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    F8 r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+
+// Sum over tiles [t0, t0+nt) of P[t*N + n] for the 32 columns n = blockIdx.x*32 + lane of a 1024-thread
+// block: warp w adds tiles w, w+32, ... (independent loads, one memory round trip for <= 128 tiles); the
+// 32 partials are then added in warp order (fixed association).  The result is valid in warp 0.
+constexpr int TS_WARPS = 32;
+__device__ __forceinline__ float block_tile_sum(const float* __restrict__ P, int t0, int nt, int N, int n,
+                                                float (*s)[33]) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float a = 0.f;
+    if (n < N) {
+#pragma unroll 4
+        for (int t = w; t < nt; t += TS_WARPS) a += P[(size_t)(t0 + t) * N + n];
+    }
+    s[w][lane] = a;
+    __syncthreads();
+    float r = 0.f;
+    if (w == 0) {
+#pragma unroll
+        for (int i = 0; i < TS_WARPS; ++i) r += s[i][lane];
+    }
+    __syncthreads();
+    return r;
+}
+
 // ---- fp32 -> bf16 copies of the layer weights (they change every step) ----------------------------
 struct CvtJobs {
     const float* src[TRS_MAX_LAYERS];
@@ -103,18 +136,16 @@ gather_concat_kernel(const __grid_constant__ trs_model m, const int64_t* __restr
 // ---- BatchNorm statistics from the GEMM epilogue's per-tile column sums -----------------------------
 // One thread per column; passes in order (pos, then neg), so the running statistics take the two
 // momentum updates in the reference's order (model.py:173-183 calls net.forward twice).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * TS_WARPS)
 bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int tiles_per_half, int halves,
                    int N, int n_valid, float* __restrict__ mean, float* __restrict__ rstd,
                    float* __restrict__ running_mean, float* __restrict__ running_var) {
-    const int n = blockIdx.x * 128 + threadIdx.x;
-    if (n >= N) return;
+    __shared__ float s_red[TS_WARPS][33];
+    const int n = blockIdx.x * 32 + (threadIdx.x & 31);
     for (int h = 0; h < halves; ++h) {
-        double S = 0.0, SS = 0.0;
-        for (int t = 0; t < tiles_per_half; ++t) {
-            S += (double)psum[(size_t)(h * tiles_per_half + t) * N + n];
-            SS += (double)psq[(size_t)(h * tiles_per_half + t) * N + n];
-        }
+        const double S = block_tile_sum(psum, h * tiles_per_half, tiles_per_half, N, n, s_red);
+        const double SS = block_tile_sum(psq, h * tiles_per_half, tiles_per_half, N, n, s_red);
+        if (threadIdx.x >= 32 || n >= N) continue;
         const double mu = S / n_valid;
         double var = SS / n_valid - mu * mu;
         var = var > 0.0 ? var : 0.0;
@@ -137,30 +168,45 @@ bn_eval_stats_kernel(const float* __restrict__ running_mean, const float* __rest
 }
 
 // ---- X_{l+1} = relu(BN(Z_l)) --------------------------------------------------------------------------
+// CTA = 128 rows (one pass: Bp is a multiple of 128) x 64 columns; thread = 8 columns x 4 rows, its column
+// parameters held in registers.
 __global__ void __launch_bounds__(EW_THREADS)
 bn_relu_kernel(const bf16* __restrict__ Z, bf16* __restrict__ A, const float* __restrict__ mean,
                const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                int R, int N, int Bp, int B, int use_bn) {
-    const int cpr = N / 8;
-    const long long total = (long long)R * cpr;
-    for (long long idx = (long long)blockIdx.x * EW_THREADS + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * EW_THREADS) {
-        const int r = (int)(idx / cpr), c = (int)(idx % cpr) * 8;
-        const int h = r / Bp;
-        F8 y;
+    const int c8 = threadIdx.x & 7, rg = threadIdx.x >> 3;
+    const int c = blockIdx.y * 64 + c8 * 8;
+    if (c >= N) return;
+    const int h = (blockIdx.x * 128) / Bp;
+    F8 mu, rs, ga, be;
+    if (use_bn) {
+        mu = ld_f8(mean + h * N + c);
+        rs = ld_f8(rstd + h * N + c);
+        ga = ld_f8(gamma + c);
+        be = ld_f8(beta + c);
+    }
+    F8 y[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = blockIdx.x * 128 + rg + 32 * i;
+        if (r < R && (r % Bp) < B) y[i] = ld_bf8(Z + (size_t)r * N + c);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = blockIdx.x * 128 + rg + 32 * i;
+        if (r >= R) continue;
         if ((r % Bp) < B) {
-            y = ld_bf8(Z + (size_t)r * N + c);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                float t = y.v[j];
-                if (use_bn) t = (t - mean[h * N + c + j]) * rstd[h * N + c + j] * gamma[c + j] + beta[c + j];
-                y.v[j] = fmaxf(t, 0.f);
+                float t = y[i].v[j];
+                if (use_bn) t = (t - mu.v[j]) * rs.v[j] * ga.v[j] + be.v[j];
+                y[i].v[j] = fmaxf(t, 0.f);
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) y.v[j] = 0.f;
+            for (int j = 0; j < 8; ++j) y[i].v[j] = 0.f;
         }
-        st_bf8(A + (size_t)r * N + c, y);
+        st_bf8(A + (size_t)r * N + c, y[i]);
     }
 }
 
@@ -231,21 +277,36 @@ struct BwdIn {
     const float* rstd;
     int R, N, Bp, B, use_bn;
 };
+// column parameters of a thread's 8 columns (pass h): loaded once, before its rows
+struct BwdCols {
+    F8 mu, rs, wo;
+};
 template <bool FROM_DS>
-__device__ __forceinline__ void bwd_load(const BwdIn& in, int r, int c, int h, F8& dy, F8& xhat, F8& a, float& dsr) {
+__device__ __forceinline__ BwdCols bwd_cols(const BwdIn& in, int c, int h) {
+    BwdCols k;
+    if (in.use_bn) {
+        k.mu = ld_f8(in.mean + h * in.N + c);
+        k.rs = ld_f8(in.rstd + h * in.N + c);
+    }
+    if (FROM_DS) k.wo = ld_f8(in.w_out + c);
+    return k;
+}
+template <bool FROM_DS>
+__device__ __forceinline__ void bwd_load(const BwdIn& in, const BwdCols& k, int r, int c, F8& dy, F8& xhat, F8& a,
+                                         float& dsr) {
     a = ld_bf8(in.A + (size_t)r * in.N + c);
     F8 da;
     if (FROM_DS) {
         dsr = in.ds[r];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) da.v[j] = dsr * __ldg(in.w_out + c + j);
+        for (int j = 0; j < 8; ++j) da.v[j] = dsr * k.wo.v[j];
     } else {
         da = ld_bf8(in.dA + (size_t)r * in.N + c);
     }
     if (in.use_bn) {
         const F8 z = ld_bf8(in.Z + (size_t)r * in.N + c);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) xhat.v[j] = (z.v[j] - in.mean[h * in.N + c + j]) * in.rstd[h * in.N + c + j];
+        for (int j = 0; j < 8; ++j) xhat.v[j] = (z.v[j] - k.mu.v[j]) * k.rs.v[j];
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) dy.v[j] = a.v[j] > 0.f ? da.v[j] : 0.f;
@@ -263,13 +324,14 @@ bn_bwd_reduce_kernel(const __grid_constant__ BwdIn in, float* __restrict__ P1, f
 #pragma unroll
     for (int j = 0; j < 8; ++j) a1[j] = a2[j] = a3[j] = 0.f;
     if (c < in.N) {
+        const BwdCols cols = bwd_cols<FROM_DS>(in, c, h);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int r = blockIdx.x * 128 + rg + 32 * i;
             if (r < in.R && (r % in.Bp) < in.B) {
                 F8 dy, xhat, a;
                 float dsr = 0.f;
-                bwd_load<FROM_DS>(in, r, c, h, dy, xhat, a, dsr);
+                bwd_load<FROM_DS>(in, cols, r, c, dy, xhat, a, dsr);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     a1[j] += dy.v[j];
@@ -298,20 +360,19 @@ bn_bwd_reduce_kernel(const __grid_constant__ BwdIn in, float* __restrict__ P1, f
     }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * TS_WARPS)
 bn_bwd_finalize_kernel(const float* __restrict__ P1, const float* __restrict__ P2, const float* __restrict__ P3,
                        int tiles_per_half, int N, float* __restrict__ S1, float* __restrict__ S2,
                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw_out) {
-    const int n = blockIdx.x * 128 + threadIdx.x;
-    if (n >= N) return;
+    __shared__ float s_red[TS_WARPS][33];
+    const int n = blockIdx.x * 32 + (threadIdx.x & 31);
     float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f}, s3 = 0.f;
-    for (int h = 0; h < 2; ++h)
-        for (int t = 0; t < tiles_per_half; ++t) {
-            const size_t i = (size_t)(h * tiles_per_half + t) * N + n;
-            s1[h] += P1[i];
-            if (P2) s2[h] += P2[i];
-            if (P3) s3 += P3[i];
-        }
+    for (int h = 0; h < 2; ++h) {
+        s1[h] = block_tile_sum(P1, h * tiles_per_half, tiles_per_half, N, n, s_red);
+        if (P2) s2[h] = block_tile_sum(P2, h * tiles_per_half, tiles_per_half, N, n, s_red);
+    }
+    if (P3) s3 = block_tile_sum(P3, 0, 2 * tiles_per_half, N, n, s_red);
+    if (threadIdx.x >= 32 || n >= N) return;
     S1[n] = s1[0];
     S1[N + n] = s1[1];
     S2[n] = s2[0];
@@ -334,6 +395,19 @@ bn_bwd_apply_kernel(const __grid_constant__ BwdIn in, const float* __restrict__ 
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     if (c < in.N) {
+        const BwdCols cols = bwd_cols<FROM_DS>(in, c, h);
+        F8 ga, m1, m2;  // gamma*rstd, mean(dy), mean(dy*xhat) of the thread's columns
+        if (in.use_bn) {
+            ga = ld_f8(gamma + c);
+            m1 = ld_f8(S1 + h * in.N + c);
+            m2 = ld_f8(S2 + h * in.N + c);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                ga.v[j] *= cols.rs.v[j];
+                m1.v[j] *= invB;
+                m2.v[j] *= invB;
+            }
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int r = blockIdx.x * 128 + rg + 32 * i;
@@ -342,14 +416,11 @@ bn_bwd_apply_kernel(const __grid_constant__ BwdIn in, const float* __restrict__ 
             if ((r % in.Bp) < in.B) {
                 F8 dy, xhat, a;
                 float dsr;
-                bwd_load<FROM_DS>(in, r, c, h, dy, xhat, a, dsr);
+                bwd_load<FROM_DS>(in, cols, r, c, dy, xhat, a, dsr);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float t = dy.v[j];
-                    if (in.use_bn) {
-                        const int n = h * in.N + c + j;
-                        t = gamma[c + j] * in.rstd[n] * (t - S1[n] * invB - xhat.v[j] * (S2[n] * invB));
-                    }
+                    if (in.use_bn) t = ga.v[j] * (t - m1.v[j] - xhat.v[j] * m2.v[j]);
                     dz.v[j] = t;
                     acc[j] += t;
                 }
@@ -369,6 +440,15 @@ bn_bwd_apply_kernel(const __grid_constant__ BwdIn in, const float* __restrict__ 
         for (int g = 0; g < 32; ++g) t += s_red[g][threadIdx.x];
         Pdb[(size_t)blockIdx.x * in.N + blockIdx.y * 64 + threadIdx.x] = t;
     }
+}
+
+// out[n] = sum over the T row tiles of P[t, n] (db)
+__global__ void __launch_bounds__(32 * TS_WARPS)
+colsum_tiles_kernel(const float* __restrict__ P, int T, int N, float* __restrict__ out) {
+    __shared__ float s_red[TS_WARPS][33];
+    const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+    const float r = block_tile_sum(P, 0, T, N, n, s_red);
+    if (threadIdx.x < 32 && n < N) out[n] = r;
 }
 
 // out[i] = sum_p part[p*stride + i], p in order (split-K partials of dW; per-tile partials of db)
@@ -574,14 +654,14 @@ static int mlp_forward_layers(const trs_mlp* mlp, const MlpLayout& L, char* W, i
         float* mean = (float*)(W + L.mean[l]);
         float* rstd = (float*)(W + L.rstd[l]);
         if (stats) {
-            bn_finalize_kernel<<<(N + 127) / 128, 128, 0, st>>>(g.col_sum, g.col_sumsq, L.T / halves, halves, N, n_valid,
+            bn_finalize_kernel<<<(N + 31) / 32, 32 * TS_WARPS, 0, st>>>(g.col_sum, g.col_sumsq, L.T / halves, halves, N, n_valid,
                                                                 mean, rstd, update_running ? mlp->running_mean[l] : nullptr,
                                                                 update_running ? mlp->running_var[l] : nullptr);
         } else if (mlp->use_bn) {
             bn_eval_stats_kernel<<<(N + 127) / 128, 128, 0, st>>>(mlp->running_mean[l], mlp->running_var[l], N, mean, rstd);
         }
         // eval mode: one (mean, rstd) row shared by all rows -> present it as a single "pass" of R rows
-        bn_relu_kernel<<<ew_grid((long long)L.R * N / 8), EW_THREADS, 0, st>>>(
+        bn_relu_kernel<<<dim3(L.T, (N + 63) / 64), EW_THREADS, 0, st>>>(
             (const bf16*)(W + L.Z[l]), (bf16*)(W + L.A[l]), mean, rstd, mlp->gamma[l], mlp->beta[l], L.R, N,
             stats ? L.Bp : L.R, stats ? n_valid : L.R, mlp->use_bn);
     }
@@ -716,7 +796,7 @@ extern "C" int trs_mlp_train_steps(const trs_model* model, const trs_mlp* mlp, c
                 bn_bwd_reduce_kernel<false><<<tg, EW_THREADS, 0, st>>>(in, P1, P2, nullptr);
             }
             if (l == last || mlp->use_bn)
-                bn_bwd_finalize_kernel<<<(N + 127) / 128, 128, 0, st>>>(
+                bn_bwd_finalize_kernel<<<(N + 31) / 32, 32 * TS_WARPS, 0, st>>>(
                     P1, mlp->use_bn ? P2 : nullptr, l == last ? P3 : nullptr, L.T / 2, N, S1, S2,
                     mlp->use_bn ? mlp->dgamma[l] : nullptr, mlp->use_bn ? mlp->dbeta[l] : nullptr,
                     l == last ? mlp->dw_out : nullptr);
@@ -724,7 +804,7 @@ extern "C" int trs_mlp_train_steps(const trs_model* model, const trs_mlp* mlp, c
                 bn_bwd_apply_kernel<true><<<tg, EW_THREADS, 0, st>>>(in, mlp->gamma[l], S1, S2, (bf16*)(W + L.G[l]), Pdb);
             else
                 bn_bwd_apply_kernel<false><<<tg, EW_THREADS, 0, st>>>(in, mlp->gamma[l], S1, S2, (bf16*)(W + L.G[l]), Pdb);
-            reduce_partials_kernel<<<ew_grid(N), EW_THREADS, 0, st>>>(Pdb, L.T, N, N, mlp->db[l]);
+            colsum_tiles_kernel<<<(N + 31) / 32, 32 * TS_WARPS, 0, st>>>(Pdb, L.T, N, mlp->db[l]);
             // wgrad: dW_l[out, in] = sum_r dZ_l[r, out] * X_l[r, in]
             trs_gemm_args g = {};
             g.a = W + L.G[l];
