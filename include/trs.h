@@ -234,6 +234,21 @@ int trs_mlp_train_steps(const trs_model* model, const trs_mlp* mlp, const trs_ep
                         const trs_optim* optim, const void* plan, void* workspace, size_t workspace_bytes,
                         int first_step, int n_steps, float* loss, trs_stream_t stream);
 
+/* ---- a11: predict (model.py:341-452) batched over users: top-k items per user against ALL items ------ */
+/* For each query user users[q]: out_idx[q, 0..k) = item ids (+ item_offset) of the k best scores, best
+ * first, ties broken towards the lower item id (== torch.sort(stable=True, descending=True) on the
+ * scores trs_scores returns); out_score[q, :] those fp32 scores.  Phase 1 scores user tiles against every
+ * item on the tcgen05 tensor cores (bf16) with the top-k filter fused into the epilogue and keeps a
+ * provable superset of the exact top-k; phase 2 re-scores the survivors in fp32 (csrc/topk.cu).
+ * overflow[q] != 0 marks a user whose candidate superset did not fit (e.g. thousands of tied, saturated
+ * FM scores): its output row is invalid and the caller must rank that user with trs_scores + sort.
+ * item_meta ([n_items, n_meta], NULL without metadata) gives every item's metadata ids.
+ * Linear and FM only (the MLP tower does not factorise into user x item). 1 <= k <= 128. */
+size_t trs_predict_topk_workspace_bytes(const trs_model* model, int64_t n_query, int k);
+int trs_predict_topk(const trs_model* model, const int64_t* users, int64_t n_query, const int64_t* item_meta,
+                     int k, int64_t item_offset, int64_t* out_idx, float* out_score, int32_t* overflow,
+                     void* workspace, size_t workspace_bytes, trs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

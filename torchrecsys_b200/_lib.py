@@ -23,7 +23,8 @@ SYMBOLS = [
     "trs_philox_negatives", "trs_validate_ids", "trs_plan_bytes", "trs_plan_tmp_bytes",
     "trs_plan_build", "trs_train_workspace_bytes", "trs_train_steps", "trs_eval_pairwise",
     "trs_gemm_bf16_tn", "trs_mlp_forward_workspace_bytes", "trs_mlp_forward",
-    "trs_mlp_train_workspace_bytes", "trs_mlp_train_steps",
+    "trs_mlp_train_workspace_bytes", "trs_mlp_train_steps", "trs_predict_topk_workspace_bytes",
+    "trs_predict_topk",
 ]
 
 
@@ -278,3 +279,27 @@ def mlp_train_steps(model: Model, mlp: Mlp, epoch: Epoch, optim: Optim, plan, wo
                                      C.c_void_p(plan.data_ptr()), C.c_void_p(workspace.data_ptr()),
                                      C.c_size_t(workspace.numel()), first_step, n_steps,
                                      C.c_void_p(_ptr(loss_out, torch.float32)), _stream()))
+
+
+def predict_topk(model: Model, users, k: int, item_meta=None, item_offset: int = 0):
+    """Top-k items for each user id in ``users`` against all items of ``model.item``.
+    Returns (idx int64 [n, k], score fp32 [n, k], overflow int32 [n])."""
+    L = lib()
+    L.trs_predict_topk_workspace_bytes.restype = C.c_size_t
+    n = users.shape[0]
+    dev = users.device
+    idx = torch.empty((n, k), dtype=torch.int64, device=dev)
+    score = torch.empty((n, k), dtype=torch.float32, device=dev)
+    over = torch.empty(n, dtype=torch.int32, device=dev)
+    if n == 0:
+        return idx, score, over
+    nbytes = L.trs_predict_topk_workspace_bytes(C.byref(model), C.c_int64(n), k)
+    if nbytes == 0:
+        raise RuntimeError(f"libtrs_b200: {L.trs_last_error().decode()}")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _check(L.trs_predict_topk(C.byref(model), C.c_void_p(_ptr(users, torch.int64)), C.c_int64(n),
+                              C.c_void_p(_ptr(item_meta, torch.int64)), k, C.c_int64(item_offset),
+                              C.c_void_p(idx.data_ptr()), C.c_void_p(score.data_ptr()),
+                              C.c_void_p(over.data_ptr()), C.c_void_p(ws.data_ptr()),
+                              C.c_size_t(nbytes), _stream()))
+    return idx, score, over

@@ -84,4 +84,15 @@ __device__ __forceinline__ float fm_logit(const trs_model& m, int nch, int gl,
     return lin + pair;
 }
 
+// one (user, item[, meta]) score exactly as trs_scores computes it (Linear: raw score; FM: sigmoid)
+template <int NET, int V, int G, int IT>
+__device__ __forceinline__ float score_one(const trs_model& m, int nch, int gl, int64_t u,
+                                           int64_t it, const int64_t* meta) {
+    Row<V, IT> ru = load_row<V, G, IT>(m.user.emb + (size_t)u * m.dim, nch, gl);
+    float bu = m.user.lin ? m.user.lin[u] : 0.f;
+    Row<V, IT> a, b;
+    if (NET == TRS_NET_LINEAR) return linear_score<V, G, IT>(m, nch, gl, ru, bu, it, meta, a);
+    return sigmoidf_acc(fm_logit<V, G, IT>(m, nch, gl, ru, bu, it, meta, a, b));
+}
+
 }  // namespace trs

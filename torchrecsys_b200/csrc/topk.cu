@@ -1,0 +1,533 @@
+// topk.cu -- batched predict (reference model.py:341-452: score one user against every item, sort, keep
+// top_k) as a user-tile x all-items score GEMM on the tcgen05 tensor cores with the top-k selection fused
+// into the epilogue, followed by an exact fp32 re-scoring of the surviving candidates.
+//
+// Why two phases: the reference ranks fp32 scores; tensor cores multiply bf16.  Phase 1 therefore only
+// has to produce, per user, a SUPERSET of the exact top-k:
+//   |s_bf16(u,i) - s_exact(u,i)| <= eps_u := 2^-7 (1+2^-9) * |[u,1]| * max_i |[w_i,c_i]|   (Cauchy-Schwarz)
+//   so every exact top-k item has s_bf16 >= tau_k - 2 eps_u, tau_k = the k-th best bf16 score seen.
+// Phase 2 recomputes the candidates' scores with the same fp32 code path as trs_scores and ranks them by
+// (score descending, item id ascending) == torch.sort(stable=True, descending=True) on the reference's
+// scores, so the returned indices are those of the fp32 path, tie-break "lower item id first".
+//
+// Phase 1 operands (prepared once per call):  Ub[q,:] = bf16([u_q, 1, 0..]),  Vb[i,:] = bf16([w_i, c_i, 0..])
+//   Linear: w_i = item_i + sum_f meta_f(i)   c_i = item_bias_i                      (linear.py:64-78)
+//   FM    : w_i = item_i + sum_f meta_f(i)   c_i = lin_item_i + sum_f lin_meta_f(i)
+//                                                  + 1/2 sum_d [w_id^2 - item_id^2 - sum_f meta_f(i)_d^2]
+//           so that z(u,i) = lin_user_u + <[u,1],[w_i,c_i]> is the FM logit (fm.py:81-97) and the score is
+//           sigmoid(z), monotone in z.
+// Kernel: CTA = 128 users (A tile resident in shared memory) x a range of 128-item tiles streamed by TMA
+// through a ring; accumulators double-buffered in TMEM (2 x 128 columns) so the tensor core computes tile
+// t+1 while the four epilogue warps filter tile t: thread = user row, one compare per score against the
+// row's running threshold, survivors appended to the row's candidate list in global memory.  When a list
+// nears its capacity the warp compacts its 32 rows (warp-parallel k-th-largest by bisection on the float
+// bit pattern) and raises the thresholds.
+#include "scorer.cuh"
+#include "tc.cuh"
+
+namespace trs {
+
+typedef __nv_bfloat16 bf16;
+constexpr int TK_BM = 128, TK_BN = 128, TK_CAP = 512, TK_THREADS = 192, TK_BOX_BYTES = 128 * 128;
+constexpr int TK_MAX_SPLITS = 8;
+constexpr int TK_MAX_STAGE2 = 4096;  // candidates one user may bring to phase 2 (>= TK_MAX_SPLITS * TK_CAP)
+
+struct TopkDev {
+    int n_query, n_items, nbox, kslices, stages;
+    int n_item_tiles, tiles_per_split, splits;
+    int k, fm;
+    const float* unorm;   // [n_query] |[u,1]|
+    const float* ulin;    // [n_query] lin_user (FM) or 0
+    const float* vmax2;   // [1] max_i |[w_i,c_i]|^2
+    float* cand_s;        // [n_query, splits, TK_CAP]
+    int* cand_i;
+    int* cand_cnt;        // [n_query, splits]
+    int* overflow;        // [n_query]
+};
+
+__device__ __forceinline__ uint32_t float_key(float x) {  // order-preserving map float -> uint32
+    const uint32_t b = __float_as_uint(x);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// warp-cooperative compaction of one row's candidate list; returns the new count, sets thr
+__device__ __forceinline__ int compact_row(float* __restrict__ cs, int* __restrict__ ci, int n, int k, float margin2,
+                                           float ulin, int fm, int lane, float& thr_out) {
+    constexpr int PER = TK_CAP / 32;
+    float e[PER];
+    int id[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int slot = i * 32 + lane;
+        e[i] = slot < n ? cs[slot] : -INFINITY;
+        id[i] = slot < n ? ci[slot] : 0;
+    }
+    float keep = -INFINITY;
+    if (n >= k) {
+        // largest T with #{key >= T} >= k  ==  key of the k-th largest score
+        uint32_t lo = 0u, hi = 0xffffffffu;
+        uint32_t key[PER];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) key[i] = (i * 32 + lane < n) ? float_key(e[i]) : 0u;
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1) + 1u;  // upper middle: lo < mid <= hi
+            int c = 0;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) c += (key[i] >= mid) ? 1 : 0;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (c >= k) lo = mid;
+            else hi = mid - 1u;
+        }
+        const float tau = key_float(lo);
+        float margin = margin2;
+        if (fm) {
+            // distinct logits whose fp32 sigmoids coincide are ties the final ranking breaks by item id:
+            // widen by the logit interval one ulp of sigmoid(tau) spans (inf once the sigmoid saturates)
+            const float s = 1.0f / (1.0f + expf(-(tau + ulin)));
+            const float d = s * (1.0f - s);
+            margin += (d > 1e-30f) ? 1.2e-7f * fmaxf(s, 1e-30f) / d : INFINITY;
+        }
+        keep = tau - margin;
+    }
+    __syncwarp();
+    int base = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const bool p = (i * 32 + lane < n) && (e[i] >= keep);
+        const unsigned bal = __ballot_sync(0xffffffffu, p);
+        if (p) {
+            const int pos = base + __popc(bal & ((1u << lane) - 1u));
+            cs[pos] = e[i];
+            ci[pos] = id[i];
+        }
+        base += __popc(bal);
+    }
+    __syncwarp();
+    thr_out = keep;
+    return base;
+}
+
+__global__ void __launch_bounds__(TK_THREADS, 1)
+topk_score_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_v,
+                  const __grid_constant__ TopkDev g) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* sA = base;
+    unsigned char* sB = base + g.nbox * TK_BOX_BYTES;
+    uint64_t* bars = (uint64_t*)(sB + g.stages * g.nbox * TK_BOX_BYTES);
+    uint64_t* a_full = bars;
+    uint64_t* full = bars + 1;
+    uint64_t* empty = full + g.stages;
+    uint64_t* acc_full = empty + g.stages;   // [2]
+    uint64_t* acc_empty = acc_full + 2;       // [2]
+    uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int u0 = blockIdx.x * TK_BM;
+    const int split = blockIdx.y;
+    const int tile0 = split * g.tiles_per_split;
+    const int ntiles = min(g.tiles_per_split, g.n_item_tiles - tile0);
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmap_u);
+        tc::tma_prefetch_desc(&tmap_v);
+        tc::mbar_init(a_full, 1);
+        for (int s = 0; s < g.stages; ++s) {
+            tc::mbar_init(&full[s], 1);
+            tc::mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            tc::mbar_init(&acc_full[b], 1);
+            tc::mbar_init(&acc_empty[b], 4);  // one arrival per epilogue warp
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, 2 * TK_BN);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tc::mbar_arrive_expect_tx(a_full, g.nbox * TK_BOX_BYTES);
+            for (int b = 0; b < g.nbox; ++b) tc::tma_load_2d(sA + b * TK_BOX_BYTES, &tmap_u, a_full, b * 64, u0);
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % g.stages;
+                const uint32_t ph = (uint32_t)(t / g.stages) & 1u;
+                tc::mbar_wait(&empty[s], ph ^ 1u);
+                tc::mbar_arrive_expect_tx(&full[s], g.nbox * TK_BOX_BYTES);
+                for (int b = 0; b < g.nbox; ++b)
+                    tc::tma_load_2d(sB + (s * g.nbox + b) * TK_BOX_BYTES, &tmap_v, &full[s], b * 64, (tile0 + t) * TK_BN);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::idesc_bf16_f32(TK_BM, TK_BN);
+            tc::mbar_wait(a_full, 0);
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % g.stages;
+                const uint32_t ph = (uint32_t)(t / g.stages) & 1u;
+                const int buf = t & 1;
+                const uint32_t bph = (uint32_t)(t >> 1) & 1u;
+                tc::mbar_wait(&acc_empty[buf], bph ^ 1u);
+                tc::mbar_wait(&full[s], ph);
+                tc::tc_fence_after();
+                for (int ks = 0; ks < g.kslices; ++ks) {
+                    const int box = ks >> 2, kin = (ks & 3) * 16;
+                    const uint64_t da = tc::smem_desc_sw128(sA + box * TK_BOX_BYTES, kin);
+                    const uint64_t db = tc::smem_desc_sw128(sB + (s * g.nbox + box) * TK_BOX_BYTES, kin);
+                    tc::umma_bf16(tmem + (uint32_t)(buf * TK_BN), da, db, idesc, ks ? 1u : 0u);
+                }
+                tc::umma_commit(&empty[s]);
+                tc::umma_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = u0 + q * 32 + lane;
+        const bool valid = row < g.n_query;
+        const size_t lst = ((size_t)(valid ? row : 0) * g.splits + split) * TK_CAP;
+        float* cs = g.cand_s + lst;
+        int* ci = g.cand_i + lst;
+        const float vmax = sqrtf(__ldg(g.vmax2));
+        const float margin2 = valid ? 0.015625f * 1.004f * __ldg(g.unorm + row) * vmax : 0.f;
+        const float ulin = valid ? __ldg(g.ulin + row) : 0.f;
+        int cnt = 0;
+        float thr = -INFINITY;
+        bool over = false;
+        for (int t = 0; t < ntiles; ++t) {
+            const int buf = t & 1;
+            const uint32_t bph = (uint32_t)(t >> 1) & 1u;
+            tc::mbar_wait(&acc_full[buf], bph);
+            tc::tc_fence_after();
+            const int item0 = (tile0 + t) * TK_BN;
+            const int ncols = min(TK_BN, g.n_items - item0);
+#pragma unroll 1
+            for (int c = 0; c < TK_BN / 32; ++c) {
+                uint32_t r[32];
+                tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TK_BN + c * 32), r);
+                tc::tmem_ld_wait();
+                if (c == TK_BN / 32 - 1) {  // this warp is done with the TMEM buffer
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+                }
+                if (valid && !over) {
+                    const int lim = ncols - c * 32;  // columns of this chunk that are real items
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float v = __uint_as_float(r[j]);
+                        if (v >= thr && j < lim) {
+                            if (cnt < TK_CAP) {
+                                cs[cnt] = v;
+                                ci[cnt] = item0 + c * 32 + j;
+                            }
+                            ++cnt;
+                        }
+                    }
+                }
+            }
+            // a list that could overflow on the next tile -> the warp compacts all of its rows; after the
+            // last tile every list is compacted once more, so phase 2 only sees scores >= tau_k - margin
+            if (__any_sync(0xffffffffu, cnt > TK_CAP - TK_BN || (t == ntiles - 1 && cnt > g.k))) {
+                __syncwarp();
+                for (int rr = 0; rr < 32; ++rr) {
+                    const int n_r = __shfl_sync(0xffffffffu, cnt, rr);
+                    const int row_r = u0 + q * 32 + rr;
+                    if (row_r >= g.n_query || n_r == 0) continue;
+                    const float m_r = __shfl_sync(0xffffffffu, margin2, rr);
+                    const float ul_r = __shfl_sync(0xffffffffu, ulin, rr);
+                    const size_t l_r = ((size_t)row_r * g.splits + split) * TK_CAP;
+                    float thr_r;
+                    const int new_n = compact_row(g.cand_s + l_r, g.cand_i + l_r, min(n_r, TK_CAP), g.k, m_r, ul_r, g.fm,
+                                                  lane, thr_r);
+                    if (lane == rr) {
+                        if (n_r > TK_CAP || new_n > TK_CAP - TK_BN) {
+                            // the margin admits more candidates than a list holds: this user takes the
+                            // exact fp32 path on the host side (trs_scores + sort)
+                            over = true;
+                            g.overflow[row] = 1;
+                        }
+                        cnt = over ? 0 : new_n;
+                        thr = thr_r;
+                    }
+                }
+            }
+        }
+        if (valid) g.cand_cnt[(size_t)row * g.splits + split] = over ? 0 : min(cnt, TK_CAP);
+        if (valid && cnt > TK_CAP) g.overflow[row] = 1;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem, 2 * TK_BN);
+    }
+}
+
+// ---- operand preparation ------------------------------------------------------------------------------
+// one warp per item: Vb[i] = bf16([w_i, c_i, 0...]) and max |[w_i, c_i]|^2
+__global__ void __launch_bounds__(256)
+topk_prep_items_kernel(const __grid_constant__ trs_model m, const int64_t* __restrict__ item_meta, int64_t n_items,
+                       int Kp, bf16* __restrict__ Vb, unsigned* __restrict__ vmax2_bits) {
+    const int lane = threadIdx.x & 31;
+    const int D = m.dim, F = m.n_meta;
+    float wmax = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < n_items; i += (int64_t)gridDim.x * 8) {
+        float c = m.item.lin ? m.item.lin[i] : 0.f;
+        float half = 0.f, n2 = 0.f;
+        for (int d = lane; d < Kp; d += 32) {
+            float w = 0.f;
+            if (d < D) {
+                const float v = m.item.emb[(size_t)i * D + d];
+                w = v;
+                float q = v * v;
+                for (int f = 0; f < F; ++f) {
+                    const float e = m.meta[f].emb[(size_t)item_meta[i * F + f] * D + d];
+                    w += e;
+                    q = fmaf(e, e, q);
+                }
+                half += w * w - q;
+                n2 = fmaf(w, w, n2);
+                Vb[(size_t)i * Kp + d] = __float2bfloat16_rn(w);
+            } else if (d > D) {
+                Vb[(size_t)i * Kp + d] = __float2bfloat16_rn(0.f);
+            }
+        }
+        half = warp_sum(half);
+        n2 = warp_sum(n2);
+        if (m.net == TRS_NET_FM) {
+            for (int f = 0; f < F; ++f)
+                if (m.meta[f].lin) c += m.meta[f].lin[item_meta[i * F + f]];
+            c += 0.5f * half;
+        }
+        if (lane == 0) Vb[(size_t)i * Kp + D] = __float2bfloat16_rn(c);
+        wmax = fmaxf(wmax, n2 + c * c);
+    }
+    if (lane == 0) atomicMax(vmax2_bits, __float_as_uint(wmax));  // non-negative floats order like their bits
+}
+
+// one warp per query user: Ub[q] = bf16([u, 1, 0...]), |[u,1]|, lin_user
+__global__ void __launch_bounds__(256)
+topk_prep_users_kernel(const __grid_constant__ trs_model m, const int64_t* __restrict__ users, int n_query, int Kp,
+                       bf16* __restrict__ Ub, float* __restrict__ unorm, float* __restrict__ ulin) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (q >= n_query) return;
+    const int D = m.dim;
+    const int64_t u = users[q];
+    float n2 = 0.f;
+    for (int d = lane; d < Kp; d += 32) {
+        float v = d < D ? m.user.emb[(size_t)u * D + d] : (d == D ? 1.0f : 0.f);
+        n2 = fmaf(v, v, n2);
+        Ub[(size_t)q * Kp + d] = __float2bfloat16_rn(v);
+    }
+    n2 = warp_sum(n2);
+    if (lane == 0) {
+        unorm[q] = sqrtf(n2);
+        ulin[q] = (m.net == TRS_NET_FM && m.user.lin) ? m.user.lin[u] : 0.f;
+    }
+}
+
+// ---- phase 2: exact fp32 scores of the candidates, rank, write the top k ------------------------------------
+template <int NET, int V, int G, int IT>
+__global__ void __launch_bounds__(128)
+topk_rescore_kernel(const __grid_constant__ trs_model m, const int64_t* __restrict__ users,
+                    const int64_t* __restrict__ item_meta, const __grid_constant__ TopkDev g, int64_t item_offset,
+                    int64_t* __restrict__ out_idx, float* __restrict__ out_score) {
+    __shared__ float s_score[TK_MAX_STAGE2];
+    __shared__ int s_idx[TK_MAX_STAGE2];
+    __shared__ int s_n;
+    const int q = blockIdx.x;
+    const int64_t u = users[q];
+    // gather the split lists (thread 0 computes the offsets; lists are short)
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int sp = 0; sp < g.splits; ++sp) n += g.cand_cnt[(size_t)q * g.splits + sp];
+        if (n > TK_MAX_STAGE2) {
+            g.overflow[q] = 1;
+            n = 0;
+        }
+        if (g.overflow[q]) n = 0;
+        s_n = n;
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n > 0) {
+        int off = 0;
+        for (int sp = 0; sp < g.splits; ++sp) {
+            const int c = g.cand_cnt[(size_t)q * g.splits + sp];
+            const int* src = g.cand_i + ((size_t)q * g.splits + sp) * TK_CAP;
+            for (int j = threadIdx.x; j < c; j += 128) s_idx[off + j] = src[j];
+            off += c;
+        }
+    }
+    __syncthreads();
+    // exact scores: one row group per candidate, warp-uniform trip count
+    const int nch = m.dim / V, gl = threadIdx.x % G;
+    constexpr int GPB = 128 / G, GPW = 32 / G;
+    const int sub = (threadIdx.x / G) % GPW;
+    for (int j0 = threadIdx.x / G - sub; j0 < n; j0 += GPB) {
+        const bool ok = j0 + sub < n;
+        const int j = ok ? j0 + sub : n - 1;
+        const int64_t it = s_idx[j];
+        const float s = score_one<NET, V, G, IT>(m, nch, gl, u, it, item_meta ? item_meta + it * m.n_meta : nullptr);
+        if (gl == 0 && ok) s_score[j] = s;
+    }
+    __syncthreads();
+    // rank by (score desc, item id asc): a strict total order, so ranks are distinct
+    for (int j = threadIdx.x; j < n; j += 128) {
+        const float s = s_score[j];
+        const int id = s_idx[j];
+        int rank = 0;
+        for (int o = 0; o < n; ++o) {
+            const float so = s_score[o];
+            rank += (so > s || (so == s && s_idx[o] < id)) ? 1 : 0;
+        }
+        if (rank < g.k) {
+            out_idx[(size_t)q * g.k + rank] = (int64_t)id + item_offset;
+            out_score[(size_t)q * g.k + rank] = s;
+        }
+    }
+    for (int r = n + threadIdx.x; r < g.k; r += 128) {  // fewer candidates than k (n_items < k) or overflow
+        out_idx[(size_t)q * g.k + r] = -1;
+        out_score[(size_t)q * g.k + r] = -INFINITY;
+    }
+}
+
+template <int V, int G, int IT>
+static void launch_rescore(const trs_model* m, const int64_t* users, const int64_t* item_meta, const TopkDev* g,
+                           int64_t item_offset, int64_t* out_idx, float* out_score, cudaStream_t st) {
+    if (m->net == TRS_NET_LINEAR)
+        topk_rescore_kernel<TRS_NET_LINEAR, V, G, IT><<<g->n_query, 128, 0, st>>>(*m, users, item_meta, *g, item_offset,
+                                                                                 out_idx, out_score);
+    else
+        topk_rescore_kernel<TRS_NET_FM, V, G, IT><<<g->n_query, 128, 0, st>>>(*m, users, item_meta, *g, item_offset,
+                                                                             out_idx, out_score);
+}
+
+struct TopkLayout {
+    int Kp, nbox, kslices, stages, n_item_tiles, user_tiles, splits, tiles_per_split;
+    size_t Ub, Vb, unorm, ulin, vmax2, cand_s, cand_i, cand_cnt, overflow, total;
+    size_t smem;
+};
+static TopkLayout topk_layout(const trs_model* m, int64_t n_query) {
+    TopkLayout L = {};
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) / 256 * 256;
+        return o;
+    };
+    L.Kp = (m->dim + 1 + 15) / 16 * 16;
+    L.kslices = L.Kp / 16;
+    L.nbox = (L.Kp + 63) / 64;
+    L.stages = L.nbox <= 3 ? 3 : 2;
+    L.n_item_tiles = (int)((m->item.n_rows + TK_BN - 1) / TK_BN);
+    L.user_tiles = (int)((n_query + TK_BM - 1) / TK_BM);
+    // few users: cut the catalogue into up to TK_MAX_SPLITS item ranges so more SMs work; each range keeps
+    // its own candidate list (<= TK_CAP - TK_BN entries after the final compaction), and a range needs
+    // enough tiles for the running threshold to bite
+    int want = (2 * device_props().sm_count + L.user_tiles - 1) / L.user_tiles;
+    if (want > TK_MAX_SPLITS) want = TK_MAX_SPLITS;
+    if (want > L.n_item_tiles / 16) want = L.n_item_tiles / 16;
+    L.splits = want < 1 ? 1 : want;
+    L.tiles_per_split = (L.n_item_tiles + L.splits - 1) / L.splits;
+    L.splits = (L.n_item_tiles + L.tiles_per_split - 1) / L.tiles_per_split;
+    L.Ub = take((size_t)L.user_tiles * TK_BM * L.Kp * 2);
+    L.Vb = take((size_t)m->item.n_rows * L.Kp * 2);
+    L.unorm = take((size_t)n_query * 4);
+    L.ulin = take((size_t)n_query * 4);
+    L.vmax2 = take(256);
+    L.cand_s = take((size_t)n_query * L.splits * TK_CAP * 4);
+    L.cand_i = take((size_t)n_query * L.splits * TK_CAP * 4);
+    L.cand_cnt = take((size_t)n_query * L.splits * 4);
+    L.overflow = take((size_t)n_query * 4);
+    L.total = off;
+    L.smem = 1024 + (size_t)(1 + L.stages) * L.nbox * TK_BOX_BYTES + 8 * (2 * L.stages + 5) + 16;
+    return L;
+}
+
+static int check_topk(const trs_model* m, int64_t n_query, int k) {
+    RowShape shape;
+    int rc = check_model(m, &shape);
+    if (rc) return rc;
+    TRS_REQUIRE(m->net != TRS_NET_MLP, "predict_topk: the MLP tower has no user x item factorisation; score with trs_mlp_forward");
+    TRS_REQUIRE(m->dim <= 239, "predict_topk: n_factors up to 239 (got %d)", m->dim);
+    TRS_REQUIRE(k >= 1 && k <= TK_CAP / 4, "predict_topk: top_k must be in 1..%d (got %d)", TK_CAP / 4, k);
+    TRS_REQUIRE(n_query >= 0 && n_query < (1ll << 31) - TK_BM && m->item.n_rows < (1ll << 31) - TK_BN,
+                "predict_topk: too many users / items for one call");
+    return TRS_OK;
+}
+
+}  // namespace trs
+
+using namespace trs;
+
+extern "C" size_t trs_predict_topk_workspace_bytes(const trs_model* model, int64_t n_query, int k) {
+    if (check_topk(model, n_query, k) || n_query == 0) return 0;
+    return topk_layout(model, n_query).total;
+}
+
+extern "C" int trs_predict_topk(const trs_model* model, const int64_t* users, int64_t n_query,
+                                const int64_t* item_meta, int k, int64_t item_offset, int64_t* out_idx,
+                                float* out_score, int32_t* overflow, void* workspace, size_t workspace_bytes,
+                                trs_stream_t stream) {
+    int rc = check_topk(model, n_query, k);
+    if (rc) return rc;
+    if (n_query == 0) return TRS_OK;
+    TRS_REQUIRE(users && out_idx && out_score && overflow && workspace, "predict_topk: NULL pointer");
+    TRS_REQUIRE(model->n_meta == 0 || item_meta, "predict_topk: model has metadata tables but item_meta is NULL");
+    const TopkLayout L = topk_layout(model, n_query);
+    if (workspace_bytes < L.total) {
+        set_error("predict_topk workspace too small: %zu < %zu", workspace_bytes, L.total);
+        return TRS_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char* W = (char*)workspace;
+    const int64_t n_items = model->item.n_rows;
+    TRS_CUDA(cudaMemsetAsync(W + L.vmax2, 0, 256, st));
+    TRS_CUDA(cudaMemsetAsync(overflow, 0, (size_t)n_query * 4, st));
+    TRS_CUDA(cudaMemsetAsync(W + L.Ub, 0, (size_t)L.user_tiles * TK_BM * L.Kp * 2, st));
+    {
+        long long blocks = (n_items + 7) / 8;
+        const long long cap = (long long)device_props().sm_count * 32;
+        topk_prep_items_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(
+            *model, item_meta, n_items, L.Kp, (bf16*)(W + L.Vb), (unsigned*)(W + L.vmax2));
+        topk_prep_users_kernel<<<(int)((n_query + 7) / 8), 256, 0, st>>>(*model, users, (int)n_query, L.Kp, (bf16*)(W + L.Ub),
+                                                                         (float*)(W + L.unorm), (float*)(W + L.ulin));
+    }
+    TopkDev g = {};
+    g.n_query = (int)n_query;
+    g.n_items = (int)n_items;
+    g.nbox = L.nbox;
+    g.kslices = L.kslices;
+    g.stages = L.stages;
+    g.n_item_tiles = L.n_item_tiles;
+    g.tiles_per_split = L.tiles_per_split;
+    g.splits = L.splits;
+    g.k = k;
+    g.fm = model->net == TRS_NET_FM;
+    g.unorm = (const float*)(W + L.unorm);
+    g.ulin = (const float*)(W + L.ulin);
+    g.vmax2 = (const float*)(W + L.vmax2);
+    g.cand_s = (float*)(W + L.cand_s);
+    g.cand_i = (int*)(W + L.cand_i);
+    g.cand_cnt = (int*)(W + L.cand_cnt);
+    g.overflow = overflow;
+    CUtensorMap tu, tv;
+    if ((rc = make_tmap_bf16(&tu, W + L.Ub, (int64_t)L.user_tiles * TK_BM, L.Kp, L.Kp, TK_BM))) return rc;
+    if ((rc = make_tmap_bf16(&tv, W + L.Vb, n_items, L.Kp, L.Kp, TK_BN))) return rc;
+    TRS_CUDA(cudaFuncSetAttribute(topk_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    topk_score_kernel<<<dim3(L.user_tiles, L.splits), TK_THREADS, L.smem, st>>>(tu, tv, g);
+    TRS_CUDA(cudaGetLastError());
+    RowShape shape;
+    pick_row_shape(model->dim, &shape);
+    TRS_DISPATCH_ROW_SHAPE(shape, launch_rescore, model, users, item_meta, &g, item_offset, out_idx, out_score, st);
+    TRS_CUDA(cudaGetLastError());
+    return TRS_OK;
+}

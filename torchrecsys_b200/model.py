@@ -227,8 +227,15 @@ class TorchRecSys(torch.nn.Module):
         ``prediction_batch_size`` is accepted for compatibility; all items are scored in one pass."""
         dev = self._require_cuda()
         self.net = self.net.eval()
+        if self.net_type != "mlp" and 1 <= top_k <= 128:
+            return self.predict_batch(torch.tensor([int(user_id)]), top_k)[0]
+        return self._predict_exact(int(user_id), top_k, dev)
+
+    def _predict_exact(self, user_id: int, top_k: int, dev) -> torch.Tensor:
+        """Score every item in fp32 and sort (stable, descending): the MLP tower, top_k > 128, and users
+        the tensor-core path flags as overflowing."""
         items = torch.arange(self.n_items, device=dev)
-        users = torch.full_like(items, int(user_id))
+        users = torch.full_like(items, user_id)
         meta = self._dev_cache.get("item_meta") if self.use_metadata else None
         if self.net_type == "mlp":
             scores = _lib.mlp_forward(self.net.abi_model(), self.net.abi_mlp(), users, items, meta)
@@ -236,3 +243,24 @@ class TorchRecSys(torch.nn.Module):
             scores = _lib.scores(self.net.abi_model(), users, items, meta)
         order = torch.sort(scores, descending=True, stable=True)[1]
         return order[:top_k].cpu()
+
+    def predict_batch(self, user_ids, top_k: int = 10) -> torch.Tensor:
+        """Top-k item ids for MANY users at once -> CPU int64 ``[n_users, top_k]`` (new entry point; the
+        reference API is one user per call, model.py:341).  Linear / FM: user tiles x all items on the
+        tensor cores with the top-k fused into the epilogue, exact fp32 re-scoring of the candidates
+        (csrc/topk.cu); same indices and tie-break as ``predict``."""
+        dev = self._require_cuda()
+        self.net = self.net.eval()
+        users = torch.as_tensor(user_ids, dtype=torch.int64).to(dev).contiguous()
+        if self.net_type == "mlp" or not (1 <= top_k <= 128):
+            return torch.stack([self._predict_exact(int(u), top_k, dev) for u in users.tolist()])
+        if self.use_metadata and "item_meta" not in self._dev_cache:
+            self._device_split("train_data")
+        meta = self._dev_cache.get("item_meta") if self.use_metadata else None
+        idx, _, over = _lib.predict_topk(self.net.abi_model(), users, top_k, meta)
+        idx = idx.cpu()
+        for q in torch.nonzero(over.cpu()).flatten().tolist():
+            idx[q] = self._predict_exact(int(users[q]), top_k, dev)
+        if top_k > self.n_items:
+            idx = idx[:, :self.n_items]
+        return idx
