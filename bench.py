@@ -45,6 +45,9 @@ WORKLOADS = {
     "c3_mlp": dict(net="mlp", n_users=1_000_000, n_items=200_000, dim=64, n_cat=0, batch=16384, opt="adagrad",
                    lr=1e-2, hidden=[512, 256, 128], desc="BASELINE configs[2]: MLP [512,256,128] + batch norm, bf16 "
                    "tensor-core GEMMs, 1M users x 200k items, dim 64, batch 16384, Adagrad"),
+    "c5_predict": dict(net="linear", n_users=1_000_000, n_items=5_000_000, dim=128, n_cat=0, batch=148 * 128, k=100,
+                       opt=None, lr=0.0, predict=True, desc="BASELINE configs[4]: batched predict top-100 against a "
+                       "5M-item table (linear scorer, dim 128); a step = 18944 users (148 user tiles)"),
     "c4_linear": dict(net="linear", n_users=50_000_000, n_items=5_000_000, dim=128, n_cat=0, batch=16384,
                       opt="sparse_adam", lr=1e-3, desc="BASELINE configs[3]: linear 50M x 5M, dim 128, batch 16384/GPU"),
 }
@@ -398,6 +401,96 @@ def gpu_bench(args, wl):
     return out, rank
 
 
+# ------------------------------------------------------------------------------------------------
+# predict / top-k (BASELINE configs[4])
+# ------------------------------------------------------------------------------------------------
+def cpu_predict(wl, budget_s):
+    """The reference's predict (model.py:341-452: score every item for one user, sort, slice) on the host
+    cores through oracle/torch_port.py (same ATen ops, without the per-chunk pandas frame)."""
+    import torch
+    from oracle import torch_port as TP
+    ncores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(ncores)
+    torch.manual_seed(1234)
+    net = TP.make_net("linear", 1024, wl["n_items"], [], wl["dim"]).eval()
+    t0, done = time.perf_counter(), 0
+    while done < 3 or (time.perf_counter() - t0 < budget_s and done < 64):
+        TP.predict_topk(net, done % 1024, wl["n_items"], wl["k"], chunk=1 << 20)
+        done += 1
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": "users/s", "cores": ncores, "kind": "port",
+            "sample": f"{done} users x all {wl['n_items']} items, top-{wl['k']}, torch {torch.__version__} CPU, "
+                      f"{ncores} threads (user table cut to 1024 rows: it is not on the path)",
+            "ms_per_step": dt / done * 1e3, "steps": done}
+
+
+def predict_bench(args, wl):
+    import torch
+    from torchrecsys_b200 import _lib
+    from torchrecsys_b200.collaborative.linear import Linear
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    K, W, B, k = args.steps, max(args.warmup, 3), args.batch or wl["batch"], wl["k"]
+    torch.manual_seed(1234)
+    net = Linear(wl["n_users"], wl["n_items"], {}, wl["dim"], use_metadata=False, use_cuda=True).to(dev).eval()
+    with torch.no_grad():
+        net.item_bias.weight.normal_(0, 0.01)
+    model = net.abi_model()
+    import numpy as np
+    rng = np.random.default_rng(1234)
+    users_h = torch.from_numpy(rng.integers(0, wl["n_users"], (K + W) * B)).pin_memory()
+    users = users_h.to(dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for s in range(W):
+        _lib.predict_topk(model, users[s * B:(s + 1) * B], k)
+    torch.cuda.synchronize()
+    e0, e1 = ev(), ev()
+    with ClockSampler(dev.index) as clocks:
+        e0.record()
+        for s in range(W, W + K):
+            idx, score, over = _lib.predict_topk(model, users[s * B:(s + 1) * B], k)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    n_over = int(over.sum())
+    x0, x1 = ev(), ev()
+    out_h = torch.empty((B, k), dtype=torch.int64).pin_memory()
+    x0.record()
+    for s in range(W, W + K):
+        u = users_h[s * B:(s + 1) * B].to(dev, non_blocking=True)
+        idx, score, over = _lib.predict_topk(model, u, k)
+        out_h.copy_(idx, non_blocking=True)
+    x1.record()
+    torch.cuda.synchronize()
+    e2e_ms = x0.elapsed_time(x1)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    flops = 2.0 * wl["n_items"] * wl["dim"] * B * K
+    tach = flops / (ms * 1e-3) / 1e12
+    return {
+        "metric": "predict top-k users/sec", "value": K * B / (ms * 1e-3), "unit": "users/s", "n_gpus": 1, "steps": K,
+        "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": wl["desc"], "name": args.workload, "users_per_step": B, "top_k": k,
+                   "l2": "inputs larger than L2: bf16 item operand 1.44 GB streamed per user wave",
+                   "timed_region": "operand preparation (fp32 tables -> bf16 [w,c] rows) + tcgen05 score/top-k kernel "
+                                   "+ exact fp32 re-scoring, every step", "overflow_users_last_step": n_over},
+        "e2e": {"value": K * B / (e2e_ms * 1e-3), "unit": "users/s", "h2d_bytes_per_step": 8 * B,
+                "d2h_bytes_per_step": 8 * B * k},
+        "gpu_launches": 7 * K,
+        "roofline": {"bound": "tensor", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s", "frac": tach / tpeak,
+                     "traffic": None, "kernel": "trs::topk_score_kernel, timed inside the whole predict call "
+                     "(preparation and re-scoring are in the denominator)",
+                     "algorithmic_flops_per_step": flops / K,
+                     "peak_source": "measured sustained bf16 (MEASURED_PEAKS.json)" if peaks else "fallback 1400"},
+        "clocks": clocks.summary(),
+    }
+
+
 def main():
     args = parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -406,6 +499,26 @@ def main():
     if args.users:
         wl["n_users"] = args.users
     rank = int(os.environ.get("RANK", "0"))
+    if wl.get("predict"):
+        if rank != 0:
+            return
+        if args.impl == "reference":
+            r = cpu_predict(wl, max(args.cpu_seconds, 20.0) * 3)
+            print(json.dumps({"impl": "reference", "metric": "predict top-k users/sec", "value": r["value"],
+                              "unit": "users/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": 0,
+                              "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                              "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                              "config": {"workload": wl["desc"], "name": args.workload},
+                              "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                              "e2e": {"value": r["value"], "unit": "users/s", "h2d_bytes_per_step": 0,
+                                      "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+            return
+        out = predict_bench(args, wl)
+        if not args.no_cpu_baseline:
+            r = cpu_predict(wl, args.cpu_seconds)
+            out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(out))
+        return
     if args.impl == "reference":
         if rank != 0:
             return

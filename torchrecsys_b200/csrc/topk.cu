@@ -217,16 +217,23 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_const
                     if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
                 }
                 if (valid && !over) {
-                    const int lim = ncols - c * 32;  // columns of this chunk that are real items
+                    // steady state: about k/n of the scores pass, so first ask whether ANY of the 32 does
+                    // (branch-free max tree), and only then walk the chunk
+                    float mx = __uint_as_float(r[0]);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float v = __uint_as_float(r[j]);
-                        if (v >= thr && j < lim) {
-                            if (cnt < TK_CAP) {
-                                cs[cnt] = v;
-                                ci[cnt] = item0 + c * 32 + j;
+                    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                    if (mx >= thr) {
+                        const int lim = ncols - c * 32;  // columns of this chunk that are real items
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float v = __uint_as_float(r[j]);
+                            if (v >= thr && j < lim) {
+                                if (cnt < TK_CAP) {
+                                    cs[cnt] = v;
+                                    ci[cnt] = item0 + c * 32 + j;
+                                }
+                                ++cnt;
                             }
-                            ++cnt;
                         }
                     }
                 }
