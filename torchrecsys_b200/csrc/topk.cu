@@ -206,27 +206,33 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_const
             tc::tc_fence_after();
             const int item0 = (tile0 + t) * TK_BN;
             const int ncols = min(TK_BN, g.n_items - item0);
-#pragma unroll 1
-            for (int c = 0; c < TK_BN / 32; ++c) {
-                uint32_t r[32];
-                tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TK_BN + c * 32), r);
-                tc::tmem_ld_wait();
-                if (c == TK_BN / 32 - 1) {  // this warp is done with the TMEM buffer
-                    tc::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
-                }
-                if (valid && !over) {
-                    // steady state: about k/n of the scores pass, so first ask whether ANY of the 32 does
-                    // (branch-free max tree), and only then walk the chunk
-                    float mx = __uint_as_float(r[0]);
+            // all four 32-column chunks of the row are fetched back to back (one TMEM round trip), the
+            // buffer is handed back to the MMA warp at once, and the filtering runs from registers
+            uint32_t r[TK_BN / 32][32];
 #pragma unroll
-                    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-                    if (mx >= thr) {
+            for (int c = 0; c < TK_BN / 32; ++c)
+                tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TK_BN + c * 32), r[c]);
+            tc::tmem_ld_wait();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+            if (valid && !over) {
+#pragma unroll
+                for (int c = 0; c < TK_BN / 32; ++c) {
+                    // steady state: about k/n of the scores pass, so first ask whether ANY of the 32 does
+                    // (branch-free max tree, independent pairs), and only then walk the chunk
+                    float m16[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) m16[j] = fmaxf(__uint_as_float(r[c][j]), __uint_as_float(r[c][j + 16]));
+#pragma unroll
+                    for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+                        for (int j = 0; j < w; ++j) m16[j] = fmaxf(m16[j], m16[j + w]);
+                    if (m16[0] >= thr) {
                         const int lim = ncols - c * 32;  // columns of this chunk that are real items
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float v = __uint_as_float(r[j]);
+                            const float v = __uint_as_float(r[c][j]);
                             if (v >= thr && j < lim) {
                                 if (cnt < TK_CAP) {
                                     cs[cnt] = v;
