@@ -326,16 +326,19 @@ def gpu_bench(args, wl):
     alg_bytes = algorithmic_bytes(wl, uK, pK, neg, K, B, S)
 
     # ---- e2e: ids start in pinned host memory, losses end on the host ----
-    x0, x1 = ev(), ev()
-    sync_all()
-    x0.record()
-    u_d = user_h[W * B:].to(dev, non_blocking=True)
-    p_d = pos_h[W * B:].to(dev, non_blocking=True)
-    loss3 = step_block(u_d, p_d, (W + K) * B)
-    loss_host = loss3.to("cpu", non_blocking=True)
-    x1.record()
-    sync_all()
-    e2e_ms = x0.elapsed_time(x1)
+    loss_host = torch.empty(K, dtype=torch.float32).pin_memory()
+    e2e_ms = None
+    for attempt in range(2):  # first pass untimed: it warms the allocator for this region's buffer sizes
+        x0, x1 = ev(), ev()
+        sync_all()
+        x0.record()
+        u_d = user_h[W * B:].to(dev, non_blocking=True)
+        p_d = pos_h[W * B:].to(dev, non_blocking=True)
+        loss3 = step_block(u_d, p_d, (W + K * (1 + attempt)) * B)
+        loss_host.copy_(loss3, non_blocking=True)
+        x1.record()
+        sync_all()
+        e2e_ms = x0.elapsed_time(x1)
     assert loss_host.numel() == K
 
     times = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device=dev)
@@ -393,7 +396,9 @@ def gpu_bench(args, wl):
                 "h2d_bytes_per_step": 16 * B, "d2h_bytes_per_step": 4,
                 "note": "user+positive ids from pinned host memory; metadata ids and negatives are derived on the device"},
         "gpu_launches": launches,
-        "roofline": dict(roofline, traffic=traffic),
+        # traffic: dram bytes of the dominant kernel per launch, from the committed ncu --set full capture
+        # (profiles/traffic.json holds bytes per step; one launch = K steps)
+        "roofline": dict(roofline, traffic=(traffic * K if traffic else None)),
         "clocks": clocks.summary(),
     }
     if world > 1:

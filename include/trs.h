@@ -249,6 +249,32 @@ int trs_predict_topk(const trs_model* model, const int64_t* users, int64_t n_que
                      int k, int64_t item_offset, int64_t* out_idx, float* out_score, int32_t* overflow,
                      void* workspace, size_t workspace_bytes, trs_stream_t stream);
 
+/* ---- multi-GPU building blocks (the reference is single-device, model.py:74) ----------- */
+/* a7 for the OWNER of a table shard: grad.coalesce() + the row-wise optimizer step (torch:
+ * optim/_functional.py:44-84, optim/adagrad.py:363-373) on an explicit list of n (row id, gradient row)
+ * pairs, e.g. the gradient rows other ranks sent.  Duplicate rows are summed in list order after a stable
+ * sort by id (deterministic); grad_lin (nullable) is the gradient of the width-1 companion table.
+ * optim->step_scale[step] scales the update as in trs_train_steps. */
+size_t trs_sparse_update_workspace_bytes(int64_t n);
+int trs_sparse_row_update(const trs_table* table, int dim, const int64_t* ids, int64_t n, const float* grad_rows,
+                          const float* grad_lin, const trs_optim* optim, int step, void* workspace,
+                          size_t workspace_bytes, trs_stream_t stream);
+
+/* Linear scorer forward x2 + hinge + backward (linear.py:54-80, loss.py:5-9) on rows gathered elsewhere:
+ * u/pos/neg rows [batch, dim] and their biases [batch] in, one gradient row per lookup out
+ * (g = [hinge >= 0] * inv_batch; d user_bias = 0); *loss_sum = sum of the batch's hinges.
+ * workspace: at least 8 * SM-count floats. */
+int trs_linear_rows_step(int dim, int64_t batch, float inv_batch, const float* u_rows, const float* pos_rows,
+                         const float* neg_rows, const float* u_bias, const float* pos_bias, const float* neg_bias,
+                         float* g_u, float* g_pos, float* g_neg, float* g_pos_bias, float* g_neg_bias,
+                         float* loss_sum, float* workspace, size_t workspace_floats, trs_stream_t stream);
+
+/* Merge n_lists per-shard top-k lists (score / idx laid out [n_lists, n_query, k], idx < 0 = padding) into
+ * the global top-k per user, ordered by (score descending, item id ascending) -- the allgather half of the
+ * item-sharded predict. n_lists * k <= 4000. */
+int trs_topk_merge(const float* score, const int64_t* idx, int n_lists, int k, int64_t n_query,
+                   int64_t* out_idx, float* out_score, trs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -144,7 +144,7 @@ static int bits_for(int64_t n_rows) {
 }
 
 // Sort one id space for all steps.  Final (key, perm) land in out_key/out_val.
-static int sort_space(const int64_t* a, const int64_t* b, int stride, int off, int mult,
+int sort_space(const int64_t* a, const int64_t* b, int stride, int off, int mult,
                       int64_t n_rows, const trs_epoch* ep, uint32_t* out_key, uint32_t* out_val,
                       uint32_t* tmp_key, uint32_t* tmp_val, uint32_t* hist, cudaStream_t st) {
     const int64_t steps = n_steps_of(ep);
@@ -263,7 +263,7 @@ PlanLayout plan_layout(int64_t n_samples, int batch, int n_meta) {
     return L;
 }
 
-static size_t hist_bytes(const trs_epoch* ep) {
+size_t hist_bytes(const trs_epoch* ep) {
     const int tiles = (int)((2ll * ep->batch + SORT_TILE - 1) / SORT_TILE);
     return (size_t)n_steps_of(ep) * 256 * tiles * sizeof(uint32_t);
 }

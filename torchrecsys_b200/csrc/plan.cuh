@@ -36,4 +36,12 @@ struct PlanLayout {
 };
 PlanLayout plan_layout(int64_t n_samples, int batch, int n_meta);
 
+// Stable LSD radix sort of one id space for every step of `ep` (ids of step s, lookup j: j < B_s ? a[...] :
+// b[...], see plan.cu); final (row, lookup) pairs land in out_key / out_val.  tmp_key / tmp_val hold
+// mult * n_samples entries each, hist hist_bytes(ep) bytes.
+int sort_space(const int64_t* a, const int64_t* b, int stride, int off, int mult, int64_t n_rows,
+               const trs_epoch* ep, uint32_t* out_key, uint32_t* out_val, uint32_t* tmp_key, uint32_t* tmp_val,
+               uint32_t* hist, cudaStream_t st);
+size_t hist_bytes(const trs_epoch* ep);
+
 }  // namespace trs

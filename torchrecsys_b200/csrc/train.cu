@@ -52,11 +52,6 @@ struct Stage {
     unsigned long long* trace; // debug (TRS_DEBUG_SKIP & 64): [n_steps, gridDim.x, 4] globaltimer stamps
 };
 
-struct OptScalars {
-    int kind;
-    float omb1, omb2, eps;  // 1-beta1, 1-beta2, eps rounded to fp32 as torch's scalar ops do
-    const float* step_scale;
-};
 
 struct StageLayout {
     size_t gU, gI, gM[TRS_MAX_META], gbU, gbI, loss_part, partials, partials_lin, sync_words, trace, total;
@@ -155,26 +150,6 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
     __syncthreads();
 }
 
-// ---- row-wise optimizers (torch: optim/_functional.py:65-84, optim/adagrad.py:363-373, sgd) ----
-// Explicit _rn intrinsics keep nvcc from contracting mul+add into FMA where torch runs two ops.
-__device__ __forceinline__ void opt_update(const OptScalars& o, float scale, float g, float& p,
-                                           float& s0, float& s1) {
-    if (o.kind == TRS_OPT_SPARSE_ADAM) {
-        const float um = __fmul_rn(__fsub_rn(g, s0), o.omb1);
-        const float uv = __fmul_rn(__fsub_rn(__fmul_rn(g, g), s1), o.omb2);
-        s0 = __fadd_rn(s0, um);
-        s1 = __fadd_rn(s1, uv);
-        const float denom = __fadd_rn(__fsqrt_rn(s1), o.eps);
-        p = __fadd_rn(p, __fmul_rn(-scale, __fdiv_rn(s0, denom)));
-    } else if (o.kind == TRS_OPT_ADAGRAD) {
-        s0 = __fadd_rn(s0, __fmul_rn(g, g));
-        const float stdv = __fadd_rn(__fsqrt_rn(s0), o.eps);
-        p = __fadd_rn(p, __fmul_rn(-scale, __fdiv_rn(g, stdv)));
-    } else {
-        p = __fadd_rn(p, __fmul_rn(-scale, g));
-    }
-}
-
 // Which arrays an id space (0 user, 1 item, 2+f metadata f) reduces from / updates.
 struct SpaceRef {
     const trs_table* t;
@@ -252,7 +227,10 @@ __device__ __forceinline__ void apply_and_store(const trs_table& t, uint32_t key
 // synchronisation is needed: cp.async.wait_group makes a thread's own copies visible to it.
 constexpr int RING = 4;
 template <int V, int IT>
-constexpr int train_threads() { return V == 1 ? 256 : (IT == 1 ? 512 : (IT == 2 ? 256 : 128)); }
+#ifndef TRS_TRAIN_T1
+#define TRS_TRAIN_T1 512  // threads per CTA for rows of <= 32 chunks (tuning hook: -DTRS_TRAIN_T1=256|384|512)
+#endif
+constexpr int train_threads() { return V == 1 ? 256 : (IT == 1 ? TRS_TRAIN_T1 : (IT == 2 ? 256 : 128)); }
 template <int V, int IT>
 constexpr size_t train_smem_bytes() {
     return V == 1 ? 0 : (size_t)train_threads<V, IT>() * (2 * RING * 16 + RING * 4 * IT * 16);
