@@ -49,7 +49,8 @@ WORKLOADS = {
                        opt=None, lr=0.0, predict=True, desc="BASELINE configs[4]: batched predict top-100 against a "
                        "5M-item table (linear scorer, dim 128); a step = 18944 users (148 user tiles)"),
     "c4_linear": dict(net="linear", n_users=50_000_000, n_items=5_000_000, dim=128, n_cat=0, batch=16384,
-                      opt="sparse_adam", lr=1e-3, desc="BASELINE configs[3]: linear 50M x 5M, dim 128, batch 16384/GPU"),
+                      opt="sparse_adam", lr=1e-3, sharded=True,
+                      desc="BASELINE configs[3]: linear 50M x 5M, dim 128, batch 16384/GPU, tables row-sharded"),
 }
 
 
@@ -89,6 +90,10 @@ def cpu_reference(wl, steps, warmup, budget_s):
     from oracle import cf_oracle as O
     from oracle import torch_port as TP
     B = wl["batch"]
+    cap_note = ""
+    if wl["n_users"] > 5_000_000:  # host RAM: 50M x 128 fp32 + SparseAdam state would be 77 GB
+        wl = dict(wl, n_users=5_000_000)
+        cap_note = " (user table cut to 5M rows on the host: 25.6 GB + optimizer state does not fit; row access stays random)"
     n = (steps + warmup) * B
     user, pos = synth_ids(wl, n)
     neg = O.philox_negatives(1234, 0, pos, wl["n_items"])
@@ -136,7 +141,7 @@ def cpu_reference(wl, steps, warmup, budget_s):
     return {"value": value, "unit": "samples/s", "cores": nt, "kind": "port",
             "sample": f"{done} steps of batch {B} ({done * B} samples) of the same workload after "
                       f"{warmup} warm-up steps, torch {torch.__version__} CPU, threads swept "
-                      f"{ {k: round(v) for k, v in tried.items()} } on {ncores} cores, best kept",
+                      f"{ {k: round(v) for k, v in tried.items()} } on {ncores} cores, best kept" + cap_note,
             "ms_per_step": dt / done * 1e3, "steps": done}
 
 
@@ -429,6 +434,13 @@ def cpu_predict(wl, budget_s):
             "ms_per_step": dt / done * 1e3, "steps": done}
 
 
+def _traffic(workload):
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
+    except Exception:
+        return None
+
+
 def predict_bench(args, wl):
     import torch
     from torchrecsys_b200 import _lib
@@ -488,12 +500,98 @@ def predict_bench(args, wl):
                 "d2h_bytes_per_step": 8 * B * k},
         "gpu_launches": 7 * K,
         "roofline": {"bound": "tensor", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s", "frac": tach / tpeak,
-                     "traffic": None, "kernel": "trs::topk_score_kernel, timed inside the whole predict call "
+                     "traffic": _traffic(args.workload), "kernel": "trs::topk_score_kernel, timed inside the whole predict call "
                      "(preparation and re-scoring are in the denominator)",
                      "algorithmic_flops_per_step": flops / K,
                      "peak_source": "measured sustained bf16 (MEASURED_PEAKS.json)" if peaks else "fallback 1400"},
         "clocks": clocks.summary(),
     }
+
+
+# ------------------------------------------------------------------------------------------------
+# row-sharded large-table training (BASELINE configs[3]) -- torchrun, one rank per GPU
+# ------------------------------------------------------------------------------------------------
+def sharded_bench(args, wl):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from torchrecsys_b200 import sharded as S
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if not dist.is_initialized():
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    K, W, B = args.steps, max(args.warmup, 3), args.batch or wl["batch"]
+    tr = S.ShardedLinearTrainer(wl["n_users"], wl["n_items"], wl["dim"], optimizer=wl["opt"], lr=wl["lr"], device=dev)
+    rng = np.random.default_rng(1234 + rank)
+    ids_h = [torch.from_numpy(rng.integers(0, n, (K + W) * B)).pin_memory()
+             for n in (wl["n_users"], wl["n_items"], wl["n_items"])]
+    ids = [t.to(dev) for t in ids_h]
+    step = lambda src, s: tr.train_step(*(t[s * B:(s + 1) * B] for t in src))
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    sync_all = lambda: (torch.cuda.synchronize(), dist.barrier(), torch.cuda.synchronize())
+    for s in range(W):
+        step(ids, s)
+    e0, e1 = ev(), ev()
+    hs = torch.zeros(1, device=dev)
+    with ClockSampler(local) as clocks:
+        sync_all()
+        e0.record()
+        for s in range(W, W + K):
+            hs += step(ids, s)
+        e1.record()
+        sync_all()
+    ms = e0.elapsed_time(e1)
+    x0, x1 = ev(), ev()
+    hs2 = torch.zeros(1, device=dev)
+    sync_all()
+    x0.record()
+    for s in range(W, W + K):
+        hs2 += step([t[s * B:(s + 1) * B].to(dev, non_blocking=True) for t in ids_h], 0)
+    loss_h = hs2.cpu()
+    x1.record()
+    sync_all()
+    e2e_ms = x0.elapsed_time(x1)
+    times = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dist.all_reduce(hs)
+    ms, e2e_ms = (float(x) for x in times.cpu())
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    S_ = {"sgd": 0, "adagrad": 1, "sparse_adam": 2}[wl["opt"]]
+    # no-duplicate bound (uniform ids over 50M / 5M rows): 3 rows of (dim+1) floats, param + S states, read + write
+    alg = K * B * (24 + 3 * (wl["dim"] + 1) * 4 * (2 + 2 * S_))
+    ach = alg / (ms * 1e-3) / 1e9
+    nvl = K * B * 3 * (8 + 2 * (wl["dim"] + 1) * 4) * (world - 1) / world  # ids out, rows back, gradient rows out
+    out = {
+        "metric": "train samples/sec (fwd+bwd+sparse update)", "value": world * K * B / (ms * 1e-3), "unit": "samples/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "name": args.workload, "batch_per_gpu": B, "global_batch": B * world,
+                   "optimizer": wl["opt"], "parallelism": f"tables row-sharded over {world} ranks (row % G), "
+                   "all_to_all of ids / rows / gradient rows per step, owner-side coalesce + update",
+                   "l2": f"inputs larger than L2: {(wl['n_users'] + wl['n_items']) * (wl['dim'] + 1) * 4 * (1 + S_) / world / 1e9:.1f} "
+                         "GB of tables + optimizer state per rank, rows hit at random",
+                   "mean_loss": float(hs) / (world * K * B)},
+        "e2e": {"value": world * K * B / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": 24 * B,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": K * 14,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "kernel": "per rank: gather + trs_linear_rows_step + trs_sparse_row_update (the whole step incl. "
+                               "routing and NCCL is in the denominator)",
+                     "algorithmic_bytes_per_step": alg / K, "nvlink_bytes_per_step_per_rank": nvl / K,
+                     "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650"},
+        "clocks": clocks.summary(),
+    }
+    dist.destroy_process_group()
+    return out, rank
 
 
 def main():
@@ -539,7 +637,7 @@ def main():
                 "gpu_launches": 0}
         print(json.dumps(line))
         return
-    out, rank = gpu_bench(args, wl)
+    out, rank = sharded_bench(args, wl) if wl.get("sharded") else gpu_bench(args, wl)
     if rank == 0:
         if args.gpus == 1 and not args.no_cpu_baseline:
             r = cpu_reference(wl, steps=8, warmup=1, budget_s=args.cpu_seconds)

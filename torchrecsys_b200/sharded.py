@@ -39,10 +39,11 @@ import torch.distributed as dist
 @dataclass
 class Route:
     order: torch.Tensor        # [n] permutation: lookups sorted by (owner, space)
-    send_counts: torch.Tensor  # [G, S] lookups this rank sends to each owner, per id space
-    recv_counts: torch.Tensor  # [G, S] lookups each rank sends to THIS owner
+    send_splits: List[int]     # lookups this rank sends to each owner (host ints)
+    recv_splits: List[int]     # lookups each rank sends to THIS owner
     recv_rows: torch.Tensor    # [n_recv] local row ids requested from this owner (rank-major, then space, then lookup order)
-    recv_space: torch.Tensor   # [n_recv] id space of each request
+    by_space: torch.Tensor     # [n_recv] permutation grouping the received requests by id space (stable)
+    space_sizes: List[int]     # requests per id space on this owner (host ints)
 
 
 def _a2a(out: torch.Tensor, inp: torch.Tensor, out_splits: List[int], in_splits: List[int], group) -> None:
@@ -57,22 +58,22 @@ def make_route(ids: torch.Tensor, space: torch.Tensor, n_spaces: int, world: int
     send_counts = torch.bincount(key, minlength=world * n_spaces).view(world, n_spaces)
     recv_counts = torch.empty_like(send_counts)
     dist.all_to_all_single(recv_counts, send_counts, group=group)
-    in_splits = send_counts.sum(1).tolist()
-    out_splits = recv_counts.sum(1).tolist()
+    # the one host synchronisation of a step: all_to_all needs its split sizes on the host
+    counts = torch.stack([send_counts, recv_counts]).cpu()
+    in_splits = counts[0].sum(1).tolist()
+    out_splits = counts[1].sum(1).tolist()
     recv_rows = torch.empty(sum(out_splits), dtype=ids.dtype, device=ids.device)
     _a2a(recv_rows, (ids[order] // world).contiguous(), out_splits, in_splits, group)
     # the space of each received request follows from the counts: per source rank, space 0 block then space 1 ...
-    recv_space = torch.repeat_interleave(
-        torch.arange(n_spaces, device=ids.device).repeat(world), recv_counts.reshape(-1))
-    return Route(order, send_counts, recv_counts, recv_rows, recv_space)
+    recv_space = torch.repeat_interleave(torch.arange(n_spaces).repeat(world), counts[1].reshape(-1))
+    by_space = torch.sort(recv_space, stable=True)[1].to(ids.device, non_blocking=True)
+    return Route(order, in_splits, out_splits, recv_rows, by_space, counts[1].sum(0).tolist())
 
 
 def exchange_back(route: Route, payload: torch.Tensor, group=None) -> torch.Tensor:
     """Owner -> requester: payload[n_recv, W] (one row per received request) -> [n, W] in LOOKUP order."""
-    in_splits = route.recv_counts.sum(1).tolist()
-    out_splits = route.send_counts.sum(1).tolist()
-    got = torch.empty((sum(out_splits), payload.shape[1]), dtype=payload.dtype, device=payload.device)
-    _a2a(got, payload.contiguous(), out_splits, in_splits, group)
+    got = torch.empty((sum(route.send_splits), payload.shape[1]), dtype=payload.dtype, device=payload.device)
+    _a2a(got, payload.contiguous(), route.send_splits, route.recv_splits, group)
     out = torch.empty_like(got)
     out[route.order] = got
     return out
@@ -80,10 +81,8 @@ def exchange_back(route: Route, payload: torch.Tensor, group=None) -> torch.Tens
 
 def exchange_forward(route: Route, payload: torch.Tensor, group=None) -> torch.Tensor:
     """Requester -> owner: payload[n, W] in lookup order -> [n_recv, W] aligned with route.recv_rows."""
-    in_splits = route.send_counts.sum(1).tolist()
-    out_splits = route.recv_counts.sum(1).tolist()
-    got = torch.empty((sum(out_splits), payload.shape[1]), dtype=payload.dtype, device=payload.device)
-    _a2a(got, payload[route.order].contiguous(), out_splits, in_splits, group)
+    got = torch.empty((sum(route.recv_splits), payload.shape[1]), dtype=payload.dtype, device=payload.device)
+    _a2a(got, payload[route.order].contiguous(), route.recv_splits, route.send_splits, group)
     return got
 
 
@@ -171,15 +170,15 @@ class ShardedLinearTrainer:
         ids = torch.cat([user, pos, neg])
         space = torch.cat([torch.zeros_like(user), torch.ones_like(pos), torch.ones_like(neg)])
         route = make_route(ids, space, 2, self.world, self.group)
-        is_item = route.recv_space == 1
-        payload = torch.empty((route.recv_rows.shape[0], self.dim + 1), dtype=torch.float32, device=ids.device)
-        payload[~is_item] = self._gather("user", route.recv_rows[~is_item])
-        payload[is_item] = self._gather("item", route.recv_rows[is_item])
+        nu = route.space_sizes[0]
+        req = route.recv_rows[route.by_space]                       # user requests first, then item requests
+        payload = torch.empty((req.shape[0], self.dim + 1), dtype=torch.float32, device=ids.device)
+        payload[route.by_space] = torch.cat([self._gather("user", req[:nu]), self._gather("item", req[nu:])])
         rows = exchange_back(route, payload, self.group)            # [3B, dim+1] in lookup order
         g_u, g_vp, g_vn, hsum = self._compute(rows[:B], rows[B:2 * B], rows[2 * B:], 1.0 / (B * self.world))
-        grads = exchange_forward(route, torch.cat([g_u, g_vp, g_vn]), self.group)
-        self._update("user", route.recv_rows[~is_item], grads[~is_item])
-        self._update("item", route.recv_rows[is_item], grads[is_item])
+        grads = exchange_forward(route, torch.cat([g_u, g_vp, g_vn]), self.group)[route.by_space]
+        self._update("user", req[:nu], grads[:nu])
+        self._update("item", req[nu:], grads[nu:])
         self.step += 1
         return hsum
 
