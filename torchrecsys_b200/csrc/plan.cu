@@ -174,8 +174,7 @@ __global__ void __launch_bounds__(256)
 build_items_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ perm, int mult,
                    int space, int64_t n_samples, int B, uint32_t* __restrict__ item_cnt,
                    uint4* __restrict__ items, int item_cap, uint32_t* __restrict__ long_cnt,
-                   uint4* __restrict__ long_segs, int long_cap, uint32_t* __restrict__ chunk_cnt,
-                   uint4* __restrict__ chunks, int chunk_cap) {
+                   uint4* __restrict__ long_segs, int long_cap, uint8_t* __restrict__ single) {
     const int64_t step = blockIdx.y;
     const int Bs = (int)min((int64_t)B, n_samples - step * B);
     const int len = mult * Bs;
@@ -198,6 +197,12 @@ build_items_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict
         }
     }
     uint4* out = items + (size_t)step * item_cap;
+    // a row looked up exactly once in this step: the sample's own row group updates it in phase A
+    // (`single` is null for id spaces / nets whose rows are always reduced in phase B)
+    if (head && !is_long && c == 1 && single) {
+        single[(int64_t)mult * step * B + P[k]] = 1;
+        head = false;
+    }
     // short segments: one warp-aggregated append
     const bool is_short = head && !is_long;
     const uint32_t m = __ballot_sync(0xffffffffu, is_short);
@@ -218,17 +223,9 @@ build_items_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict
             if (K[mid] == key) lo = mid; else hi = mid;
         }
         const int cl = hi - k;
-        const int n_chunks = (cl + LONG_CHUNK - 1) / LONG_CHUNK;
         const uint32_t seg = atomicAdd(&long_cnt[step], 1u);
-        const uint32_t pslot = atomicAdd(&chunk_cnt[step], (uint32_t)n_chunks);
-        if (seg < (uint32_t)long_cap && pslot + n_chunks <= (uint32_t)chunk_cap) {
-            long_segs[(size_t)step * long_cap + seg] = make_uint4((uint32_t)space, (uint32_t)k, (uint32_t)cl, pslot);
-            uint4* co = chunks + (size_t)step * chunk_cap + pslot;
-            for (int q = 0; q < n_chunks; ++q) {
-                const int cc = min(LONG_CHUNK, cl - q * LONG_CHUNK);
-                co[q] = make_uint4((uint32_t)space | ((uint32_t)cc << 8), (uint32_t)(k + q * LONG_CHUNK), seg, (uint32_t)q);
-            }
-        }
+        if (seg < (uint32_t)long_cap)
+            long_segs[(size_t)step * long_cap + seg] = make_uint4((uint32_t)space, (uint32_t)k, (uint32_t)cl, key);
     }
 }
 
@@ -252,13 +249,12 @@ PlanLayout plan_layout(int64_t n_samples, int batch, int n_meta) {
     const int64_t lookups = (int64_t)batch * (3 + 2 * n_meta);
     L.item_cap = (int)lookups;                            // every item covers >= 1 lookup
     L.long_cap = (int)(lookups / (LONG_SEG_T + 1) + 1);   // a long segment has > T lookups
-    L.chunk_cap = (int)(lookups / LONG_CHUNK + L.long_cap + 1);
     L.item_cnt = take((size_t)steps);
     L.long_cnt = take((size_t)steps);
-    L.chunk_cnt = take((size_t)steps);
+    L.single_user = take((size_t)(n_samples + 3) / 4);        // one byte per lookup
+    L.single_item = take((size_t)(2 * n_samples + 3) / 4);
     L.items = take((size_t)steps * L.item_cap * 4);
     L.long_segs = take((size_t)steps * L.long_cap * 4);
-    L.chunks = take((size_t)steps * L.chunk_cap * 4);
     L.total = off;
     return L;
 }
@@ -323,15 +319,19 @@ extern "C" int trs_plan_build(const trs_model* model, const trs_epoch* ep, void*
     const int64_t steps = n_steps_of(ep);
     uint32_t* item_cnt = (uint32_t*)(P + L.item_cnt);
     uint32_t* long_cnt = (uint32_t*)(P + L.long_cnt);
-    uint32_t* chunk_cnt = (uint32_t*)(P + L.chunk_cnt);
-    // the three counter arrays are adjacent (take() order): one memset
+    // counters and singleton flags are adjacent (take() order): one memset
     TRS_CUDA(cudaMemsetAsync(item_cnt, 0, L.items - L.item_cnt, stream));
+    // the MLP tower stages every gradient row itself (mlp.cu): nothing is updated in a phase A there
+    const bool fuse_single = model->net != TRS_NET_MLP;
     auto build_items = [&](size_t key_off, size_t perm_off, int mult, int space) {
+        uint8_t* single = !fuse_single ? nullptr
+                          : space == 0 ? (uint8_t*)(P + L.single_user)
+                          : space == 1 ? (uint8_t*)(P + L.single_item) : nullptr;
         dim3 grid((unsigned)(((int64_t)mult * ep->batch + 255) / 256), (unsigned)steps);
         build_items_kernel<<<grid, 256, 0, stream>>>(
             (const uint32_t*)(P + key_off), (const uint32_t*)(P + perm_off), mult, space, ep->n_samples,
             ep->batch, item_cnt, (uint4*)(P + L.items), L.item_cap, long_cnt, (uint4*)(P + L.long_segs),
-            L.long_cap, chunk_cnt, (uint4*)(P + L.chunks), L.chunk_cap);
+            L.long_cap, single);
     };
     build_items(L.user_key, L.user_perm, 1, 0);
     build_items(L.item_key, L.item_perm, 2, 1);

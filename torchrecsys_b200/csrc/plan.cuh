@@ -10,28 +10,27 @@ namespace trs {
 // user arrays hold n_samples entries (segment of step s starts at s*batch); item/meta arrays
 // hold 2*n_samples entries (segment of step s starts at 2*s*batch).
 //
-// On top of the sorted pairs the plan holds, per step, the WORK ITEMS of the reduce+update phase
+// On top of the sorted pairs the plan holds, per step, what the training kernel does with every touched row
 // (built once per epoch, off the training kernel's critical path):
-//   item_cnt[s], items[s][i] (uint4)   a SHORT segment: one row with <= LONG_SEG_T lookups
+//   single_user[lookup], single_item[lookup] (uint8)   1 = this lookup's row is looked up exactly ONCE in the
+//        step: no other sample reads or writes it, so the sample's own row group applies the optimizer update
+//        right in phase A (no staging, no barrier).  Indexed like the perm values: step*B + j / 2*step*B + j.
+//   item_cnt[s], items[s][i] (uint4)   a SHORT segment: one row with 2..LONG_SEG_T lookups (metadata spaces
+//        and the MLP tower's plans also list their single-lookup rows here)
 //        x = id space (0 user, 1 item, 2+f metadata f) | count << 8
 //        y = start position k in the step's sorted arrays, z = row id, w = first lookup id (perm[k])
-//   chunk_cnt[s], chunks[s][i] (uint4) a CHUNK: <= LONG_CHUNK consecutive lookups of a LONG segment
-//        x = id space | count << 8, y = start position, z = index into long_segs[s], w = chunk index
-//        (slot i of chunks[s] is also the slot of the chunk's partial sum)
-//   long_cnt[s], long_segs[s][i] (uint4)  {id space, start k, length c, index of its first chunk}
-// A row looked up more than LONG_SEG_T times in a step (always the case for the small metadata
-// tables, and for hot rows under skew) is cut into chunks that different row groups sum in
-// parallel; the group that finishes last adds the partials in chunk order and applies the update.
+//   long_cnt[s], long_segs[s][i] (uint4)  a LONG segment: {id space, start k, length c, row id}
+// A row looked up more than LONG_SEG_T times in a step (always the case for the small metadata tables, and
+// for hot rows under skew) is reduced by a whole CTA: its row groups sum strided subsets of the lookups, the
+// partial sums are added in group order, one group applies the update.
 constexpr int LONG_SEG_T = 8;
-constexpr int LONG_CHUNK = 16;
 
 struct PlanLayout {
     size_t user_key, user_perm, item_key, item_perm;
     size_t meta_key[TRS_MAX_META], meta_perm[TRS_MAX_META];
-    size_t item_cnt, long_cnt, chunk_cnt, items, long_segs, chunks;
+    size_t item_cnt, long_cnt, single_user, single_item, items, long_segs;
     int item_cap;   // entries per step in items
     int long_cap;   // entries per step in long_segs
-    int chunk_cap;  // entries per step in chunks (= partial slots)
     size_t total;
 };
 PlanLayout plan_layout(int64_t n_samples, int batch, int n_meta);

@@ -3,19 +3,25 @@
 //
 // Per step (reference model.py:274-284):
 //   phase A  one row group per sample: gather u, v+, v- (+ metadata rows), both scores, hinge,
-//            closed-form gradient rows -> L2-resident staging, one row per lookup.
-//            While it waits it prefetches into L2 the optimizer-state rows phase B will need.
-//   grid barrier (every score of the step is computed from pre-update parameters)
-//   phase B  work items from the plan (plan.cu): a short segment = one touched row whose few
-//            lookups are summed in lookup order, then param+state are read once, updated
-//            (SGD / Adagrad / SparseAdam) and written once; a chunk = 32 lookups of a hot row,
-//            summed to a partial, the last chunk to arrive adds the partials in chunk order and
-//            updates.  First thing in phase B, the rows of the NEXT step's samples are prefetched
-//            into L2, so that phase A's gathers hit L2 as well.
+//            closed-form gradient rows.  A user / item row that this step looks up exactly
+//            ONCE (plan.cuh: single_*; >90 % of the lookups under uniform ids) has no other reader or writer
+//            in the step, so the sample's own row group applies the optimizer update to it right here:
+//            parameter and optimizer-state rows are fetched together with the gather, updated in registers
+//            and written once.  Every other gradient row goes to an L2-resident staging buffer.
+//   grid barrier (staged rows complete; every score of the step was computed from pre-update parameters)
+//   phase B  long segments (rows with > LONG_SEG_T lookups: the small metadata tables, hot rows) are reduced
+//            by a whole CTA -- its row groups sum strided subsets of the staged rows, the partial sums are
+//            added in group order through shared memory, one group updates the row; short segments (2..T
+//            lookups, and every metadata row) stream through a per-thread cp.async ring: param + state rows
+//            fetched before the barrier, staged gradient rows after it, duplicates summed in lookup order.
+//            First thing in phase B the rows (parameters AND optimizer state) of the NEXT step's samples are
+//            prefetched into L2.
 //   grid barrier
-// HBM traffic per step is ids + (param+state read, param+state write) per unique touched row;
-// staging, plan and partials are served from L2.  Nothing depends on the order in which CTAs or
-// row groups run: every floating-point sum has a fixed association (deterministic results).
+// HBM traffic per step is ids + (param+state read, param+state write) per unique touched row; staging and plan
+// are served from L2.  Nothing depends on the order in which CTAs or row groups run: every floating-point sum
+// has a fixed association (deterministic results).
+//
+// NET == TRS_NET_MLP: phase A is skipped -- the gradient rows were staged by the tower's backward (mlp.cu).
 #include <stdlib.h>
 
 #include "plan.cuh"
@@ -24,37 +30,34 @@
 
 namespace trs {
 
-constexpr int MF = 2;  // metadata features whose rows are kept in registers between fwd and bwd
+constexpr int MF = 1;  // metadata features whose rows are kept in registers between fwd and bwd
 
 struct PlanPtrs {
     const uint32_t *user_key, *user_perm, *item_key, *item_perm;
     const uint32_t* meta_key[TRS_MAX_META];
     const uint32_t* meta_perm[TRS_MAX_META];
     const uint32_t* item_cnt;
-    const uint32_t* chunk_cnt;
+    const uint32_t* long_cnt;
+    const uint8_t* single_user;
+    const uint8_t* single_item;
     const uint4* items;
-    const uint4* chunks;
     const uint4* long_segs;
-    int item_cap, long_cap, chunk_cap;
+    int item_cap, long_cap;
 };
 
 struct Stage {
     float* gU;                 // [B, dim]
     float* gI;                 // [2B, dim]
-    float* gM[TRS_MAX_META];   // FM only: [2B, dim]
+    float* gM[TRS_MAX_META];   // FM / MLP: [2B, dim]
     float* gbU;                // FM only: [B]
     float* gbI;                // [2B]  (FM: also the gradient of linear_metadata, d w_k = delta)
     float* loss_part;          // [n_steps, gridDim.x]
-    float* partials;           // [chunk_cap, dim]   partial sums of long-segment chunks
-    float* partials_lin;       // [chunk_cap]
-    unsigned* seg_arrive;      // [long_cap]  finished chunks per long segment (self-resetting)
     unsigned* barrier;         // [1] monotonically increasing arrival counter
-    unsigned long long* trace; // debug (TRS_DEBUG_SKIP & 64): [n_steps, gridDim.x, 4] globaltimer stamps
+    unsigned long long* trace; // debug (TRS_DEBUG_SKIP & 64): [n_steps, gridDim.x, 16] globaltimer stamps
 };
 
-
 struct StageLayout {
-    size_t gU, gI, gM[TRS_MAX_META], gbU, gbI, loss_part, partials, partials_lin, sync_words, trace, total;
+    size_t gU, gI, gM[TRS_MAX_META], gbU, gbI, loss_part, sync_words, trace, total;
     size_t sync_bytes;
 };
 
@@ -66,7 +69,6 @@ static StageLayout stage_layout(const trs_model* m, const trs_epoch* ep, int gri
         off += (n_floats * sizeof(float) + 255) / 256 * 256;
         return o;
     };
-    const PlanLayout PL = plan_layout(ep->n_samples, ep->batch, m->n_meta);
     const size_t B = (size_t)ep->batch, D = (size_t)m->dim;
     L.gU = take(B * D);
     L.gI = take(2 * B * D);
@@ -74,10 +76,8 @@ static StageLayout stage_layout(const trs_model* m, const trs_epoch* ep, int gri
     L.gbU = take(B);
     L.gbI = take(2 * B);
     L.loss_part = take((size_t)n_steps_of(ep) * grid);
-    L.partials = take((size_t)PL.chunk_cap * D);
-    L.partials_lin = take((size_t)PL.chunk_cap);
-    L.sync_words = off;  // seg_arrive[long_cap], pad, barrier[1]; zeroed before every launch
-    L.sync_bytes = ((size_t)PL.long_cap + 64) * sizeof(unsigned);
+    L.sync_words = off;  // barrier[1] (+ padding); zeroed before every launch
+    L.sync_bytes = 64 * sizeof(unsigned);
     off += (L.sync_bytes + 255) / 256 * 256;
     L.trace = take((size_t)n_steps_of(ep) * grid * 16 * 2);
     L.total = off;
@@ -176,64 +176,47 @@ __device__ __forceinline__ SpaceRef resolve_space(int space, const trs_model& m,
     return r;
 }
 
-// The row being updated: parameter + optimizer state, and its width-1 companion.
-template <int V, int IT>
-struct RowState {
-    Row<V, IT> p, s0, s1;
-    float pl, l0, l1;
-};
-
+// update one row held in registers and write it (param + the optimizer's state tensors)
 template <int V, int G, int IT>
-__device__ __forceinline__ RowState<V, IT> load_state(const trs_table& t, uint32_t key, int dim, int nch,
-                                                      int gl, int kind, bool lin) {
-    RowState<V, IT> r;
-    const size_t roff = (size_t)key * dim;
-    r.p = load_row_cg<V, G, IT>(t.emb + roff, nch, gl);
-    row_zero(r.s0);
-    row_zero(r.s1);
-    if (kind != TRS_OPT_SGD) r.s0 = load_row_cg<V, G, IT>(t.emb_s0 + roff, nch, gl);
-    if (kind == TRS_OPT_SPARSE_ADAM) r.s1 = load_row_cg<V, G, IT>(t.emb_s1 + roff, nch, gl);
-    r.pl = r.l0 = r.l1 = 0.f;
-    if (lin) {
-        r.pl = __ldcg(t.lin + key);
-        if (kind != TRS_OPT_SGD) r.l0 = __ldcg(t.lin_s0 + key);
-        if (kind == TRS_OPT_SPARSE_ADAM) r.l1 = __ldcg(t.lin_s1 + key);
-    }
-    return r;
-}
-
-template <int V, int G, int IT>
-__device__ __forceinline__ void apply_and_store(const trs_table& t, uint32_t key, int dim, int nch, int gl,
-                                                const OptScalars& o, float scale, RowState<V, IT>& r,
-                                                const Row<V, IT>& g, float g_lin, bool lin) {
+__device__ __forceinline__ void update_store_row(const trs_table& t, size_t roff, int nch, int gl, const OptScalars& o,
+                                                 float scale, Row<V, IT>& p, Row<V, IT>& s0, Row<V, IT>& s1,
+                                                 const Row<V, IT>& g) {
 #pragma unroll
     for (int a = 0; a < IT; ++a)
 #pragma unroll
-        for (int b = 0; b < V; ++b) opt_update(o, scale, g.c[a][b], r.p.c[a][b], r.s0.c[a][b], r.s1.c[a][b]);
-    const size_t roff = (size_t)key * dim;
-    store_row<V, G, IT>(t.emb + roff, nch, gl, r.p);
-    if (o.kind != TRS_OPT_SGD) store_row<V, G, IT>(t.emb_s0 + roff, nch, gl, r.s0);
-    if (o.kind == TRS_OPT_SPARSE_ADAM) store_row<V, G, IT>(t.emb_s1 + roff, nch, gl, r.s1);
-    if (lin && gl == 0) {
-        opt_update(o, scale, g_lin, r.pl, r.l0, r.l1);
-        t.lin[key] = r.pl;
-        if (o.kind != TRS_OPT_SGD) t.lin_s0[key] = r.l0;
-        if (o.kind == TRS_OPT_SPARSE_ADAM) t.lin_s1[key] = r.l1;
-    }
+        for (int b = 0; b < V; ++b) opt_update(o, scale, g.c[a][b], p.c[a][b], s0.c[a][b], s1.c[a][b]);
+    store_row<V, G, IT>(t.emb + roff, nch, gl, p);
+    if (o.kind != TRS_OPT_SGD) store_row<V, G, IT>(t.emb_s0 + roff, nch, gl, s0);
+    if (o.kind == TRS_OPT_SPARSE_ADAM) store_row<V, G, IT>(t.emb_s1 + roff, nch, gl, s1);
+}
+// the width-1 companion of a row (bias / first-order weight), one thread
+__device__ __forceinline__ void update_lin(const trs_table& t, uint32_t key, const OptScalars& o, float scale, float g) {
+    float pl = __ldcg(t.lin + key), l0 = 0.f, l1 = 0.f;
+    if (o.kind != TRS_OPT_SGD) l0 = __ldcg(t.lin_s0 + key);
+    if (o.kind == TRS_OPT_SPARSE_ADAM) l1 = __ldcg(t.lin_s1 + key);
+    opt_update(o, scale, g, pl, l0, l1);
+    t.lin[key] = pl;
+    if (o.kind != TRS_OPT_SGD) t.lin_s0[key] = l0;
+    if (o.kind == TRS_OPT_SPARSE_ADAM) t.lin_s1[key] = l1;
 }
 
 // ---- cp.async ring: per-thread prefetch slots in shared memory (V == 4 only) -------------------
 // Every lane copies only the 16-byte chunks it will itself consume, so no cross-thread
 // synchronisation is needed: cp.async.wait_group makes a thread's own copies visible to it.
 constexpr int RING = 4;
-template <int V, int IT>
 #ifndef TRS_TRAIN_T1
 #define TRS_TRAIN_T1 512  // threads per CTA for rows of <= 32 chunks (tuning hook: -DTRS_TRAIN_T1=256|384|512)
 #endif
+template <int V, int IT>
 constexpr int train_threads() { return V == 1 ? 256 : (IT == 1 ? TRS_TRAIN_T1 : (IT == 2 ? 256 : 128)); }
 template <int V, int IT>
-constexpr size_t train_smem_bytes() {
+constexpr size_t ring_smem_bytes() {
     return V == 1 ? 0 : (size_t)train_threads<V, IT>() * (2 * RING * 16 + RING * 4 * IT * 16);
+}
+// + the partial sums of a CTA-cooperative long-segment reduce: one row slice per thread, one scalar per group
+template <int V, int IT>
+constexpr size_t train_smem_bytes() {
+    return ring_smem_bytes<V, IT>() + (size_t)train_threads<V, IT>() * (IT * V * 4 + 4);
 }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -254,118 +237,10 @@ struct Ring {
     }
 };
 
-// A chunk of a long segment: sum its (<= LONG_CHUNK) staged rows in lookup order into a partial;
-// the group whose chunk completes the segment adds the partials in chunk order and updates the row.
-// All lookup ids of the chunk are fetched in one go, then all its rows (one L2 round trip each).
-template <int NET, int V, int G, int IT>
-__device__ __noinline__ void chunk_item(const uint4 it, int ci, const trs_model& m, const PlanPtrs& plan,
-                                           const Stage& st, int64_t s, int64_t lo, int dim, int nch, int gl,
-                                           const OptScalars& o, float scale) {
-    constexpr int NB = (LONG_CHUNK / 2) / IT > 0 ? (LONG_CHUNK / 2) / IT : 1;  // rows in flight per batch (register budget)
-    const SpaceRef sp = resolve_space<NET>((int)(it.x & 0xffu), m, plan, st, lo);
-    const int cc = (int)((it.x >> 8) & 0xffu);
-    const uint32_t* P = sp.P + it.y;
-    const uint4 seg = plan.long_segs[(size_t)s * plan.long_cap + it.z];
-    uint32_t j[LONG_CHUNK];
-#pragma unroll
-    for (int q = 0; q < LONG_CHUNK; ++q) j[q] = P[q < cc ? q : 0];
-    const uint32_t key = sp.K[seg.y];
-    if (it.w == 0) {  // first chunk of the segment: pull the row's param + state towards L2 now
-        const size_t roff = (size_t)key * dim;
-        prefetch_row<V, G, IT>(sp.t->emb + roff, nch, gl);
-        if (o.kind != TRS_OPT_SGD) prefetch_row<V, G, IT>(sp.t->emb_s0 + roff, nch, gl);
-        if (o.kind == TRS_OPT_SPARSE_ADAM) prefetch_row<V, G, IT>(sp.t->emb_s1 + roff, nch, gl);
-    }
-    Row<V, IT> acc;
-    row_zero(acc);
-    float accl = 0.f;
-#pragma unroll
-    for (int b0 = 0; b0 < LONG_CHUNK; b0 += NB) {
-        if (b0 < cc) {
-            Row<V, IT> r[NB];
-            float l[NB];
-#pragma unroll
-            for (int q = 0; q < NB; ++q) {
-                if (b0 + q < cc) {
-                    r[q] = load_row_cg<V, G, IT>(sp.stage + (size_t)j[b0 + q] * dim, nch, gl);
-                    l[q] = sp.stage_lin ? __ldcg(sp.stage_lin + j[b0 + q]) : 0.f;
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < NB; ++q) {
-                if (b0 + q < cc) {
-                    row_acc(acc, r[q]);
-                    accl = __fadd_rn(accl, l[q]);
-                }
-            }
-        }
-    }
-    const uint32_t first = seg.w;  // index of the segment's first chunk == its first partial slot
-    const int n_chunks = ((int)seg.z + LONG_CHUNK - 1) / LONG_CHUNK;
-    store_row<V, G, IT>(st.partials + (size_t)ci * dim, nch, gl, acc);
-    if (gl == 0) st.partials_lin[ci] = accl;
-    __threadfence();
-    constexpr unsigned GM = (G == 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u);
-    const unsigned gmask = GM << ((threadIdx.x & 31) & ~(G - 1));
-    __syncwarp(gmask);
-    unsigned old = 0;
-    if (gl == 0) old = atomicAdd(&st.seg_arrive[it.z], 1u);
-    old = __shfl_sync(gmask, old, 0, G);
-    if ((int)old != n_chunks - 1) return;
-    __threadfence();
-    if (gl == 0) st.seg_arrive[it.z] = 0u;  // ready for the next step
-    RowState<V, IT> rs = load_state<V, G, IT>(*sp.t, key, dim, nch, gl, o.kind, sp.stage_lin != nullptr);
-    Row<V, IT> g;
-    row_zero(g);
-    float g_lin = 0.f;
-    constexpr int PB = 8 / (IT > 2 ? 2 : 1);
-    for (int q = 0; q < n_chunks; q += PB) {
-        Row<V, IT> r[PB];
-        float l[PB];
-#pragma unroll
-        for (int z = 0; z < PB; ++z) {
-            if (q + z < n_chunks) {
-                r[z] = load_row_cg<V, G, IT>(st.partials + (size_t)(first + q + z) * dim, nch, gl);
-                l[z] = __ldcg(st.partials_lin + first + q + z);
-            }
-        }
-#pragma unroll
-        for (int z = 0; z < PB; ++z) {
-            if (q + z < n_chunks) {
-                row_acc(g, r[z]);
-                g_lin = __fadd_rn(g_lin, l[z]);
-            }
-        }
-    }
-    apply_and_store<V, G, IT>(*sp.t, key, dim, nch, gl, o, scale, rs, g, g_lin, sp.stage_lin != nullptr);
-}
-
 // ids of one sample, as 32-bit row numbers (every table has < 2^32 rows, checked by plan_build)
 struct SampleIds {
     uint32_t u, ip, in, pm[MF], nm[MF];
 };
-struct SampleIds3 {
-    uint32_t u, ip, in;
-};
-__device__ __forceinline__ SampleIds3 load_ids3(const trs_epoch& ep, int64_t smp) {
-    SampleIds3 r;
-    r.u = (uint32_t)ep.user[smp];
-    r.ip = (uint32_t)ep.pos[smp];
-    r.in = (uint32_t)ep.neg[smp];
-    return r;
-}
-__device__ __forceinline__ SampleIds with_meta(const trs_epoch& ep, const SampleIds3& a, int64_t smp, int F) {
-    SampleIds r;
-    r.u = a.u;
-    r.ip = a.ip;
-    r.in = a.in;
-#pragma unroll
-    for (int f = 0; f < MF; ++f) {
-        r.pm[f] = f < F ? (uint32_t)ep.pos_meta[smp * F + f] : 0u;
-        r.nm[f] = f < F ? (uint32_t)ep.neg_meta[smp * F + f] : 0u;
-    }
-    return r;
-}
 __device__ __forceinline__ SampleIds load_ids(const trs_epoch& ep, int64_t smp, int F) {
     SampleIds r;
     r.u = (uint32_t)ep.user[smp];
@@ -377,6 +252,16 @@ __device__ __forceinline__ SampleIds load_ids(const trs_epoch& ep, int64_t smp, 
         r.nm[f] = f < F ? (uint32_t)ep.neg_meta[smp * F + f] : 0u;
     }
     return r;
+}
+
+// optimizer state of a row that phase A updates itself (zeros where the optimizer has none / not fused)
+template <int V, int G, int IT>
+__device__ __forceinline__ void load_state_rows(const trs_table& t, size_t roff, int nch, int gl, int kind, bool fused,
+                                                Row<V, IT>& s0, Row<V, IT>& s1) {
+    row_zero(s0);
+    row_zero(s1);
+    if (fused && kind != TRS_OPT_SGD) s0 = load_row_cg<V, G, IT>(t.emb_s0 + roff, nch, gl);
+    if (fused && kind == TRS_OPT_SPARSE_ADAM) s1 = load_row_cg<V, G, IT>(t.emb_s1 + roff, nch, gl);
 }
 
 // ---- the kernel -------------------------------------------------------------------------------
@@ -393,12 +278,15 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
     Ring<NT, IT> ring;
     ring.desc = reinterpret_cast<uint4*>(smem_raw);
     ring.rows = reinterpret_cast<float4*>(smem_raw + (size_t)2 * RING * NT * sizeof(uint4));
+    float* s_part = reinterpret_cast<float*>(smem_raw + ring_smem_bytes<V, IT>());  // [GPB][IT][G][V]
+    float* s_part_lin = s_part + (size_t)NT * IT * V;                                // [GPB]
 
     const int dim = m.dim, nch = dim / V, F = m.n_meta;
     const int gl = threadIdx.x % G;
     constexpr int GPW = 32 / G;                        // groups per warp
     constexpr int GPB = NT / G;                        // groups per block
-    const int gid = blockIdx.x * GPB + threadIdx.x / G;
+    const int g_in_cta = threadIdx.x / G;
+    const int gid = blockIdx.x * GPB + g_in_cta;
     const int ngroups = gridDim.x * GPB;
     const int gid_warp0 = gid - (gid % GPW);           // first group of my warp
     const int kind = opt.kind;
@@ -481,27 +369,19 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
             const uint32_t j = sp.P[it.y + q];
             row_acc(g, load_row_cg<V, G, IT>(sp.stage + (size_t)j * dim, nch, gl));
         }
-#pragma unroll
-        for (int a = 0; a < IT; ++a)
-#pragma unroll
-            for (int b = 0; b < V; ++b) opt_update(opt, scale, g.c[a][b], p.c[a][b], s0.c[a][b], s1.c[a][b]);
-        store_row<V, G, IT>(sp.t->emb + roff, nch, gl, p);
-        if (kind != TRS_OPT_SGD) store_row<V, G, IT>(sp.t->emb_s0 + roff, nch, gl, s0);
-        if (kind == TRS_OPT_SPARSE_ADAM) store_row<V, G, IT>(sp.t->emb_s1 + roff, nch, gl, s1);
+        update_store_row<V, G, IT>(*sp.t, roff, nch, gl, opt, scale, p, s0, s1, g);
     };
 
     // ---- prologue: what step `first_step` needs before its phase A ----
-    int n_items_cur = 0, n_chunks_cur = 0;
-    SampleIds ids0;   // ids of this group's first sample of the current step
-    SampleIds3 ids1;  // and (user, pos, neg) of its second
+    int n_items_cur = 0, n_long_cur = 0;
+    SampleIds ids0;  // ids of this group's first sample of the current step
     {
         const int64_t s0i = first_step;
         const int64_t lo0 = s0i * (int64_t)ep.batch;
         const int Bs0 = (int)min((int64_t)ep.batch, ep.n_samples - lo0);
         n_items_cur = min((int)plan.item_cnt[s0i], plan.item_cap);
-        n_chunks_cur = min((int)plan.chunk_cnt[s0i], plan.chunk_cap);
+        n_long_cur = min((int)plan.long_cnt[s0i], plan.long_cap);
         ids0 = load_ids(ep, lo0 + min(gid, Bs0 - 1), F);
-        ids1 = load_ids3(ep, lo0 + min(gid + ngroups, Bs0 - 1));
         const uint4* items0 = plan.items + (size_t)s0i * plan.item_cap;
         for (int n = 0; n < 2 * RING; ++n) issue_desc(items0, n_items_cur, n);
         cp_async_commit();
@@ -513,33 +393,29 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
         const int Bs = (int)min((int64_t)ep.batch, ep.n_samples - lo);
         const float invB = 1.0f / (float)Bs;
         const uint4* items = plan.items + (size_t)s * plan.item_cap;
-        const int n_items = n_items_cur, n_chunks = n_chunks_cur;
+        const int n_items = n_items_cur, n_long = n_long_cur;
         const float scale = opt.step_scale[s];
         // what the next step will need (loaded now, used after two barriers)
-        int n_items_next = 0, n_chunks_next = 0;
-        SampleIds nid0 = ids0;  // ids of my first two samples of the NEXT step
-        SampleIds3 nid1 = ids1;
+        int n_items_next = 0, n_long_next = 0;
+        SampleIds nid0 = ids0;  // ids of my first sample of the NEXT step
         const int64_t lo2 = lo + ep.batch;
         const int Bs2 = (si + 1 < n_steps) ? (int)min((int64_t)ep.batch, ep.n_samples - lo2) : 0;
         if (si + 1 < n_steps) {
             n_items_next = min((int)plan.item_cnt[s + 1], plan.item_cap);
-            n_chunks_next = min((int)plan.chunk_cnt[s + 1], plan.chunk_cap);
+            n_long_next = min((int)plan.long_cnt[s + 1], plan.long_cap);
             nid0 = load_ids(ep, lo2 + min(gid, Bs2 - 1), F);
-            nid1 = load_ids3(ep, lo2 + min(gid + ngroups, Bs2 - 1));
         }
         // width-1 companion work of this thread (phase B): descriptor fetched now
         const int lin_i = threadIdx.x * gridDim.x + blockIdx.x;  // every CTA gets every gridDim-th item
         uint4 lin_it = make_uint4(0, 0, 0, 0);
         if (lin_i < n_items) lin_it = items[lin_i];
 
-        // debug trace: slots 0-7 by thread 0 (a warp that also owns chunks), 8-15 by thread NT/2
+        // debug trace: slots 0-7 by thread 0, 8-15 by thread NT/2
         const bool tracing = (dbg & 64) && (threadIdx.x == 0 || threadIdx.x == NT / 2);
         unsigned long long* tr = st.trace + ((size_t)si * gridDim.x + blockIdx.x) * 16 + (threadIdx.x ? 8 : 0);
         if (tracing) tr[0] = global_ns();
         // ------------------------------ phase A ------------------------------------------
         float hsum = 0.f;
-        // NET == TRS_NET_MLP: the gradient rows were staged by the tower's backward (mlp.cu); this
-        // kernel only runs the reduce + update phase
         if constexpr (NET != TRS_NET_MLP)
         if (!(dbg & 1))
         for (int b0 = gid_warp0; b0 < Bs; b0 += ngroups) {   // warp-uniform trip count
@@ -547,13 +423,18 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
             const bool valid = b_raw < Bs;
             const int b = valid ? b_raw : Bs - 1;
             const int64_t smp = lo + b;
-            const SampleIds id = (b0 == gid_warp0) ? ids0 : ((b0 == gid_warp0 + ngroups) ? with_meta(ep, ids1, smp, F) : load_ids(ep, smp, F));
+            const SampleIds id = (b0 == gid_warp0) ? ids0 : load_ids(ep, smp, F);
             const int64_t* pm = F ? ep.pos_meta + smp * F : nullptr;
             const int64_t* nm = F ? ep.neg_meta + smp * F : nullptr;
-            // every gather of the sample issued back to back (L2 only: rows are rewritten by other SMs)
-            const Row<V, IT> ru = load_row_cg<V, G, IT>(m.user.emb + (size_t)id.u * dim, nch, gl);
-            const Row<V, IT> rp = load_row_cg<V, G, IT>(m.item.emb + (size_t)id.ip * dim, nch, gl);
-            const Row<V, IT> rn = load_row_cg<V, G, IT>(m.item.emb + (size_t)id.in * dim, nch, gl);
+            // rows this sample alone touches in this step: updated right here
+            const bool fu = valid && !(dbg & 128) && plan.single_user[lo + b];
+            const bool fp = valid && !(dbg & 128) && plan.single_item[2 * lo + b];
+            const bool fn = valid && !(dbg & 128) && plan.single_item[2 * lo + Bs + b];
+            const size_t ou = (size_t)id.u * dim, op = (size_t)id.ip * dim, on = (size_t)id.in * dim;
+            // every load of the sample issued back to back (L2 only: rows are rewritten by other SMs)
+            Row<V, IT> ru = load_row_cg<V, G, IT>(m.user.emb + ou, nch, gl);
+            Row<V, IT> rp = load_row_cg<V, G, IT>(m.item.emb + op, nch, gl);
+            Row<V, IT> rn = load_row_cg<V, G, IT>(m.item.emb + on, nch, gl);
             Row<V, IT> mp[MF], mn[MF];
             float wp = 0.f, wn = 0.f;  // FM: sum of the metadata first-order weights
 #pragma unroll
@@ -573,15 +454,19 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
             const float bu = m.user.lin ? __ldcg(m.user.lin + id.u) : 0.f;
             const float bip = m.item.lin ? __ldcg(m.item.lin + id.ip) : 0.f;
             const float bin = m.item.lin ? __ldcg(m.item.lin + id.in) : 0.f;
-            // optimizer state of the rows this sample touches -> L2, for phase B's ring refills
+            Row<V, IT> su0, su1, sp0, sp1, sn0, sn1;
+            load_state_rows<V, G, IT>(m.user, ou, nch, gl, kind, fu, su0, su1);
+            load_state_rows<V, G, IT>(m.item, op, nch, gl, kind, fp, sp0, sp1);
+            load_state_rows<V, G, IT>(m.item, on, nch, gl, kind, fn, sn0, sn1);
+            // optimizer state of the shared rows -> L2, for phase B's ring refills
             if (kind != TRS_OPT_SGD && valid && !(dbg & 16)) {
-                prefetch_row<V, G, IT>(m.user.emb_s0 + (size_t)id.u * dim, nch, gl);
-                prefetch_row<V, G, IT>(m.item.emb_s0 + (size_t)id.ip * dim, nch, gl);
-                prefetch_row<V, G, IT>(m.item.emb_s0 + (size_t)id.in * dim, nch, gl);
+                if (!fu) prefetch_row<V, G, IT>(m.user.emb_s0 + ou, nch, gl);
+                if (!fp) prefetch_row<V, G, IT>(m.item.emb_s0 + op, nch, gl);
+                if (!fn) prefetch_row<V, G, IT>(m.item.emb_s0 + on, nch, gl);
                 if (kind == TRS_OPT_SPARSE_ADAM) {
-                    prefetch_row<V, G, IT>(m.user.emb_s1 + (size_t)id.u * dim, nch, gl);
-                    prefetch_row<V, G, IT>(m.item.emb_s1 + (size_t)id.ip * dim, nch, gl);
-                    prefetch_row<V, G, IT>(m.item.emb_s1 + (size_t)id.in * dim, nch, gl);
+                    if (!fu) prefetch_row<V, G, IT>(m.user.emb_s1 + ou, nch, gl);
+                    if (!fp) prefetch_row<V, G, IT>(m.item.emb_s1 + op, nch, gl);
+                    if (!fn) prefetch_row<V, G, IT>(m.item.emb_s1 + on, nch, gl);
                 }
             }
             // pooled sums over the fields beyond MF (rare): Sx = sum of rows, Qx = sum of squares
@@ -605,6 +490,8 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
                 }
             }
 
+            Row<V, IT> gu, gp, gn;   // gradient rows of the user / positive / negative lookups
+            float gbu = 0.f, gbp, gbn;  // and of their width-1 companions
             if (NET == TRS_NET_LINEAR) {
                 // v = item + sum_f meta_f (feature order), s = <u, v> + b_u + b_i
                 Row<V, IT> vp = rp, vn = rn;
@@ -619,16 +506,12 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
                 const float sn = (group_sum<G>(row_dot_partial(ru, vn)) + bu) + bin;
                 const float h = __fadd_rn(__fsub_rn(sn, sp), 1.0f);
                 const float g = (h >= 0.f) ? invB : 0.f;
-                if (valid) {
-                    if (gl == 0) hsum += fmaxf(h, 0.f);
-                    store_row<V, G, IT>(st.gU + (size_t)b * dim, nch, gl, row_scaled_diff(g, vn, vp));
-                    store_row<V, G, IT>(st.gI + (size_t)b * dim, nch, gl, row_scaled(-g, ru));
-                    store_row<V, G, IT>(st.gI + (size_t)(Bs + b) * dim, nch, gl, row_scaled(g, ru));
-                    if (gl == 0) {
-                        st.gbI[b] = -g;
-                        st.gbI[Bs + b] = g;
-                    }
-                }
+                if (valid && gl == 0) hsum += fmaxf(h, 0.f);
+                gu = row_scaled_diff(g, vn, vp);
+                gp = row_scaled(-g, ru);
+                gn = row_scaled(g, ru);
+                gbp = -g;
+                gbn = g;
             } else {
                 // S = sum_k e_k, Q = sum_k e_k^2 over fields user, item, meta_f
                 Row<V, IT> Sp, Sn;
@@ -663,21 +546,22 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
                 const float g = (h >= 0.f) ? invB : 0.f;
                 const float dp = -g * sp * (1.0f - sp);
                 const float dn = g * sn * (1.0f - sn);
-                if (valid) {
-                    if (gl == 0) hsum += fmaxf(h, 0.f);
-                    Row<V, IT> gu;
+                if (valid && gl == 0) hsum += fmaxf(h, 0.f);
 #pragma unroll
-                    for (int i = 0; i < IT; ++i)
+                for (int i = 0; i < IT; ++i)
 #pragma unroll
-                        for (int k = 0; k < V; ++k)
-                            // two separately rounded products, like the reference's two lookups: when
-                            // pos == neg they cancel to an exact 0 (an FMA would leave a ~1e-10 residue
-                            // that Adagrad/Adam's g/(|g|+eps) blows up into a step of ~lr)
-                            gu.c[i][k] = __fadd_rn(__fmul_rn(dp, Sp.c[i][k] - ru.c[i][k]),
-                                                   __fmul_rn(dn, Sn.c[i][k] - ru.c[i][k]));
-                    store_row<V, G, IT>(st.gU + (size_t)b * dim, nch, gl, gu);
-                    store_row<V, G, IT>(st.gI + (size_t)b * dim, nch, gl, row_scaled_diff(dp, Sp, rp));
-                    store_row<V, G, IT>(st.gI + (size_t)(Bs + b) * dim, nch, gl, row_scaled_diff(dn, Sn, rn));
+                    for (int k = 0; k < V; ++k)
+                        // two separately rounded products, like the reference's two lookups: when
+                        // pos == neg they cancel to an exact 0 (an FMA would leave a ~1e-10 residue
+                        // that Adagrad/Adam's g/(|g|+eps) blows up into a step of ~lr)
+                        gu.c[i][k] = __fadd_rn(__fmul_rn(dp, Sp.c[i][k] - ru.c[i][k]),
+                                               __fmul_rn(dn, Sn.c[i][k] - ru.c[i][k]));
+                gp = row_scaled_diff(dp, Sp, rp);
+                gn = row_scaled_diff(dn, Sn, rn);
+                gbu = dp + dn;
+                gbp = dp;
+                gbn = dn;
+                if (valid) {  // metadata rows are always reduced in phase B
 #pragma unroll
                     for (int f = 0; f < MF; ++f) {
                         if (f < F) {
@@ -691,30 +575,55 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
                         r = load_row_cg<V, G, IT>(m.meta[f].emb + (size_t)nm[f] * dim, nch, gl);
                         store_row<V, G, IT>(st.gM[f] + (size_t)(Bs + b) * dim, nch, gl, row_scaled_diff(dn, Sn, r));
                     }
-                    if (gl == 0) {
-                        st.gbU[b] = dp + dn;
-                        st.gbI[b] = dp;
-                        st.gbI[Bs + b] = dn;
-                    }
                 }
             }
+            if (valid) {
+                // user row
+                if (fu) {
+                    update_store_row<V, G, IT>(m.user, ou, nch, gl, opt, scale, ru, su0, su1, gu);
+                    if (NET == TRS_NET_FM && m.user.lin && gl == 0) update_lin(m.user, id.u, opt, scale, gbu);
+                } else {
+                    store_row<V, G, IT>(st.gU + (size_t)b * dim, nch, gl, gu);
+                    if (NET == TRS_NET_FM && gl == 0) st.gbU[b] = gbu;
+                }
+                // Linear pools the metadata rows into the item row: their gradient IS the item row's, so
+                // it stays staged for the metadata reduce even when the item row itself is updated here
+                const bool stage_items = (NET == TRS_NET_LINEAR && F > 0);
+                // FM: d linear_metadata = delta, the same scalar as d linear_item -> always staged
+                const bool meta_lin = (NET == TRS_NET_FM && F > 0);
+                if (fp) {
+                    update_store_row<V, G, IT>(m.item, op, nch, gl, opt, scale, rp, sp0, sp1, gp);
+                    if (m.item.lin && gl == 1 % G) update_lin(m.item, id.ip, opt, scale, gbp);
+                }
+                if (!fp || stage_items) store_row<V, G, IT>(st.gI + (size_t)b * dim, nch, gl, gp);
+                if ((!fp || meta_lin) && gl == 0) st.gbI[b] = gbp;
+                if (fn) {
+                    update_store_row<V, G, IT>(m.item, on, nch, gl, opt, scale, rn, sn0, sn1, gn);
+                    if (m.item.lin && gl == 2 % G) update_lin(m.item, id.in, opt, scale, gbn);
+                }
+                if (!fn || stage_items) store_row<V, G, IT>(st.gI + (size_t)(Bs + b) * dim, nch, gl, gn);
+                if ((!fn || meta_lin) && gl == 0) st.gbI[Bs + b] = gbn;
+            }
         }
-        // the step's first work items: their descriptors landed long ago; fetch param + state rows
-        // now (nothing in phase A writes them), so only the staged gradients wait for the barrier
+        // the step's first ring items: their descriptors landed long ago; fetch param + state rows
+        // now (nothing in phase A writes them: they are not single-lookup rows), so only the staged
+        // gradients wait for the barrier
         cp_async_wait<0>();
         if (!(dbg & 4)) {
             for (int n = 0; n < RING; ++n) issue_state(n_items, n, lo);
         }
         cp_async_commit();
 
-        hsum = warp_sum(hsum);
-        if ((threadIdx.x & 31) == 0) s_loss[threadIdx.x >> 5] = hsum;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float H = 0.f;
+        if (NET != TRS_NET_MLP) {
+            hsum = warp_sum(hsum);
+            if ((threadIdx.x & 31) == 0) s_loss[threadIdx.x >> 5] = hsum;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float H = 0.f;
 #pragma unroll
-            for (int w = 0; w < NT / 32; ++w) H += s_loss[w];
-            st.loss_part[(size_t)si * gridDim.x + blockIdx.x] = H;
+                for (int w = 0; w < NT / 32; ++w) H += s_loss[w];
+                st.loss_part[(size_t)si * gridDim.x + blockIdx.x] = H;
+            }
         }
         if (tracing) tr[1] = global_ns();
         if (!(dbg & 8)) grid_barrier(st.barrier, bar_target);
@@ -725,31 +634,35 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
             for (int n = 0; n < RING; ++n) issue_grad(n_items, n, lo);
         }
         cp_async_commit();
-        // rows of the next step's samples -> L2 (coherent: a row updated below is still read right
-        // after the next barrier); the ids were loaded a phase ago
+        // rows (parameters and optimizer state) of the next step's samples -> L2 (coherent: a row updated
+        // below is still read right after the next barrier)
         ids0 = nid0;
-        ids1 = nid1;
-        if (si + 1 < n_steps && !(dbg & 16)) {
-            if (gid < Bs2) {
-                prefetch_row<V, G, IT>(m.user.emb + (size_t)ids0.u * dim, nch, gl);
-                prefetch_row<V, G, IT>(m.item.emb + (size_t)ids0.ip * dim, nch, gl);
-                prefetch_row<V, G, IT>(m.item.emb + (size_t)ids0.in * dim, nch, gl);
-            }
-            if (gid + ngroups < Bs2) {
-                prefetch_row<V, G, IT>(m.user.emb + (size_t)ids1.u * dim, nch, gl);
-                prefetch_row<V, G, IT>(m.item.emb + (size_t)ids1.ip * dim, nch, gl);
-                prefetch_row<V, G, IT>(m.item.emb + (size_t)ids1.in * dim, nch, gl);
-            }
-            for (int b = gid + 2 * ngroups; b < Bs2; b += ngroups) {
-                const int64_t u = ep.user[lo2 + b], ip = ep.pos[lo2 + b], in = ep.neg[lo2 + b];
+        if (si + 1 < n_steps && !(dbg & 16) && NET != TRS_NET_MLP) {
+            for (int b = gid; b < Bs2; b += ngroups) {
+                uint32_t u = ids0.u, ip = ids0.ip, in = ids0.in;
+                if (b != gid) {
+                    u = (uint32_t)ep.user[lo2 + b];
+                    ip = (uint32_t)ep.pos[lo2 + b];
+                    in = (uint32_t)ep.neg[lo2 + b];
+                }
                 prefetch_row<V, G, IT>(m.user.emb + (size_t)u * dim, nch, gl);
                 prefetch_row<V, G, IT>(m.item.emb + (size_t)ip * dim, nch, gl);
                 prefetch_row<V, G, IT>(m.item.emb + (size_t)in * dim, nch, gl);
+                if (kind != TRS_OPT_SGD) {
+                    prefetch_row<V, G, IT>(m.user.emb_s0 + (size_t)u * dim, nch, gl);
+                    prefetch_row<V, G, IT>(m.item.emb_s0 + (size_t)ip * dim, nch, gl);
+                    prefetch_row<V, G, IT>(m.item.emb_s0 + (size_t)in * dim, nch, gl);
+                }
+                if (kind == TRS_OPT_SPARSE_ADAM) {
+                    prefetch_row<V, G, IT>(m.user.emb_s1 + (size_t)u * dim, nch, gl);
+                    prefetch_row<V, G, IT>(m.item.emb_s1 + (size_t)ip * dim, nch, gl);
+                    prefetch_row<V, G, IT>(m.item.emb_s1 + (size_t)in * dim, nch, gl);
+                }
             }
         }
         if (tracing) tr[4] = global_ns();
-        // width-1 companions (biases / first-order weights): one THREAD per short segment; the
-        // loads are issued here and consumed after the chunk work below
+        // width-1 companions (biases / first-order weights) of the short segments: one THREAD per segment;
+        // the loads are issued here and consumed after the long segments below
         float lin_p = 0.f, lin_0 = 0.f, lin_1 = 0.f, lin_g = 0.f;
         bool lin_live = false;
         SpaceRef lin_sp = {};
@@ -765,17 +678,72 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
             }
         }
         if (tracing) tr[5] = global_ns();
-        // chunks of long segments, spread over the CTAs and over the warps of a CTA
+        // long segments: one CTA per segment, every row group sums a strided subset of its lookups
         if (!(dbg & 2)) {
-            const uint4* chunks = plan.chunks + (size_t)s * plan.chunk_cap;
-            const int g_in_cta = threadIdx.x / G;
-            // chunk ci -> CTA ci % grid, local index lc = ci / grid -> group (lc * 4) mod GPB (+ carry)
-            for (int lc = 0; lc * (int)gridDim.x + (int)blockIdx.x < n_chunks; ++lc) {
-                const int owner = (GPB >= 4) ? ((lc * 4) % GPB + ((lc * 4) / GPB) % 4) % GPB : lc % GPB;
-                if (owner == g_in_cta) {
-                    const int ci = lc * gridDim.x + blockIdx.x;
-                    chunk_item<NET, V, G, IT>(chunks[ci], ci, m, plan, st, s, lo, dim, nch, gl, opt, scale);
+            for (int sg = blockIdx.x; sg < n_long; sg += gridDim.x) {   // block-uniform trip count
+                const uint4 seg = plan.long_segs[(size_t)s * plan.long_cap + sg];  // space, start, length, row
+                const SpaceRef sp = resolve_space<NET>((int)seg.x, m, plan, st, lo);
+                const uint32_t* P = sp.P + seg.y;
+                const int c = (int)seg.z;
+                const uint32_t key = seg.w;
+                const size_t roff = (size_t)key * dim;
+                // the updating group fetches the row's parameter + state while the sums are formed
+                Row<V, IT> p, s0, s1;
+                row_zero(p); row_zero(s0); row_zero(s1);
+                if (g_in_cta == 0) {
+                    p = load_row_cg<V, G, IT>(sp.t->emb + roff, nch, gl);
+                    if (kind != TRS_OPT_SGD) s0 = load_row_cg<V, G, IT>(sp.t->emb_s0 + roff, nch, gl);
+                    if (kind == TRS_OPT_SPARSE_ADAM) s1 = load_row_cg<V, G, IT>(sp.t->emb_s1 + roff, nch, gl);
                 }
+                Row<V, IT> acc;
+                row_zero(acc);
+                float accl = 0.f;
+                constexpr int U = 4;  // staged rows in flight per group
+                for (int q0 = g_in_cta; q0 < c; q0 += U * GPB) {
+                    uint32_t j[U];
+#pragma unroll
+                    for (int z = 0; z < U; ++z) j[z] = (q0 + z * GPB < c) ? P[q0 + z * GPB] : 0u;
+                    Row<V, IT> r[U];
+                    float l[U];
+#pragma unroll
+                    for (int z = 0; z < U; ++z) {
+                        if (q0 + z * GPB < c) {
+                            r[z] = load_row_cg<V, G, IT>(sp.stage + (size_t)j[z] * dim, nch, gl);
+                            l[z] = (sp.stage_lin && gl == 0) ? __ldcg(sp.stage_lin + j[z]) : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int z = 0; z < U; ++z) {
+                        if (q0 + z * GPB < c) {
+                            row_acc(acc, r[z]);
+                            accl = __fadd_rn(accl, l[z]);
+                        }
+                    }
+                }
+                // partial sums -> shared memory, [group][chunk of the row][lane][V]
+#pragma unroll
+                for (int a = 0; a < IT; ++a)
+#pragma unroll
+                    for (int k = 0; k < V; ++k) s_part[((g_in_cta * IT + a) * G + gl) * V + k] = acc.c[a][k];
+                if (gl == 0) s_part_lin[g_in_cta] = accl;
+                __syncthreads();
+                if (g_in_cta == 0) {
+                    Row<V, IT> g;
+                    row_zero(g);
+                    float g_lin = 0.f;
+                    const int ng = min(GPB, c);  // groups that summed at least one row, in group order
+                    for (int q = 0; q < ng; ++q) {
+#pragma unroll
+                        for (int a = 0; a < IT; ++a)
+#pragma unroll
+                            for (int k = 0; k < V; ++k)
+                                g.c[a][k] = __fadd_rn(g.c[a][k], s_part[((q * IT + a) * G + gl) * V + k]);
+                        g_lin = __fadd_rn(g_lin, s_part_lin[q]);
+                    }
+                    update_store_row<V, G, IT>(*sp.t, roff, nch, gl, opt, scale, p, s0, s1, g);
+                    if (sp.stage_lin && gl == 0) update_lin(*sp.t, key, opt, scale, g_lin);
+                }
+                __syncthreads();
             }
         }
         // finish the width-1 companion items
@@ -793,18 +761,10 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
                 const uint4 it = items[i];
                 const SpaceRef sp = resolve_space<NET>((int)(it.x & 0xffu), m, plan, st, lo);
                 if (!sp.stage_lin) continue;
-                const trs_table& t = *sp.t;
-                const uint32_t key = it.z;
-                float pl = __ldcg(t.lin + key), l0 = 0.f, l1 = 0.f;
-                if (kind != TRS_OPT_SGD) l0 = __ldcg(t.lin_s0 + key);
-                if (kind == TRS_OPT_SPARSE_ADAM) l1 = __ldcg(t.lin_s1 + key);
                 float g_lin = __ldcg(sp.stage_lin + it.w);
                 const int c = (int)((it.x >> 8) & 0xffu);
                 for (int q = 1; q < c; ++q) g_lin = __fadd_rn(g_lin, __ldcg(sp.stage_lin + sp.P[it.y + q]));
-                opt_update(opt, scale, g_lin, pl, l0, l1);
-                t.lin[key] = pl;
-                if (kind != TRS_OPT_SGD) t.lin_s0[key] = l0;
-                if (kind == TRS_OPT_SPARSE_ADAM) t.lin_s1[key] = l1;
+                update_lin(*sp.t, it.z, opt, scale, g_lin);
             }
         }
         if (tracing) tr[6] = global_ns();
@@ -830,7 +790,7 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
         }
         cp_async_commit();
         n_items_cur = n_items_next;
-        n_chunks_cur = n_chunks_next;
+        n_long_cur = n_long_next;
         if (tracing) tr[3] = global_ns();
         if (!(dbg & 8)) grid_barrier(st.barrier, bar_target);
     }
@@ -848,24 +808,12 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
     }
 }
 
-// one CTA per SM: the ring takes most of the SM's shared memory
-template <int NET, int V, int G, int IT>
-static int train_grid_size() {
-    return device_props().sm_count;
-}
-
-template <int V, int G, int IT>
-static void query_grid(int net, int* grid) {
-    *grid = train_grid_size<TRS_NET_LINEAR, V, G, IT>();
-    (void)net;
-}
-
 template <int V, int G, int IT>
 static void launch_train(const trs_model* m, const trs_epoch* ep, const OptScalars* opt,
                          const PlanPtrs* plan, const Stage* st, int first_step, int n_steps,
                          float* loss, int grid, cudaStream_t stream, cudaError_t* err) {
-    // TRS_DEBUG_SKIP (timing experiments only, results are wrong): 1 phase A, 2 long-segment chunks,
-    // 4 phase B, 8 grid barriers, 16 L2 prefetches
+    // TRS_DEBUG_SKIP (timing experiments only, results are wrong): 1 phase A, 2 long segments, 4 ring,
+    // 8 grid barriers, 16 L2 prefetches, 32 width-1 companions, 64 phase trace, 128 no phase-A updates
     const char* dbg_env = getenv("TRS_DEBUG_SKIP");
     int dbg = dbg_env ? atoi(dbg_env) : 0;
     void* args[] = {(void*)m, (void*)ep, (void*)opt, (void*)plan, (void*)st,
@@ -881,11 +829,8 @@ static void launch_train(const trs_model* m, const trs_epoch* ep, const OptScala
     *err = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(train_threads<V, IT>()), args, smem, stream);
 }
 
-static int train_grid_for(const trs_model* m, const RowShape& shape) {
-    int grid = 0;
-    TRS_DISPATCH_ROW_SHAPE(shape, query_grid, m->net, &grid);
-    return grid;
-}
+// one CTA per SM: the ring takes most of the SM's shared memory
+static int train_grid_for(const trs_model*, const RowShape&) { return device_props().sm_count; }
 
 }  // namespace trs
 
@@ -894,14 +839,7 @@ using namespace trs;
 extern "C" int trs_device_info(int* sm_count_host, int* train_grid_host, int* train_block_host) {
     if (sm_count_host) *sm_count_host = device_props().sm_count;
     if (train_block_host) *train_block_host = train_threads<4, 1>();
-    if (train_grid_host) {
-        trs_model m = {};
-        m.net = TRS_NET_FM;
-        m.dim = 64;
-        RowShape shape;
-        pick_row_shape(m.dim, &shape);
-        *train_grid_host = train_grid_for(&m, shape);
-    }
+    if (train_grid_host) *train_grid_host = device_props().sm_count;
     TRS_CUDA(cudaGetLastError());
     return TRS_OK;
 }
@@ -989,10 +927,7 @@ int trs::run_train_steps(const trs_model* model, const trs_epoch* ep, const trs_
     st.gbU = (float*)(W + SL.gbU);
     st.gbI = (float*)(W + SL.gbI);
     st.loss_part = (float*)(W + SL.loss_part);
-    st.partials = (float*)(W + SL.partials);
-    st.partials_lin = (float*)(W + SL.partials_lin);
-    st.seg_arrive = (unsigned*)(W + SL.sync_words);
-    st.barrier = st.seg_arrive + PL.long_cap + 32;
+    st.barrier = (unsigned*)(W + SL.sync_words);
     st.trace = (unsigned long long*)(W + SL.trace);
     TRS_CUDA(cudaMemsetAsync(W + SL.sync_words, 0, SL.sync_bytes, stream));
 
@@ -1007,21 +942,15 @@ int trs::run_train_steps(const trs_model* model, const trs_epoch* ep, const trs_
         pp.meta_perm[f] = (const uint32_t*)(P + PL.meta_perm[f]);
     }
     pp.item_cnt = (const uint32_t*)(P + PL.item_cnt);
-    pp.chunk_cnt = (const uint32_t*)(P + PL.chunk_cnt);
-    pp.chunks = (const uint4*)(P + PL.chunks);
+    pp.long_cnt = (const uint32_t*)(P + PL.long_cnt);
+    pp.single_user = (const uint8_t*)(P + PL.single_user);
+    pp.single_item = (const uint8_t*)(P + PL.single_item);
     pp.items = (const uint4*)(P + PL.items);
     pp.long_segs = (const uint4*)(P + PL.long_segs);
     pp.item_cap = PL.item_cap;
     pp.long_cap = PL.long_cap;
-    pp.chunk_cap = PL.chunk_cap;
 
-    OptScalars os;
-    os.kind = optim->kind;
-    os.omb1 = (float)(1.0 - optim->beta1);
-    os.omb2 = (float)(1.0 - optim->beta2);
-    os.eps = (float)optim->eps;
-    os.step_scale = optim->step_scale;
-
+    const OptScalars os = make_opt_scalars(optim);
     cudaError_t err = cudaSuccess;
     TRS_DISPATCH_ROW_SHAPE(shape, launch_train, model, ep, &os, &pp, &st, first_step, n_steps, loss,
                            grid, stream, &err);
