@@ -6,10 +6,12 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-variants = [("full", {}), ("no_phaseA", {"TRS_DEBUG_SKIP": "1"}), ("no_chunks", {"TRS_DEBUG_SKIP": "2"}),
-            ("no_ring", {"TRS_DEBUG_SKIP": "4"}), ("no_lin", {"TRS_DEBUG_SKIP": "32"}),
+variants = [("full", {}), ("no_phaseA", {"TRS_DEBUG_SKIP": "1"}), ("no_long", {"TRS_DEBUG_SKIP": "2"}),
+            ("no_short", {"TRS_DEBUG_SKIP": "4"}), ("no_lin", {"TRS_DEBUG_SKIP": "32"}),
             ("no_phaseB", {"TRS_DEBUG_SKIP": "38"}), ("no_sync", {"TRS_DEBUG_SKIP": "8"}),
-            ("only_sync", {"TRS_DEBUG_SKIP": "55"}), ("no_prefetch", {"TRS_DEBUG_SKIP": "16"})]
+            ("only_sync", {"TRS_DEBUG_SKIP": "55"}), ("no_prefetch", {"TRS_DEBUG_SKIP": "16"}),
+            ("no_fused_update", {"TRS_DEBUG_SKIP": "128"}), ("no_fused_lin", {"TRS_DEBUG_SKIP": "256"}),
+            ("A_only_no_fused", {"TRS_DEBUG_SKIP": str(2 + 4 + 32 + 128)}), ("A_only", {"TRS_DEBUG_SKIP": str(2 + 4 + 32)})]
 extra = sys.argv[1:]
 for name, env in variants:
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "200", "--warmup", "20",

@@ -229,6 +229,29 @@ build_items_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict
     }
 }
 
+// Bit 1 of a lookup's flag byte: its row is updated in phase B of the PREVIOUS step (it has >= 2 lookups
+// there), so a copy fetched during that phase may be stale -- the training kernel then reads the row after
+// the step barrier instead of taking it from its early shared-memory prefetch.
+__global__ void __launch_bounds__(256)
+dirty_flags_kernel(const uint32_t* __restrict__ keys, const int64_t* __restrict__ a, const int64_t* __restrict__ b,
+                   int mult, int64_t n_samples, int B, uint8_t* __restrict__ flags) {
+    const int64_t step = (int64_t)blockIdx.y + 1;  // lookups of step s+1 against the sorted rows of step s
+    const int Bs = (int)min((int64_t)B, n_samples - step * B);
+    const int len = mult * Bs;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= len) return;
+    const int64_t sample0 = step * (int64_t)B;
+    const uint32_t row = (uint32_t)((j < Bs) ? a[sample0 + j] : b[sample0 + j - Bs]);
+    const uint32_t* K = keys + (int64_t)mult * (step - 1) * B;
+    const int plen = mult * B;  // every step but the last is full
+    int lo = 0, hi = plen;      // lower bound of row in K
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (K[mid] < row) lo = mid + 1; else hi = mid;
+    }
+    if (lo + 1 < plen && K[lo] == row && K[lo + 1] == row) flags[(int64_t)mult * step * B + j] |= 2;
+}
+
 PlanLayout plan_layout(int64_t n_samples, int batch, int n_meta) {
     PlanLayout L;
     size_t off = 0;
@@ -336,6 +359,14 @@ extern "C" int trs_plan_build(const trs_model* model, const trs_epoch* ep, void*
     build_items(L.user_key, L.user_perm, 1, 0);
     build_items(L.item_key, L.item_perm, 2, 1);
     for (int f = 0; f < model->n_meta; ++f) build_items(L.meta_key[f], L.meta_perm[f], 2, 2 + f);
+    if (fuse_single && steps > 1) {
+        dim3 gu((unsigned)((ep->batch + 255) / 256), (unsigned)(steps - 1));
+        dirty_flags_kernel<<<gu, 256, 0, stream>>>((const uint32_t*)(P + L.user_key), ep->user, ep->user, 1,
+                                                   ep->n_samples, ep->batch, (uint8_t*)(P + L.single_user));
+        dim3 gi((unsigned)((2ll * ep->batch + 255) / 256), (unsigned)(steps - 1));
+        dirty_flags_kernel<<<gi, 256, 0, stream>>>((const uint32_t*)(P + L.item_key), ep->pos, ep->neg, 2,
+                                                   ep->n_samples, ep->batch, (uint8_t*)(P + L.single_item));
+    }
     TRS_CUDA(cudaGetLastError());
     return TRS_OK;
 }

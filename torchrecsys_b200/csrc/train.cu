@@ -213,10 +213,19 @@ template <int V, int IT>
 constexpr size_t ring_smem_bytes() {
     return V == 1 ? 0 : (size_t)train_threads<V, IT>() * (2 * RING * 16 + RING * 4 * IT * 16);
 }
+// Linear / FM use the same region for the early fetch of the NEXT step's rows instead (the ring only serves
+// the MLP tower's staged mode there): PF samples per row group x 9 rows (param, s0, s1 of user / pos / neg),
+// thread-private 16-byte slots like the ring's.
+constexpr int PF = 2;
+template <int V, int IT>
+constexpr size_t front_smem_bytes() {
+    const size_t pf = V == 1 ? 0 : (size_t)train_threads<V, IT>() * PF * 9 * IT * 16;
+    return pf > ring_smem_bytes<V, IT>() ? pf : ring_smem_bytes<V, IT>();
+}
 // + the partial sums of a CTA-cooperative long-segment reduce: one row slice per thread, one scalar per group
 template <int V, int IT>
 constexpr size_t train_smem_bytes() {
-    return ring_smem_bytes<V, IT>() + (size_t)train_threads<V, IT>() * (IT * V * 4 + 4);
+    return front_smem_bytes<V, IT>() + (size_t)train_threads<V, IT>() * (IT * V * 4 + 4);
 }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -272,13 +281,14 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
              const __grid_constant__ Stage st, const int first_step, const int n_steps,
              float* __restrict__ loss_out, const int dbg) {
     constexpr int NT = train_threads<V, IT>();
-    constexpr bool RINGED = (V == 4);
+    constexpr bool RINGED = (V == 4) && NET == TRS_NET_MLP;   // cp.async ring for the short segments
+    constexpr bool PFETCH = (V == 4) && NET != TRS_NET_MLP;   // early shared-memory fetch of the next step's rows
     __shared__ float s_loss[NT / 32];
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ring<NT, IT> ring;
     ring.desc = reinterpret_cast<uint4*>(smem_raw);
     ring.rows = reinterpret_cast<float4*>(smem_raw + (size_t)2 * RING * NT * sizeof(uint4));
-    float* s_part = reinterpret_cast<float*>(smem_raw + ring_smem_bytes<V, IT>());  // [GPB][IT][G][V]
+    float* s_part = reinterpret_cast<float*>(smem_raw + front_smem_bytes<V, IT>());  // [GPB][IT][G][V]
     float* s_part_lin = s_part + (size_t)NT * IT * V;                                // [GPB]
 
     const int dim = m.dim, nch = dim / V, F = m.n_meta;
@@ -291,6 +301,28 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
     const int gid_warp0 = gid - (gid % GPW);           // first group of my warp
     const int kind = opt.kind;
     unsigned bar_target = 0;
+    float4* pf_base = reinterpret_cast<float4*>(smem_raw);
+    // slot of (sample k of this group, row r: 3*table + {param, s0, s1}, chunk a) in the early-fetch region
+    auto pf_slot = [&](int k, int r, int a) { return pf_base + (((k * 9 + r) * IT + a) * NT + threadIdx.x); };
+    auto pf_issue = [&](int k, int r, const float* row) {
+#pragma unroll
+        for (int a = 0; a < IT; ++a) {
+            const int c = gl + a * G;
+            if (c < nch) cp_async16(pf_slot(k, r, a), row + (size_t)c * 4);
+        }
+    };
+    auto pf_row = [&](int k, int r) {
+        Row<V, IT> x;
+#pragma unroll
+        for (int a = 0; a < IT; ++a) {
+            const int c = gl + a * G;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < nch) v = *pf_slot(k, r, a);
+            x.c[a][0] = v.x; x.c[a][V > 1 ? 1 : 0] = v.y; x.c[a][V > 2 ? 2 : 0] = v.z; x.c[a][V > 3 ? 3 : 0] = v.w;
+        }
+        return x;
+    };
+    unsigned have = 0;  // bit 3k+t: the param (+ state, if fused) row of table t of my sample k sits in shared memory
 
     // ---- ring stages (phase B), item n of this group = global item n*ngroups + gid ----
     auto issue_desc = [&](const uint4* items, int n_items, int n) {
@@ -416,9 +448,10 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
         if (tracing) tr[0] = global_ns();
         // ------------------------------ phase A ------------------------------------------
         float hsum = 0.f;
+        if (PFETCH) cp_async_wait<0>();  // my own copies of this step's rows (issued during the last phase B)
         if constexpr (NET != TRS_NET_MLP)
         if (!(dbg & 1))
-        for (int b0 = gid_warp0; b0 < Bs; b0 += ngroups) {   // warp-uniform trip count
+        for (int b0 = gid_warp0, kk = 0; b0 < Bs; b0 += ngroups, ++kk) {   // warp-uniform trip count
             const int b_raw = b0 + (gid - gid_warp0);
             const bool valid = b_raw < Bs;
             const int b = valid ? b_raw : Bs - 1;
@@ -426,15 +459,19 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
             const SampleIds id = (b0 == gid_warp0) ? ids0 : load_ids(ep, smp, F);
             const int64_t* pm = F ? ep.pos_meta + smp * F : nullptr;
             const int64_t* nm = F ? ep.neg_meta + smp * F : nullptr;
-            // rows this sample alone touches in this step: updated right here
-            const bool fu = valid && !(dbg & 128) && plan.single_user[lo + b];
-            const bool fp = valid && !(dbg & 128) && plan.single_item[2 * lo + b];
-            const bool fn = valid && !(dbg & 128) && plan.single_item[2 * lo + Bs + b];
+            // rows this sample alone touches in this step (flag bit 0): updated right here
+            const bool fu = valid && !(dbg & 128) && (plan.single_user[lo + b] & 1);
+            const bool fp = valid && !(dbg & 128) && (plan.single_item[2 * lo + b] & 1);
+            const bool fn = valid && !(dbg & 128) && (plan.single_item[2 * lo + Bs + b] & 1);
             const size_t ou = (size_t)id.u * dim, op = (size_t)id.ip * dim, on = (size_t)id.in * dim;
+            // rows already sitting in shared memory (fetched during the previous step's phase B)
+            const bool hu = PFETCH && kk < PF && valid && ((have >> (3 * kk + 0)) & 1u);
+            const bool hp = PFETCH && kk < PF && valid && ((have >> (3 * kk + 1)) & 1u);
+            const bool hn = PFETCH && kk < PF && valid && ((have >> (3 * kk + 2)) & 1u);
             // every load of the sample issued back to back (L2 only: rows are rewritten by other SMs)
-            Row<V, IT> ru = load_row_cg<V, G, IT>(m.user.emb + ou, nch, gl);
-            Row<V, IT> rp = load_row_cg<V, G, IT>(m.item.emb + op, nch, gl);
-            Row<V, IT> rn = load_row_cg<V, G, IT>(m.item.emb + on, nch, gl);
+            Row<V, IT> ru = hu ? pf_row(kk, 0) : load_row_cg<V, G, IT>(m.user.emb + ou, nch, gl);
+            Row<V, IT> rp = hp ? pf_row(kk, 3) : load_row_cg<V, G, IT>(m.item.emb + op, nch, gl);
+            Row<V, IT> rn = hn ? pf_row(kk, 6) : load_row_cg<V, G, IT>(m.item.emb + on, nch, gl);
             Row<V, IT> mp[MF], mn[MF];
             float wp = 0.f, wn = 0.f;  // FM: sum of the metadata first-order weights
 #pragma unroll
@@ -454,10 +491,36 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
             const float bu = m.user.lin ? __ldcg(m.user.lin + id.u) : 0.f;
             const float bip = m.item.lin ? __ldcg(m.item.lin + id.ip) : 0.f;
             const float bin = m.item.lin ? __ldcg(m.item.lin + id.in) : 0.f;
-            Row<V, IT> su0, su1, sp0, sp1, sn0, sn1;
-            load_state_rows<V, G, IT>(m.user, ou, nch, gl, kind, fu, su0, su1);
-            load_state_rows<V, G, IT>(m.item, op, nch, gl, kind, fp, sp0, sp1);
-            load_state_rows<V, G, IT>(m.item, on, nch, gl, kind, fn, sn0, sn1);
+            // Optimizer state of the rows updated here is NOT held in registers across the scorer math: rows
+            // fetched early already sit in shared memory; the others are copied there asynchronously now
+            // (samples with a slot) or hinted into L2, and read right before their update.
+            const bool slot = PFETCH && kk < PF;
+            if (kind != TRS_OPT_SGD) {
+                const bool need[3] = {fu && !hu, fp && !hp, fn && !hn};
+                const size_t offs[3] = {ou, op, on};
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    if (!need[t]) continue;
+                    const trs_table& tb = t ? m.item : m.user;
+                    if (slot) {
+                        pf_issue(kk, 3 * t + 1, tb.emb_s0 + offs[t]);
+                        if (kind == TRS_OPT_SPARSE_ADAM) pf_issue(kk, 3 * t + 2, tb.emb_s1 + offs[t]);
+                    } else {
+                        prefetch_row<V, G, IT>(tb.emb_s0 + offs[t], nch, gl);
+                        if (kind == TRS_OPT_SPARSE_ADAM) prefetch_row<V, G, IT>(tb.emb_s1 + offs[t], nch, gl);
+                    }
+                }
+                if (slot) cp_async_commit();
+            }
+            // width-1 companions of the rows updated here: lane 0 takes the user's, lane 1 the positive
+            // item's, lane 2 the negative item's -- one code path, state fetched now, update at the end
+            const bool lf = gl == 0 ? (fu && NET == TRS_NET_FM) : (gl == 1 ? fp : (gl == 2 ? fn : false));
+            const trs_table& ltab = gl == 0 ? m.user : m.item;
+            const uint32_t lkey = gl == 0 ? id.u : (gl == 1 ? id.ip : id.in);
+            const bool ldo = lf && ltab.lin != nullptr && !(dbg & 256);
+            float lin_s0 = 0.f, lin_s1 = 0.f;
+            if (ldo && kind != TRS_OPT_SGD) lin_s0 = __ldcg(ltab.lin_s0 + lkey);
+            if (ldo && kind == TRS_OPT_SPARSE_ADAM) lin_s1 = __ldcg(ltab.lin_s1 + lkey);
             // optimizer state of the shared rows -> L2, for phase B's ring refills
             if (kind != TRS_OPT_SGD && valid && !(dbg & 16)) {
                 if (!fu) prefetch_row<V, G, IT>(m.user.emb_s0 + ou, nch, gl);
@@ -578,10 +641,20 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
                 }
             }
             if (valid) {
+                if (slot) cp_async_wait<0>();  // my state-row copies of this sample
+                auto fused = [&](const trs_table& tb, size_t off, int t, Row<V, IT>& p, const Row<V, IT>& g) {
+                    Row<V, IT> s0, s1;
+                    row_zero(s0);
+                    row_zero(s1);
+                    if (kind != TRS_OPT_SGD)
+                        s0 = slot ? pf_row(kk, 3 * t + 1) : load_row_cg<V, G, IT>(tb.emb_s0 + off, nch, gl);
+                    if (kind == TRS_OPT_SPARSE_ADAM)
+                        s1 = slot ? pf_row(kk, 3 * t + 2) : load_row_cg<V, G, IT>(tb.emb_s1 + off, nch, gl);
+                    update_store_row<V, G, IT>(tb, off, nch, gl, opt, scale, p, s0, s1, g);
+                };
                 // user row
                 if (fu) {
-                    update_store_row<V, G, IT>(m.user, ou, nch, gl, opt, scale, ru, su0, su1, gu);
-                    if (NET == TRS_NET_FM && m.user.lin && gl == 0) update_lin(m.user, id.u, opt, scale, gbu);
+                    fused(m.user, ou, 0, ru, gu);
                 } else {
                     store_row<V, G, IT>(st.gU + (size_t)b * dim, nch, gl, gu);
                     if (NET == TRS_NET_FM && gl == 0) st.gbU[b] = gbu;
@@ -591,28 +664,44 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
                 const bool stage_items = (NET == TRS_NET_LINEAR && F > 0);
                 // FM: d linear_metadata = delta, the same scalar as d linear_item -> always staged
                 const bool meta_lin = (NET == TRS_NET_FM && F > 0);
-                if (fp) {
-                    update_store_row<V, G, IT>(m.item, op, nch, gl, opt, scale, rp, sp0, sp1, gp);
-                    if (m.item.lin && gl == 1 % G) update_lin(m.item, id.ip, opt, scale, gbp);
-                }
+                if (fp) fused(m.item, op, 1, rp, gp);
                 if (!fp || stage_items) store_row<V, G, IT>(st.gI + (size_t)b * dim, nch, gl, gp);
                 if ((!fp || meta_lin) && gl == 0) st.gbI[b] = gbp;
-                if (fn) {
-                    update_store_row<V, G, IT>(m.item, on, nch, gl, opt, scale, rn, sn0, sn1, gn);
-                    if (m.item.lin && gl == 2 % G) update_lin(m.item, id.in, opt, scale, gbn);
-                }
+                if (fn) fused(m.item, on, 2, rn, gn);
                 if (!fn || stage_items) store_row<V, G, IT>(st.gI + (size_t)(Bs + b) * dim, nch, gl, gn);
                 if ((!fn || meta_lin) && gl == 0) st.gbI[Bs + b] = gbn;
+                if (ldo) {  // lanes 0..2: the width-1 companions, state already in registers
+                    float pl = gl == 0 ? bu : (gl == 1 ? bip : bin);
+                    const float gg = gl == 0 ? gbu : (gl == 1 ? gbp : gbn);
+                    opt_update(opt, scale, gg, pl, lin_s0, lin_s1);
+                    ltab.lin[lkey] = pl;
+                    if (kind != TRS_OPT_SGD) ltab.lin_s0[lkey] = lin_s0;
+                    if (kind == TRS_OPT_SPARSE_ADAM) ltab.lin_s1[lkey] = lin_s1;
+                }
             }
         }
         // the step's first ring items: their descriptors landed long ago; fetch param + state rows
         // now (nothing in phase A writes them: they are not single-lookup rows), so only the staged
         // gradients wait for the barrier
-        cp_async_wait<0>();
-        if (!(dbg & 4)) {
-            for (int n = 0; n < RING; ++n) issue_state(n_items, n, lo);
+        if (RINGED) {
+            cp_async_wait<0>();
+            if (!(dbg & 4)) {
+                for (int n = 0; n < RING; ++n) issue_state(n_items, n, lo);
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
+        // my CTA's first long segment: its descriptor and this group's first lookup ids are plan data --
+        // fetched before the barrier so that only the staged rows wait for it
+        constexpr int U = 4;  // staged rows in flight per group
+        uint4 seg_pre = make_uint4(0, 0, 0, 0);
+        uint32_t j_pre[U] = {0, 0, 0, 0};
+        if ((int)blockIdx.x < n_long && !(dbg & 2)) {
+            seg_pre = plan.long_segs[(size_t)s * plan.long_cap + blockIdx.x];
+            const SpaceRef sp = resolve_space<NET>((int)seg_pre.x, m, plan, st, lo);
+#pragma unroll
+            for (int z = 0; z < U; ++z)
+                if (g_in_cta + z * GPB < (int)seg_pre.z) j_pre[z] = sp.P[seg_pre.y + g_in_cta + z * GPB];
+        }
 
         if (NET != TRS_NET_MLP) {
             hsum = warp_sum(hsum);
@@ -630,15 +719,49 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
         if (tracing) tr[2] = global_ns();
 
         // ------------------------------ phase B ------------------------------------------
-        if (!(dbg & 4)) {
-            for (int n = 0; n < RING; ++n) issue_grad(n_items, n, lo);
+        if (RINGED) {
+            if (!(dbg & 4)) {
+                for (int n = 0; n < RING; ++n) issue_grad(n_items, n, lo);
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
-        // rows (parameters and optimizer state) of the next step's samples -> L2 (coherent: a row updated
-        // below is still read right after the next barrier)
+        // The next step's rows.  My first PF samples: parameter rows (+ optimizer state where the row will be
+        // updated in phase A) are copied into shared memory NOW, asynchronously, unless this step's phase B
+        // still updates the row (flag bit 1: read it after the barrier instead).  Every row this step's
+        // phase A updated is already visible (the copies are issued after the barrier).
         ids0 = nid0;
+        have = 0;
+        if (PFETCH && si + 1 < n_steps && !(dbg & 16)) {
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const int b = gid + k * ngroups;
+                if (b >= Bs2) continue;
+                uint32_t u = ids0.u, ip = ids0.ip, in = ids0.in;
+                if (k) {
+                    u = (uint32_t)ep.user[lo2 + b];
+                    ip = (uint32_t)ep.pos[lo2 + b];
+                    in = (uint32_t)ep.neg[lo2 + b];
+                }
+                const unsigned tu = plan.single_user[lo2 + b], tp = plan.single_item[2 * lo2 + b],
+                               tn = plan.single_item[2 * lo2 + Bs2 + b];
+                const uint32_t rows[3] = {u, ip, in};
+                const unsigned tf[3] = {tu, tp, tn};
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    if (tf[t] & 2u) continue;  // updated below by some CTA: not safe to copy yet
+                    const trs_table& tb = t ? m.item : m.user;
+                    const size_t ro = (size_t)rows[t] * dim;
+                    pf_issue(k, 3 * t, tb.emb + ro);
+                    if ((tf[t] & 1u) && kind != TRS_OPT_SGD) pf_issue(k, 3 * t + 1, tb.emb_s0 + ro);
+                    if ((tf[t] & 1u) && kind == TRS_OPT_SPARSE_ADAM) pf_issue(k, 3 * t + 2, tb.emb_s1 + ro);
+                    have |= 1u << (3 * k + t);
+                }
+            }
+            cp_async_commit();
+        }
+        // samples beyond the shared-memory budget (large batches): L2 prefetch hints
         if (si + 1 < n_steps && !(dbg & 16) && NET != TRS_NET_MLP) {
-            for (int b = gid; b < Bs2; b += ngroups) {
+            for (int b = gid + (PFETCH ? PF : 0) * ngroups; b < Bs2; b += ngroups) {
                 uint32_t u = ids0.u, ip = ids0.ip, in = ids0.in;
                 if (b != gid) {
                     u = (uint32_t)ep.user[lo2 + b];
@@ -681,7 +804,8 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
         // long segments: one CTA per segment, every row group sums a strided subset of its lookups
         if (!(dbg & 2)) {
             for (int sg = blockIdx.x; sg < n_long; sg += gridDim.x) {   // block-uniform trip count
-                const uint4 seg = plan.long_segs[(size_t)s * plan.long_cap + sg];  // space, start, length, row
+                const bool first = sg == (int)blockIdx.x;
+                const uint4 seg = first ? seg_pre : plan.long_segs[(size_t)s * plan.long_cap + sg];  // space, start, length, row
                 const SpaceRef sp = resolve_space<NET>((int)seg.x, m, plan, st, lo);
                 const uint32_t* P = sp.P + seg.y;
                 const int c = (int)seg.z;
@@ -698,11 +822,11 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
                 Row<V, IT> acc;
                 row_zero(acc);
                 float accl = 0.f;
-                constexpr int U = 4;  // staged rows in flight per group
                 for (int q0 = g_in_cta; q0 < c; q0 += U * GPB) {
                     uint32_t j[U];
 #pragma unroll
-                    for (int z = 0; z < U; ++z) j[z] = (q0 + z * GPB < c) ? P[q0 + z * GPB] : 0u;
+                    for (int z = 0; z < U; ++z)
+                        j[z] = (first && q0 == g_in_cta) ? j_pre[z] : ((q0 + z * GPB < c) ? P[q0 + z * GPB] : 0u);
                     Row<V, IT> r[U];
                     float l[U];
 #pragma unroll
@@ -770,25 +894,29 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
         if (tracing) tr[6] = global_ns();
         // short segments through the ring
         if (!(dbg & 4)) {
-            cp_async_wait<0>();
+            if (RINGED) cp_async_wait<0>();
             const int my_items = n_items > gid ? (n_items - gid + ngroups - 1) / ngroups : 0;
             for (int n = 0; n < my_items; ++n) {
-                if (n >= RING) cp_async_wait<RING - 1>();
+                if (RINGED && n >= RING) cp_async_wait<RING - 1>();
                 consume(items, n_items, n, lo, scale);
-                issue_state(n_items, n + RING, lo);
-                issue_grad(n_items, n + RING, lo);
-                issue_desc(items, n_items, n + 2 * RING);
-                cp_async_commit();
+                if (RINGED) {
+                    issue_state(n_items, n + RING, lo);
+                    issue_grad(n_items, n + RING, lo);
+                    issue_desc(items, n_items, n + 2 * RING);
+                    cp_async_commit();
+                }
             }
-            cp_async_wait<0>();
+            if (RINGED) cp_async_wait<0>();
         }
         if (tracing) tr[7] = global_ns();
         // descriptors of the next step's first work items
-        if (si + 1 < n_steps) {
-            const uint4* items2 = plan.items + (size_t)(s + 1) * plan.item_cap;
-            for (int n = 0; n < 2 * RING; ++n) issue_desc(items2, n_items_next, n);
+        if (RINGED) {
+            if (si + 1 < n_steps) {
+                const uint4* items2 = plan.items + (size_t)(s + 1) * plan.item_cap;
+                for (int n = 0; n < 2 * RING; ++n) issue_desc(items2, n_items_next, n);
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
         n_items_cur = n_items_next;
         n_long_cur = n_long_next;
         if (tracing) tr[3] = global_ns();
