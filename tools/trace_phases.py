@@ -44,16 +44,16 @@ sm, grid, _ = _lib.device_info()
 tr = ws[off:off + K * grid * 128].cpu().numpy().view(np.uint64).reshape(K, grid, 16).astype(np.int64)
 t0 = tr[:, :, 0].min(axis=1, keepdims=True)
 rel = (tr - t0[:, :, None]) / 1e3  # us
-names = ["step start", "arrive barrier1", "leave barrier1", "arrive barrier2", "B: ids+prefetch done",
-         "B: lin pass done", "B: chunks done", "B: ring done"]
-order = [0, 1, 2, 4, 5, 6, 7, 3]
-for base, who in ((0, "thread 0 (warp with chunk work)"), (8, "thread NT/2 (no chunks)")):
-    print(who)
-    prev = None
-    for k in order:
-        a = rel[5:, :, base + k]
-        d = "" if prev is None else "  delta p50 %6.2f max %6.2f" % (np.median(a - prev), (a - prev).max(axis=1).mean())
-        print(f"  {names[k]:24s} p50 {np.median(a):6.2f}  mean-of-max {a.max(axis=1).mean():6.2f}{d}")
-        prev = a
+names = {0: "step start", 8: "A: early fetch landed, meta issued", 9: "A: sample 0 loads done", 10: "A: sample 0 math done",
+         11: "A: sample 0 updates issued", 12: "A: both samples done", 13: "A: long-seg preload done", 1: "arrive barrier1",
+         2: "leave barrier1", 4: "B: next-step fetch issued", 5: "B: lin loads issued", 6: "B: long segs + lin done",
+         7: "B: short segs done", 3: "arrive barrier2"}
+order = [0, 8, 9, 10, 11, 12, 13, 1, 2, 4, 5, 6, 7, 3]
+prev = None
+for k in order:
+    a = rel[5:, :, k]
+    d = "" if prev is None else "  delta p50 %6.2f  mean-of-max-delta %6.2f" % (np.median(a - prev), (a - prev).max(axis=1).mean())
+    print(f"  {names[k]:36s} p50 {np.median(a):6.2f}  mean-of-max {a.max(axis=1).mean():6.2f}{d}")
+    prev = a
 step = np.diff(tr[:, :, 0].min(axis=1)) / 1e3
 print("step time us: p50 %.2f" % np.median(step[5:]))

@@ -216,16 +216,18 @@ constexpr size_t ring_smem_bytes() {
 // Linear / FM use the same region for the early fetch of the NEXT step's rows instead (the ring only serves
 // the MLP tower's staged mode there): PF samples per row group x 9 rows (param, s0, s1 of user / pos / neg),
 // thread-private 16-byte slots like the ring's.
+constexpr int MLIN_CAP = 2048;  // a metadata first-order table up to this many rows is cached in shared memory
 constexpr int PF = 2;
+constexpr int PF_ROWS = 11;  // 0-8: {param, s0, s1} x {user, positive item, negative item}; 9, 10: metadata rows
 template <int V, int IT>
 constexpr size_t front_smem_bytes() {
-    const size_t pf = V == 1 ? 0 : (size_t)train_threads<V, IT>() * PF * 9 * IT * 16;
+    const size_t pf = V == 1 ? 0 : (size_t)train_threads<V, IT>() * PF * PF_ROWS * IT * 16;
     return pf > ring_smem_bytes<V, IT>() ? pf : ring_smem_bytes<V, IT>();
 }
 // + the partial sums of a CTA-cooperative long-segment reduce: one row slice per thread, one scalar per group
 template <int V, int IT>
 constexpr size_t train_smem_bytes() {
-    return front_smem_bytes<V, IT>() + (size_t)train_threads<V, IT>() * (IT * V * 4 + 4);
+    return front_smem_bytes<V, IT>() + (size_t)train_threads<V, IT>() * (IT * V * 4 + 4) + MLIN_CAP * 4;
 }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -263,6 +265,27 @@ __device__ __forceinline__ SampleIds load_ids(const trs_epoch& ep, int64_t smp, 
     return r;
 }
 
+// ids and plan flags of one sample.  fl: byte 0 user flags, byte 1 positive item, byte 2 negative item.
+struct SampleRec {
+    uint32_t u, ip, in, pm, nm, fl;
+};
+constexpr int REC_WORDS = 6;
+// word f of the record of sample b of the step starting at lo
+__device__ __forceinline__ uint32_t load_rec_word(const trs_epoch& ep, const uint8_t* single_user,
+                                                  const uint8_t* single_item, int64_t lo, int Bs, int b, int F, int f) {
+    const int64_t smp = lo + b;
+    switch (f) {
+        case 0: return (uint32_t)ep.user[smp];
+        case 1: return (uint32_t)ep.pos[smp];
+        case 2: return (uint32_t)ep.neg[smp];
+        case 3: return F ? (uint32_t)ep.pos_meta[smp * F] : 0u;
+        case 4: return F ? (uint32_t)ep.neg_meta[smp * F] : 0u;
+        default:
+            return (uint32_t)single_user[lo + b] | ((uint32_t)single_item[2 * lo + b] << 8) |
+                   ((uint32_t)single_item[2 * lo + Bs + b] << 16);
+    }
+}
+
 // optimizer state of a row that phase A updates itself (zeros where the optimizer has none / not fused)
 template <int V, int G, int IT>
 __device__ __forceinline__ void load_state_rows(const trs_table& t, size_t roff, int nch, int gl, int kind, bool fused,
@@ -290,6 +313,11 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
     ring.rows = reinterpret_cast<float4*>(smem_raw + (size_t)2 * RING * NT * sizeof(uint4));
     float* s_part = reinterpret_cast<float*>(smem_raw + front_smem_bytes<V, IT>());  // [GPB][IT][G][V]
     float* s_part_lin = s_part + (size_t)NT * IT * V;                                // [GPB]
+    // FM: every sample reads linear_metadata.0 -- a table of a few cache lines that the whole GPU would hammer
+    // at once; each CTA takes one coalesced copy per step instead
+    float* s_mlin = s_part_lin + NT;                                                 // [MLIN_CAP]
+    const bool mlin_cached = NET == TRS_NET_FM && m.n_meta > 0 && m.meta[0].lin != nullptr &&
+                             m.meta[0].n_rows <= MLIN_CAP && (m.meta[0].n_rows & 3) == 0;
 
     const int dim = m.dim, nch = dim / V, F = m.n_meta;
     const int gl = threadIdx.x % G;
@@ -303,7 +331,7 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
     unsigned bar_target = 0;
     float4* pf_base = reinterpret_cast<float4*>(smem_raw);
     // slot of (sample k of this group, row r: 3*table + {param, s0, s1}, chunk a) in the early-fetch region
-    auto pf_slot = [&](int k, int r, int a) { return pf_base + (((k * 9 + r) * IT + a) * NT + threadIdx.x); };
+    auto pf_slot = [&](int k, int r, int a) { return pf_base + (((k * PF_ROWS + r) * IT + a) * NT + threadIdx.x); };
     auto pf_issue = [&](int k, int r, const float* row) {
 #pragma unroll
         for (int a = 0; a < IT; ++a) {
@@ -321,6 +349,34 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
             x.c[a][0] = v.x; x.c[a][V > 1 ? 1 : 0] = v.y; x.c[a][V > 2 ? 2 : 0] = v.z; x.c[a][V > 3 ? 3 : 0] = v.w;
         }
         return x;
+    };
+    // The records (ids + flags) of my group's first PF samples are held one WORD PER LANE (lane w % G keeps word
+    // w of the PF * REC_WORDS words) and broadcast by shuffles: they cross the step barrier in a single register.
+    constexpr int WPL = (PF * REC_WORDS + G - 1) / G;
+    auto rec_load = [&](uint32_t (&w)[WPL], int64_t lo_, int Bs_) {
+#pragma unroll
+        for (int i = 0; i < WPL; ++i) {
+            const int idx = gl + i * G;
+            w[i] = 0u;
+            if (idx < PF * REC_WORDS && Bs_ > 0) {
+                const int k = idx / REC_WORDS;
+                w[i] = load_rec_word(ep, plan.single_user, plan.single_item, lo_, Bs_, min(gid + k * ngroups, Bs_ - 1), F,
+                                     idx % REC_WORDS);
+            }
+        }
+    };
+    auto rec_get = [&](const uint32_t (&w)[WPL], int k) {   // every lane of the warp must call this
+        uint32_t f[REC_WORDS];
+#pragma unroll
+        for (int q = 0; q < REC_WORDS; ++q) {
+            const int idx = k * REC_WORDS + q;
+            uint32_t v = w[0];
+#pragma unroll
+            for (int i = 1; i < WPL; ++i) v = (idx / G == i) ? w[i] : v;
+            f[q] = __shfl_sync(0xffffffffu, v, idx % G, G);
+        }
+        SampleRec r = {f[0], f[1], f[2], f[3], f[4], f[5]};
+        return r;
     };
     unsigned have = 0;  // bit 3k+t: the param (+ state, if fused) row of table t of my sample k sits in shared memory
 
@@ -406,14 +462,16 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
 
     // ---- prologue: what step `first_step` needs before its phase A ----
     int n_items_cur = 0, n_long_cur = 0;
-    SampleIds ids0;  // ids of this group's first sample of the current step
+    uint32_t curw[WPL], nxtw[WPL];  // record words of the current / next step (see rec_load)
+#pragma unroll
+    for (int i = 0; i < WPL; ++i) curw[i] = nxtw[i] = 0u;
     {
         const int64_t s0i = first_step;
         const int64_t lo0 = s0i * (int64_t)ep.batch;
         const int Bs0 = (int)min((int64_t)ep.batch, ep.n_samples - lo0);
         n_items_cur = min((int)plan.item_cnt[s0i], plan.item_cap);
         n_long_cur = min((int)plan.long_cnt[s0i], plan.long_cap);
-        ids0 = load_ids(ep, lo0 + min(gid, Bs0 - 1), F);
+        if (NET != TRS_NET_MLP) rec_load(curw, lo0, Bs0);
         const uint4* items0 = plan.items + (size_t)s0i * plan.item_cap;
         for (int n = 0; n < 2 * RING; ++n) issue_desc(items0, n_items_cur, n);
         cp_async_commit();
@@ -429,13 +487,12 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
         const float scale = opt.step_scale[s];
         // what the next step will need (loaded now, used after two barriers)
         int n_items_next = 0, n_long_next = 0;
-        SampleIds nid0 = ids0;  // ids of my first sample of the NEXT step
         const int64_t lo2 = lo + ep.batch;
         const int Bs2 = (si + 1 < n_steps) ? (int)min((int64_t)ep.batch, ep.n_samples - lo2) : 0;
         if (si + 1 < n_steps) {
             n_items_next = min((int)plan.item_cnt[s + 1], plan.item_cap);
             n_long_next = min((int)plan.long_cnt[s + 1], plan.long_cap);
-            nid0 = load_ids(ep, lo2 + min(gid, Bs2 - 1), F);
+            if (NET != TRS_NET_MLP) rec_load(nxtw, lo2, Bs2);
         }
         // width-1 companion work of this thread (phase B): descriptor fetched now
         const int lin_i = threadIdx.x * gridDim.x + blockIdx.x;  // every CTA gets every gridDim-th item
@@ -443,12 +500,33 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
         if (lin_i < n_items) lin_it = items[lin_i];
 
         // debug trace: slots 0-7 by thread 0, 8-15 by thread NT/2
-        const bool tracing = (dbg & 64) && (threadIdx.x == 0 || threadIdx.x == NT / 2);
-        unsigned long long* tr = st.trace + ((size_t)si * gridDim.x + blockIdx.x) * 16 + (threadIdx.x ? 8 : 0);
+        const bool tracing = (dbg & 64) && threadIdx.x == 0;
+        unsigned long long* tr = st.trace + ((size_t)si * gridDim.x + blockIdx.x) * 16;
         if (tracing) tr[0] = global_ns();
         // ------------------------------ phase A ------------------------------------------
         float hsum = 0.f;
-        if (PFETCH) cp_async_wait<0>();  // my own copies of this step's rows (issued during the last phase B)
+        if (mlin_cached) {
+            for (int i = threadIdx.x * 4; i < (int)m.meta[0].n_rows; i += NT * 4)
+                *reinterpret_cast<float4*>(s_mlin + i) = __ldcg(reinterpret_cast<const float4*>(m.meta[0].lin + i));
+        }
+        if (PFETCH) {
+            cp_async_wait<0>();  // my own copies of this step's rows (issued during the last phase B)
+            // the metadata rows of my first two samples (updated by every step: L2-hot) -> shared memory,
+            // issued together so that the second sample does not wait for them again
+            if (F > 0 && NET != TRS_NET_MLP) {
+#pragma unroll
+                for (int k = 0; k < PF; ++k) {
+                    const SampleRec r = rec_get(curw, k);
+                    if (gid + k * ngroups < Bs) {
+                        pf_issue(k, 9, m.meta[0].emb + (size_t)r.pm * dim);
+                        pf_issue(k, 10, m.meta[0].emb + (size_t)r.nm * dim);
+                    }
+                }
+                cp_async_commit();
+            }
+        }
+        if (mlin_cached) __syncthreads();
+        if (tracing) tr[8] = global_ns();
         if constexpr (NET != TRS_NET_MLP)
         if (!(dbg & 1))
         for (int b0 = gid_warp0, kk = 0; b0 < Bs; b0 += ngroups, ++kk) {   // warp-uniform trip count
@@ -456,13 +534,25 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
             const bool valid = b_raw < Bs;
             const int b = valid ? b_raw : Bs - 1;
             const int64_t smp = lo + b;
-            const SampleIds id = (b0 == gid_warp0) ? ids0 : load_ids(ep, smp, F);
+            SampleRec rec;
+            if (kk < PF) {
+                rec = rec_get(curw, kk);
+            } else {
+                rec.u = (uint32_t)ep.user[smp];
+                rec.ip = (uint32_t)ep.pos[smp];
+                rec.in = (uint32_t)ep.neg[smp];
+                rec.pm = F ? (uint32_t)ep.pos_meta[smp * F] : 0u;
+                rec.nm = F ? (uint32_t)ep.neg_meta[smp * F] : 0u;
+                rec.fl = load_rec_word(ep, plan.single_user, plan.single_item, lo, Bs, b, F, 5);
+            }
+            SampleIds id;
+            id.u = rec.u; id.ip = rec.ip; id.in = rec.in; id.pm[0] = rec.pm; id.nm[0] = rec.nm;
             const int64_t* pm = F ? ep.pos_meta + smp * F : nullptr;
             const int64_t* nm = F ? ep.neg_meta + smp * F : nullptr;
             // rows this sample alone touches in this step (flag bit 0): updated right here
-            const bool fu = valid && !(dbg & 128) && (plan.single_user[lo + b] & 1);
-            const bool fp = valid && !(dbg & 128) && (plan.single_item[2 * lo + b] & 1);
-            const bool fn = valid && !(dbg & 128) && (plan.single_item[2 * lo + Bs + b] & 1);
+            const bool fu = valid && !(dbg & 128) && (rec.fl & 1u);
+            const bool fp = valid && !(dbg & 128) && (rec.fl & 0x100u);
+            const bool fn = valid && !(dbg & 128) && (rec.fl & 0x10000u);
             const size_t ou = (size_t)id.u * dim, op = (size_t)id.ip * dim, on = (size_t)id.in * dim;
             // rows already sitting in shared memory (fetched during the previous step's phase B)
             const bool hu = PFETCH && kk < PF && valid && ((have >> (3 * kk + 0)) & 1u);
@@ -472,25 +562,37 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
             Row<V, IT> ru = hu ? pf_row(kk, 0) : load_row_cg<V, G, IT>(m.user.emb + ou, nch, gl);
             Row<V, IT> rp = hp ? pf_row(kk, 3) : load_row_cg<V, G, IT>(m.item.emb + op, nch, gl);
             Row<V, IT> rn = hn ? pf_row(kk, 6) : load_row_cg<V, G, IT>(m.item.emb + on, nch, gl);
-            Row<V, IT> mp[MF], mn[MF];
+            // scalar loads first (they are in flight while the shared-memory copies are awaited below)
             float wp = 0.f, wn = 0.f;  // FM: sum of the metadata first-order weights
+            if (NET == TRS_NET_FM) {
+#pragma unroll
+                for (int f = 0; f < MF; ++f) {
+                    if (f < F && m.meta[f].lin) {
+                        wp += (f == 0 && mlin_cached) ? s_mlin[id.pm[f]] : __ldcg(m.meta[f].lin + id.pm[f]);
+                        wn += (f == 0 && mlin_cached) ? s_mlin[id.nm[f]] : __ldcg(m.meta[f].lin + id.nm[f]);
+                    }
+                }
+            }
+            const float bu = m.user.lin ? __ldcg(m.user.lin + id.u) : 0.f;
+            const float bip = m.item.lin ? __ldcg(m.item.lin + id.ip) : 0.f;
+            const float bin = m.item.lin ? __ldcg(m.item.lin + id.in) : 0.f;
+            Row<V, IT> mp[MF], mn[MF];
 #pragma unroll
             for (int f = 0; f < MF; ++f) {
                 if (f < F) {
-                    mp[f] = load_row_cg<V, G, IT>(m.meta[f].emb + (size_t)id.pm[f] * dim, nch, gl);
-                    mn[f] = load_row_cg<V, G, IT>(m.meta[f].emb + (size_t)id.nm[f] * dim, nch, gl);
-                    if (NET == TRS_NET_FM && m.meta[f].lin) {
-                        wp += __ldcg(m.meta[f].lin + id.pm[f]);
-                        wn += __ldcg(m.meta[f].lin + id.nm[f]);
+                    if (PFETCH && kk < PF && valid) {
+                        cp_async_wait<0>();
+                        mp[f] = pf_row(kk, 9);
+                        mn[f] = pf_row(kk, 10);
+                    } else {
+                        mp[f] = load_row_cg<V, G, IT>(m.meta[f].emb + (size_t)id.pm[f] * dim, nch, gl);
+                        mn[f] = load_row_cg<V, G, IT>(m.meta[f].emb + (size_t)id.nm[f] * dim, nch, gl);
                     }
                 } else {
                     row_zero(mp[f]);
                     row_zero(mn[f]);
                 }
             }
-            const float bu = m.user.lin ? __ldcg(m.user.lin + id.u) : 0.f;
-            const float bip = m.item.lin ? __ldcg(m.item.lin + id.ip) : 0.f;
-            const float bin = m.item.lin ? __ldcg(m.item.lin + id.in) : 0.f;
             // Optimizer state of the rows updated here is NOT held in registers across the scorer math: rows
             // fetched early already sit in shared memory; the others are copied there asynchronously now
             // (samples with a slot) or hinted into L2, and read right before their update.
@@ -553,6 +655,7 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
                 }
             }
 
+            if (tracing && kk == 0) tr[9] = global_ns() + (unsigned long long)(__float_as_uint(ru.c[0][0] + mp[0].c[0][0] + bu + bip + bin) & 1u);
             Row<V, IT> gu, gp, gn;   // gradient rows of the user / positive / negative lookups
             float gbu = 0.f, gbp, gbn;  // and of their width-1 companions
             if (NET == TRS_NET_LINEAR) {
@@ -640,6 +743,7 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
                     }
                 }
             }
+            if (tracing && kk == 0) tr[10] = global_ns() + (unsigned long long)(__float_as_uint(gu.c[0][0] + gp.c[0][0]) & 1u);
             if (valid) {
                 if (slot) cp_async_wait<0>();  // my state-row copies of this sample
                 auto fused = [&](const trs_table& tb, size_t off, int t, Row<V, IT>& p, const Row<V, IT>& g) {
@@ -670,6 +774,7 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
                 if (fn) fused(m.item, on, 2, rn, gn);
                 if (!fn || stage_items) store_row<V, G, IT>(st.gI + (size_t)(Bs + b) * dim, nch, gl, gn);
                 if ((!fn || meta_lin) && gl == 0) st.gbI[Bs + b] = gbn;
+                if (tracing && kk == 0) tr[11] = global_ns();
                 if (ldo) {  // lanes 0..2: the width-1 companions, state already in registers
                     float pl = gl == 0 ? bu : (gl == 1 ? bip : bin);
                     const float gg = gl == 0 ? gbu : (gl == 1 ? gbp : gbn);
@@ -683,6 +788,7 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
         // the step's first ring items: their descriptors landed long ago; fetch param + state rows
         // now (nothing in phase A writes them: they are not single-lookup rows), so only the staged
         // gradients wait for the barrier
+        if (tracing) tr[12] = global_ns();
         if (RINGED) {
             cp_async_wait<0>();
             if (!(dbg & 4)) {
@@ -692,9 +798,9 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
         }
         // my CTA's first long segment: its descriptor and this group's first lookup ids are plan data --
         // fetched before the barrier so that only the staged rows wait for it
-        constexpr int U = 4;  // staged rows in flight per group
+        constexpr int U = 6;  // staged rows in flight per group (one batch covers 6 * groups-per-CTA lookups)
         uint4 seg_pre = make_uint4(0, 0, 0, 0);
-        uint32_t j_pre[U] = {0, 0, 0, 0};
+        uint32_t j_pre[U] = {0, 0, 0, 0, 0, 0};
         if ((int)blockIdx.x < n_long && !(dbg & 2)) {
             seg_pre = plan.long_segs[(size_t)s * plan.long_cap + blockIdx.x];
             const SpaceRef sp = resolve_space<NET>((int)seg_pre.x, m, plan, st, lo);
@@ -703,6 +809,7 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
                 if (g_in_cta + z * GPB < (int)seg_pre.z) j_pre[z] = sp.P[seg_pre.y + g_in_cta + z * GPB];
         }
 
+        if (tracing) tr[13] = global_ns() + (j_pre[0] & 1u);
         if (NET != TRS_NET_MLP) {
             hsum = warp_sum(hsum);
             if ((threadIdx.x & 31) == 0) s_loss[threadIdx.x >> 5] = hsum;
@@ -729,23 +836,16 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
         // updated in phase A) are copied into shared memory NOW, asynchronously, unless this step's phase B
         // still updates the row (flag bit 1: read it after the barrier instead).  Every row this step's
         // phase A updated is already visible (the copies are issued after the barrier).
-        ids0 = nid0;
         have = 0;
         if (PFETCH && si + 1 < n_steps && !(dbg & 16)) {
 #pragma unroll
             for (int k = 0; k < PF; ++k) {
+                const SampleRec nr = rec_get(nxtw, k);   // warp-wide shuffles: before any divergence
                 const int b = gid + k * ngroups;
                 if (b >= Bs2) continue;
-                uint32_t u = ids0.u, ip = ids0.ip, in = ids0.in;
-                if (k) {
-                    u = (uint32_t)ep.user[lo2 + b];
-                    ip = (uint32_t)ep.pos[lo2 + b];
-                    in = (uint32_t)ep.neg[lo2 + b];
-                }
-                const unsigned tu = plan.single_user[lo2 + b], tp = plan.single_item[2 * lo2 + b],
-                               tn = plan.single_item[2 * lo2 + Bs2 + b];
-                const uint32_t rows[3] = {u, ip, in};
-                const unsigned tf[3] = {tu, tp, tn};
+                const uint32_t rows[3] = {nr.u, nr.ip, nr.in};
+                const unsigned tf[3] = {nr.fl & 0xffu, (nr.fl >> 8) & 0xffu, (nr.fl >> 16) & 0xffu};
+
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
                     if (tf[t] & 2u) continue;  // updated below by some CTA: not safe to copy yet
@@ -762,12 +862,8 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
         // samples beyond the shared-memory budget (large batches): L2 prefetch hints
         if (si + 1 < n_steps && !(dbg & 16) && NET != TRS_NET_MLP) {
             for (int b = gid + (PFETCH ? PF : 0) * ngroups; b < Bs2; b += ngroups) {
-                uint32_t u = ids0.u, ip = ids0.ip, in = ids0.in;
-                if (b != gid) {
-                    u = (uint32_t)ep.user[lo2 + b];
-                    ip = (uint32_t)ep.pos[lo2 + b];
-                    in = (uint32_t)ep.neg[lo2 + b];
-                }
+                const uint32_t u = (uint32_t)ep.user[lo2 + b], ip = (uint32_t)ep.pos[lo2 + b],
+                               in = (uint32_t)ep.neg[lo2 + b];
                 prefetch_row<V, G, IT>(m.user.emb + (size_t)u * dim, nch, gl);
                 prefetch_row<V, G, IT>(m.item.emb + (size_t)ip * dim, nch, gl);
                 prefetch_row<V, G, IT>(m.item.emb + (size_t)in * dim, nch, gl);
@@ -919,6 +1015,8 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
         }
         n_items_cur = n_items_next;
         n_long_cur = n_long_next;
+#pragma unroll
+        for (int i = 0; i < WPL; ++i) curw[i] = nxtw[i];
         if (tracing) tr[3] = global_ns();
         if (!(dbg & 8)) grid_barrier(st.barrier, bar_target);
     }
