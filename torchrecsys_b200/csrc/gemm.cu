@@ -76,6 +76,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t* acc_full = empty + STAGES;
     uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
 
+    constexpr int ST_ELEM = OUT_BF16 ? 2 : 4;          // output element size
+    constexpr int ST_PITCH = BN * ST_ELEM + 16;         // staged row pitch in bytes
+    static_assert(GEMM_BM * ST_PITCH <= S::RING, "the output tile is staged in the operand ring");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * BN;
     const int nkb_total = (g.K + GEMM_BK - 1) / GEMM_BK;
@@ -175,29 +178,28 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 v[j + 2] = __uint_as_float(r[j + 2]) + b.z;
                 v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
             }
-            if (row_in) {
+            // The tile goes through shared memory so that global stores are whole rows (one 16-byte piece per
+            // lane, 256-512 contiguous bytes per row) instead of 32 scattered 16-byte pieces per instruction.
+            // The staging area is the operand ring: every MMA has read it by the time acc_full fired.  Each
+            // warp stages and later writes only its own 32 rows; pitch = row bytes + 16 keeps the per-row
+            // 16-byte shared-memory stores of a quarter-warp on distinct banks.
+            {
+                unsigned char* srow = base + (size_t)(q * 32 + lane) * ST_PITCH + (size_t)c * 32 * ST_ELEM;
                 if (OUT_BF16) {
-                    __nv_bfloat16* o = (__nv_bfloat16*)g.out + (size_t)blockIdx.z * g.split_stride +
-                                       (size_t)row * g.ldc + col0;
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
-                        if (col0 + j < g.N) {  // N % 8 == 0 (checked by the host)
-                            uint4 pk;
-                            __nv_bfloat162 t;
-                            t = __floats2bfloat162_rn(v[j + 0], v[j + 1]); pk.x = *reinterpret_cast<uint32_t*>(&t);
-                            t = __floats2bfloat162_rn(v[j + 2], v[j + 3]); pk.y = *reinterpret_cast<uint32_t*>(&t);
-                            t = __floats2bfloat162_rn(v[j + 4], v[j + 5]); pk.z = *reinterpret_cast<uint32_t*>(&t);
-                            t = __floats2bfloat162_rn(v[j + 6], v[j + 7]); pk.w = *reinterpret_cast<uint32_t*>(&t);
-                            *reinterpret_cast<uint4*>(o + j) = pk;
-                        }
+                        uint4 pk;
+                        __nv_bfloat162 t;
+                        t = __floats2bfloat162_rn(v[j + 0], v[j + 1]); pk.x = *reinterpret_cast<uint32_t*>(&t);
+                        t = __floats2bfloat162_rn(v[j + 2], v[j + 3]); pk.y = *reinterpret_cast<uint32_t*>(&t);
+                        t = __floats2bfloat162_rn(v[j + 4], v[j + 5]); pk.z = *reinterpret_cast<uint32_t*>(&t);
+                        t = __floats2bfloat162_rn(v[j + 6], v[j + 7]); pk.w = *reinterpret_cast<uint32_t*>(&t);
+                        *reinterpret_cast<uint4*>(srow + j * 2) = pk;
                     }
                 } else {
-                    float* o = (float*)g.out + (size_t)blockIdx.z * g.split_stride + (size_t)row * g.ldc + col0;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (col0 + j < g.N)  // N % 4 == 0
-                            *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    }
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(srow + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
             }
             if (stats) {
@@ -213,6 +215,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 column_sums_32(b, lane);
                 s_stat[(0 * 4 + q) * BN + c * 32 + lane] = a[0];
                 s_stat[(1 * 4 + q) * BN + c * 32 + lane] = b[0];
+            }
+        }
+        {   // this warp's 32 staged rows -> global memory, whole rows at a time
+            __syncwarp();
+            constexpr int LANES_PER_ROW = (BN * ST_ELEM) / 16;      // 16-byte pieces per tile row (8 .. 32)
+            constexpr int ROWS_PER_IT = 32 / LANES_PER_ROW;
+            const int piece = lane % LANES_PER_ROW;
+            const int col = n0 + piece * (16 / ST_ELEM);             // first output column of my piece
+            unsigned char* gout = (unsigned char*)g.out + (size_t)blockIdx.z * g.split_stride * ST_ELEM;
+#pragma unroll 4
+            for (int r0 = 0; r0 < 32; r0 += ROWS_PER_IT) {
+                const int rl = q * 32 + r0 + lane / LANES_PER_ROW;
+                const int grow = m0 + rl;
+                if (grow < g.M && col < g.N) {
+                    const uint4 pk = *reinterpret_cast<const uint4*>(base + (size_t)rl * ST_PITCH + (size_t)piece * 16);
+                    *reinterpret_cast<uint4*>(gout + ((size_t)grow * g.ldc + col) * ST_ELEM) = pk;
+                }
             }
         }
         if (stats) {
