@@ -48,6 +48,9 @@ WORKLOADS = {
     "c5_predict": dict(net="linear", n_users=1_000_000, n_items=5_000_000, dim=128, n_cat=0, batch=148 * 128, k=100,
                        opt=None, lr=0.0, predict=True, desc="BASELINE configs[4]: batched predict top-100 against a "
                        "5M-item table (linear scorer, dim 128); a step = 18944 users (148 user tiles)"),
+    "c4_fused": dict(net="linear", n_users=50_000_000, n_items=5_000_000, dim=128, n_cat=0, batch=16384,
+                     opt="sparse_adam", lr=1e-3, desc="BASELINE configs[3] tables (linear 50M x 5M, dim 128, batch 16384, "
+                     "SparseAdam) on ONE GPU through the fused persistent kernel (84.5 GB of tables + state)"),
     "c4_linear": dict(net="linear", n_users=50_000_000, n_items=5_000_000, dim=128, n_cat=0, batch=16384,
                       opt="sparse_adam", lr=1e-3, sharded=True,
                       desc="BASELINE configs[3]: linear 50M x 5M, dim 128, batch 16384/GPU, tables row-sharded"),
