@@ -128,21 +128,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = tc::idesc_bf16_f32(GEMM_BM, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
-            // one thread issues every MMA: descriptors are built once per operand and advanced by constants
-            const uint64_t dA0 = A_MN ? tc::smem_desc_sw128_mn(sA, GEMM_BK * 128) : tc::smem_desc_sw128(sA, 0);
-            const uint64_t dB0 = B_MN ? tc::smem_desc_sw128_mn(sB, GEMM_BK * 128) : tc::smem_desc_sw128(sB, 0);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
                 tc::mbar_wait(&full[s], ph);
                 tc::tc_fence_after();
-                const uint64_t da_s = dA0 + (uint64_t)((uint32_t)(s * S::A_BYTES) >> 4);
-                const uint64_t db_s = dB0 + (uint64_t)((uint32_t)(s * S::B_BYTES) >> 4);
 #pragma unroll
                 for (int k = 0; k < GEMM_BK / 16; ++k) {
-                    // a 16-wide K slice: +32 bytes inside the swizzle atom (K-major), +16 rows = 2048 bytes (MN-major)
-                    const uint64_t da = da_s + (uint64_t)((A_MN ? k * 2048 : k * 32) >> 4);
-                    const uint64_t db = db_s + (uint64_t)((B_MN ? k * 2048 : k * 32) >> 4);
+                    const uint64_t da = A_MN ? tc::smem_desc_sw128_mn(sA + s * S::A_BYTES + k * 2048, GEMM_BK * 128)
+                                             : tc::smem_desc_sw128(sA + s * S::A_BYTES, k * 16);
+                    const uint64_t db = B_MN ? tc::smem_desc_sw128_mn(sB + s * S::B_BYTES + k * 2048, GEMM_BK * 128)
+                                             : tc::smem_desc_sw128(sB + s * S::B_BYTES, k * 16);
                     tc::umma_bf16(tmem_acc, da, db, idesc, (kb | k) ? 1u : 0u);
                 }
                 tc::umma_commit(&empty[s]);  // frees the ring slot once these MMAs have read it

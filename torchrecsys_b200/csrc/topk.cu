@@ -168,13 +168,6 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_const
         if (lane == 0) {
             constexpr uint32_t idesc = tc::idesc_bf16_f32(TK_BM, TK_BN);
             tc::mbar_wait(a_full, 0);
-            // ONE thread issues every MMA, so its instruction stream is the critical path: the descriptors are
-            // built once and advanced by compile-time constants (address field in 16-byte units), about three
-            // instructions per tcgen05.mma instead of rebuilding both descriptors each time.
-            const uint64_t dA0 = tc::smem_desc_sw128(sA, 0);
-            const uint64_t dB0 = tc::smem_desc_sw128(sB, 0);
-            const uint32_t stage_units = (uint32_t)(g.nbox * TK_BOX_BYTES) >> 4;
-            const int kslices = g.kslices;
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % g.stages;
                 const uint32_t ph = (uint32_t)(t / g.stages) & 1u;
@@ -183,14 +176,11 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_const
                 tc::mbar_wait(&acc_empty[buf], bph ^ 1u);
                 tc::mbar_wait(&full[s], ph);
                 tc::tc_fence_after();
-                const uint64_t dBs = dB0 + (uint64_t)((uint32_t)s * stage_units);
-                const uint32_t acc = tmem + (uint32_t)(buf * TK_BN);
-#pragma unroll
-                for (int ks = 0; ks < 16; ++ks) {   // kslices <= 15 (n_factors <= 239)
-                    if (ks < kslices) {
-                        const uint32_t off = (uint32_t)(((ks >> 2) * TK_BOX_BYTES + (ks & 3) * 32) >> 4);
-                        tc::umma_bf16(acc, dA0 + off, dBs + off, idesc, ks ? 1u : 0u);
-                    }
+                for (int ks = 0; ks < g.kslices; ++ks) {
+                    const int box = ks >> 2, kin = (ks & 3) * 16;
+                    const uint64_t da = tc::smem_desc_sw128(sA + box * TK_BOX_BYTES, kin);
+                    const uint64_t db = tc::smem_desc_sw128(sB + (s * g.nbox + box) * TK_BOX_BYTES, kin);
+                    tc::umma_bf16(tmem + (uint32_t)(buf * TK_BN), da, db, idesc, ks ? 1u : 0u);
                 }
                 tc::umma_commit(&empty[s]);
                 tc::umma_commit(&acc_full[buf]);
