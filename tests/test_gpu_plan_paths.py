@@ -1,0 +1,103 @@
+"""The two plan builders -- one CTA per (step, id space) in shared memory (batches up to 8192) and the tiled
+multi-launch radix sort (any batch) -- must agree: identical sorted (row, lookup) pairs, identical singleton
+flags and work-item sets, and bit-identical parameters after training on either plan (``-m gpu``)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _plan_arrays(_lib, model, epoch, dev, tiled):
+    os.environ["TRS_PLAN_TILED"] = "1" if tiled else "0"
+    try:
+        plan = _lib.plan_build(model, epoch, dev)
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("TRS_PLAN_TILED", None)
+    return plan.cpu().numpy().copy()
+
+
+@pytest.mark.parametrize("B,n,F,U,I", [(1024, 3000, 1, 5000, 300), (8192, 20000, 2, 1 << 20, 70000), (100, 250, 0, 40, 7)])
+def test_fused_plan_equals_tiled_plan(B, n, F, U, I):
+    from torchrecsys_b200 import _lib
+    from torchrecsys_b200.collaborative.fm import FM
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(B + F)
+    C = 11
+    net = FM(U, I, {f"m{f}": C for f in range(F)}, 8, use_metadata=F > 0, use_cuda=True).to(dev)
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    ids = {"user": rng.integers(0, U, n), "pos": rng.zipf(1.3, n) % I, "neg": rng.integers(0, I, n)}
+    if F:
+        meta = rng.integers(0, C, (I, F))
+        ids["pos_meta"], ids["neg_meta"] = meta[ids["pos"]], meta[ids["neg"]]
+    t = {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.int64)).to(dev) for k, v in ids.items()}
+    model = net.abi_model(opt.state, (None, None))
+    epoch = _lib.make_epoch(t["user"], t["pos"], t["neg"], t.get("pos_meta"), t.get("neg_meta"), B)
+    a = _plan_arrays(_lib, model, epoch, dev, tiled=False)
+    b = _plan_arrays(_lib, model, epoch, dev, tiled=True)
+    steps = -(-n // B)
+    lookups = B * (3 + 2 * F)
+    # layout of the plan buffer (plan.cuh): 256-byte aligned arrays in this order
+    off = 0
+
+    def take(nbytes):
+        nonlocal off
+        o = off
+        off += (nbytes + 255) // 256 * 256
+        return o
+
+    spans = {"user_key": take(4 * n), "user_perm": take(4 * n), "item_key": take(8 * n), "item_perm": take(8 * n)}
+    for f in range(F):
+        spans[f"meta_key{f}"], spans[f"meta_perm{f}"] = take(8 * n), take(8 * n)
+    item_cnt, long_cnt = take(4 * steps), take(4 * steps)
+    single_user, single_item = take((n + 3) // 4 * 4), take((2 * n + 3) // 4 * 4)
+    item_cap, long_cap = lookups, lookups // 9 + 1
+    items, long_segs = take(16 * steps * item_cap), take(16 * steps * long_cap)
+    assert off == a.size == b.size
+    for name, o in spans.items():
+        nb = 4 * n * (1 if name.startswith("user") else 2)
+        assert np.array_equal(a[o:o + nb], b[o:o + nb]), name
+    assert np.array_equal(a[item_cnt:single_user], b[item_cnt:single_user]), "segment counts"
+    assert np.array_equal(a[single_user:single_user + n], b[single_user:single_user + n])
+    assert np.array_equal(a[single_item:single_item + 2 * n], b[single_item:single_item + 2 * n])
+    ca, la = a[item_cnt:item_cnt + 4 * steps].view(np.uint32), a[long_cnt:long_cnt + 4 * steps].view(np.uint32)
+    assert la.max() > 0 or F == 0
+    for s in range(steps):  # the lists are sets: slots are handed out by atomics
+        for o, cap, cnt in ((items, item_cap, ca[s]), (long_segs, long_cap, la[s])):
+            xa = a[o + 16 * s * cap:o + 16 * (s * cap + cnt)].view(np.uint32).reshape(-1, 4)
+            xb = b[o + 16 * s * cap:o + 16 * (s * cap + cnt)].view(np.uint32).reshape(-1, 4)
+            ka = np.lexsort(xa.T[::-1])
+            kb = np.lexsort(xb.T[::-1])
+            assert np.array_equal(xa[ka], xb[kb]), f"step {s}"
+
+
+@pytest.mark.parametrize("opt_name", ["adagrad", "sparse_adam"])
+def test_training_is_bit_identical_on_either_plan(opt_name):
+    from torchrecsys_b200.collaborative.fm import FM
+    from torchrecsys_b200.engine import EpochRunner
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(5)
+    U, I, C, B, n, D = 4000, 900, 13, 2048, 2048 * 4 - 100, 32
+    meta = rng.integers(0, C, (I, 1))
+    ids = {"user": rng.integers(0, U, n), "pos": rng.zipf(1.2, n) % I, "neg": rng.integers(0, I, n)}
+    ids["pos_meta"], ids["neg_meta"] = meta[ids["pos"]], meta[ids["neg"]]
+    t = {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.int64)).to(dev) for k, v in ids.items()}
+    out = []
+    for tiled in ("0", "1"):
+        torch.manual_seed(3)
+        net = FM(U, I, {"m0": C}, D, use_metadata=True, use_cuda=True).to(dev)
+        opt = (torch.optim.Adagrad(net.parameters(), lr=0.05) if opt_name == "adagrad"
+               else torch.optim.SparseAdam(list(net.parameters()), lr=0.01))
+        os.environ["TRS_PLAN_TILED"] = tiled
+        try:
+            loss = EpochRunner(net, opt).run(t, B)
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("TRS_PLAN_TILED", None)
+        out.append((loss.cpu().numpy(), {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}))
+    assert np.array_equal(out[0][0], out[1][0])
+    for k in out[0][1]:
+        assert np.array_equal(out[0][1][k], out[1][1][k]), k

@@ -164,15 +164,30 @@ def count_bad_ids(ids, n_rows: int, counter: torch.Tensor) -> None:
                                   C.c_int64(n_rows), C.c_void_p(_ptr(counter, torch.int32)), _stream()))
 
 
-def plan_build(model: Model, epoch: Epoch, device) -> torch.Tensor:
+def _grown(buf, nbytes: int, device) -> torch.Tensor:
+    """A uint8 device buffer of at least nbytes: `buf` if it is big enough, else a new one."""
+    if buf is not None and buf.numel() >= nbytes and buf.device == torch.device(device):
+        return buf
+    return torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+
+
+def plan_build(model: Model, epoch: Epoch, device, plan=None, tmp=None) -> torch.Tensor:
+    """Builds the epoch's sort plan; `plan` / `tmp` are reused when they are large enough."""
     L = lib()
     nbytes = L.trs_plan_bytes(C.byref(model), C.byref(epoch))
     tbytes = L.trs_plan_tmp_bytes(C.byref(model), C.byref(epoch))
-    plan = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
-    tmp = torch.empty(max(tbytes, 1), dtype=torch.uint8, device=device)
+    plan = _grown(plan, nbytes, device)
+    tmp = _grown(tmp, tbytes, device)
     _check(L.trs_plan_build(C.byref(model), C.byref(epoch), C.c_void_p(plan.data_ptr()),
-                            C.c_size_t(nbytes), C.c_void_p(tmp.data_ptr()), C.c_size_t(tbytes), _stream()))
+                            C.c_size_t(plan.numel()), C.c_void_p(tmp.data_ptr()), C.c_size_t(tmp.numel()), _stream()))
     return plan
+
+
+def train_buffer_bytes(model: Model, epoch: Epoch):
+    """(plan, plan scratch, training workspace) sizes in bytes for an epoch of this shape."""
+    L = lib()
+    return (L.trs_plan_bytes(C.byref(model), C.byref(epoch)), L.trs_plan_tmp_bytes(C.byref(model), C.byref(epoch)),
+            L.trs_train_workspace_bytes(C.byref(model), C.byref(epoch)))
 
 
 def train_workspace(model: Model, epoch: Epoch, device) -> torch.Tensor:

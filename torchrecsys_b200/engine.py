@@ -116,6 +116,21 @@ def advance_steps(optimizer, params, b: OptBinding, n_steps: int) -> None:
     b.step0 += n_steps
 
 
+PLAN_FUSED_MAX = 16384  # plan.cu FS_MAX: lookups per (step, id space) the single-CTA plan kernel holds
+
+
+def plan_launches(model, batch_size: int, n_steps: int) -> int:
+    """CUDA kernels one trs_plan_build launches (bench.py's gpu_launches)."""
+    n_meta = model.n_meta
+    if 2 * batch_size <= PLAN_FUSED_MAX:
+        return 1  # one CTA per (step, id space): sort + work items + flags
+    dirty = 2 if (n_steps > 1 and model.net != _lib.NET_MLP) else 0
+    passes = lambda rows: max(1, -(-max(1, (rows - 1).bit_length()) // 8))
+    # (histogram, scatter) per radix pass and id space + one work-item scan per space
+    return 2 * (passes(model.user.n_rows) + passes(model.item.n_rows)
+                + sum(passes(model.meta[f].n_rows) for f in range(n_meta))) + 2 + n_meta + dirty
+
+
 class EpochRunner:
     """Runs the steps of one epoch's (already ordered) samples through the fused kernel."""
 
@@ -125,6 +140,17 @@ class EpochRunner:
         self.params = [p for p in net.parameters()]
         self.binding = bind_optimizer(optimizer, self.params)
         self.launches = 0  # CUDA kernels launched by this runner (bench.py reports it)
+
+    def reserve(self, n_samples: int, batch_size: int) -> None:
+        """Pre-sizes the device memory pool for epochs of n_samples: the plan, its scratch and the training
+        workspace are allocated once and returned to torch's caching allocator, so that no epoch -- not even the
+        first -- pays a cudaMalloc between its launches."""
+        dev = self.params[0].device
+        model = self.net.abi_model(self.optimizer.state, self.binding.keys)
+        shape = _lib.Epoch(None, None, None, None, None, n_samples, batch_size, 0)  # the size queries read no ids
+        held = [torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=dev)
+                for nbytes in _lib.train_buffer_bytes(model, shape)]  # all three alive at once, like in run()
+        del held  # back to torch's pool
 
     def run(self, samples: Dict[str, torch.Tensor], batch_size: int) -> torch.Tensor:
         """samples: device tensors user/pos/neg[/pos_meta/neg_meta] of one epoch.  Returns the
@@ -136,18 +162,17 @@ class EpochRunner:
                                 samples.get("pos_meta"), samples.get("neg_meta"), batch_size)
         n = samples["user"].shape[0]
         n_steps = -(-n // batch_size)
+        # plan and workspace are allocated once per epoch SHAPE: torch's caching allocator hands the same
+        # blocks back every epoch (reserve() takes the cudaMalloc out of the first one as well).  The plan is
+        # launched first: the device builds it while the host prepares the rest.
+        plan = _lib.plan_build(model, epoch, dev)
         scales = torch.tensor(step_scales(b, n_steps), dtype=torch.float64).to(torch.float32)
         scales = scales.to(dev, non_blocking=True)
         optim = _lib.Optim(b.kind, 0, b.beta1, b.beta2, b.eps, scales.data_ptr())
-        plan = _lib.plan_build(model, epoch, dev)
         ws = _lib.train_workspace(model, epoch, dev)
         loss = torch.empty(n_steps, dtype=torch.float32, device=dev)
         _lib.train_steps(model, epoch, optim, plan, ws, 0, n_steps, loss)
-        n_meta = model.n_meta
-        passes = lambda rows: max(1, -(-max(1, (rows - 1).bit_length()) // 8))
-        # train kernel + (histogram, scatter) per radix pass and id space + one long-segment scan per space
-        self.launches += 1 + 2 * (passes(model.user.n_rows) + passes(model.item.n_rows)
-                                  + sum(passes(model.meta[f].n_rows) for f in range(n_meta))) + 2 + n_meta
+        self.launches += 1 + plan_launches(model, batch_size, n_steps)
         advance_steps(self.optimizer, self.params, b, n_steps)
         return loss
 
