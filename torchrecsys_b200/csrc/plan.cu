@@ -244,9 +244,9 @@ build_items_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict
     }
 }
 
-// Bit 1 of a lookup's flag byte: its row is updated in phase B of the PREVIOUS step (it has >= 2 lookups
-// there), so a copy fetched during that phase may be stale -- the training kernel then reads the row after
-// the step barrier instead of taking it from its early shared-memory prefetch.
+// Bit 1 of a lookup's flag byte: its row is looked up -- hence updated -- in the PREVIOUS step, so a copy
+// fetched while that step runs may be stale: the training kernel then reads the row after the step barrier
+// instead of taking it from its early shared-memory prefetch.
 __global__ void __launch_bounds__(256)
 dirty_flags_kernel(const uint32_t* __restrict__ keys, const int64_t* __restrict__ a, const int64_t* __restrict__ b,
                    int mult, int64_t n_samples, int B, uint8_t* __restrict__ flags) {
@@ -264,7 +264,7 @@ dirty_flags_kernel(const uint32_t* __restrict__ keys, const int64_t* __restrict_
         const int mid = (lo + hi) >> 1;
         if (K[mid] < row) lo = mid + 1; else hi = mid;
     }
-    if (lo + 1 < plen && K[lo] == row && K[lo + 1] == row) flags[(int64_t)mult * step * B + j] |= 2;
+    if (lo < plen && K[lo] == row) flags[(int64_t)mult * step * B + j] |= 2;
 }
 
 // ---- single-CTA plan of one (step, id space) ---------------------------------------------------
@@ -428,8 +428,8 @@ plan_fused_kernel(const __grid_constant__ FusedArgs A, int64_t n_samples, int B,
         uint32_t* tk = ks; ks = kd; kd = tk;
         uint16_t* tv = vs; vs = vd; vd = tv;
     }
-    // the key buffer the last pass read from is free now: a FS_MAX * 32-bit hash bitmap of the rows with >= 2
-    // lookups in this step (for the next step's flag bit 1, below)
+    // the key buffer the last pass read from is free now: a FS_MAX * 32-bit hash bitmap of the rows looked up
+    // in this step (for the next step's flag bit 1, below)
     uint32_t* bitmap = kd;
     const bool want_dirty = S.single && (step + 1) * (int64_t)B < n_samples;
     if (want_dirty) {
@@ -461,7 +461,7 @@ plan_fused_kernel(const __grid_constant__ FusedArgs A, int64_t n_samples, int B,
                     if (c == 1 && S.single) flag_or(S.single, base + vs[k], 1u);
                     else a = SHORT | ((uint32_t)c << 16);
                 }
-                if (want_dirty && c > 1) {
+                if (want_dirty) {
                     const uint32_t h = row_hash(key);
                     atomicOr(&bitmap[h >> 5], 1u << (h & 31u));
                 }
@@ -491,8 +491,8 @@ plan_fused_kernel(const __grid_constant__ FusedArgs A, int64_t n_samples, int B,
         s_gbase[1] = s_cnt[1] ? atomicAdd(&long_cnt[step], s_cnt[1]) : 0u;
     }
     __syncthreads();
-    // flag bit 1 of the NEXT step's lookups (see dirty_flags_kernel): is the row updated in this step's
-    // phase B, i.e. does it have >= 2 lookups here?  One binary search in the sorted keys held in shared memory.
+    // flag bit 1 of the NEXT step's lookups (see dirty_flags_kernel): is the row looked up in this step?  A probe
+    // of the bitmap, confirmed by a binary search in the sorted keys held in shared memory.
     if (want_dirty) {
         const int64_t sample1 = sample0 + B;
         const int Bs1 = (int)min((int64_t)B, n_samples - sample1);
@@ -513,7 +513,7 @@ plan_fused_kernel(const __grid_constant__ FusedArgs A, int64_t n_samples, int B,
                     const int mid = (lo + hi) >> 1;
                     if (ks[mid] < row[it]) lo = mid + 1; else hi = mid;
                 }
-                if (lo + 1 < len && ks[lo] == row[it] && ks[lo + 1] == row[it]) flag_or(S.single, base + (int64_t)S.mult * B + j, 2u);
+                if (lo < len && ks[lo] == row[it]) flag_or(S.single, base + (int64_t)S.mult * B + j, 2u);
             }
         }
     }

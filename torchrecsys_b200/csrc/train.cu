@@ -14,8 +14,9 @@
 //            added in group order through shared memory, one group updates the row; short segments (2..T
 //            lookups, and every metadata row) stream through a per-thread cp.async ring: param + state rows
 //            fetched before the barrier, staged gradient rows after it, duplicates summed in lookup order.
-//            First thing in phase B the rows (parameters AND optimizer state) of the NEXT step's samples are
-//            prefetched into L2.
+//            Right after its phase A every row group starts copying the rows (parameters AND optimizer state)
+//            of its NEXT step's samples into shared memory -- all but the rows this step itself looks up
+//            (plan flag bit 1), which are read after the step's last barrier.
 //   grid barrier
 // HBM traffic per step is ids + (param+state read, param+state write) per unique touched row; staging and plan
 // are served from L2.  Nothing depends on the order in which CTAs or row groups run: every floating-point sum
@@ -785,6 +786,65 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
                 }
             }
         }
+        // The next step's rows.  My first PF samples: parameter rows (+ optimizer state where the row will be
+        // updated in phase A) are copied into shared memory NOW, asynchronously -- before the step's first
+        // barrier, so the copies fly during both barriers and phase B -- unless this step looks the row up
+        // itself (flag bit 1: some CTA updates it in this step; it is read after the step's last barrier
+        // instead).  My own phase A is over: its shared-memory slots are free.
+        have = 0;
+        if (PFETCH && si + 1 < n_steps && !(dbg & 16)) {
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const SampleRec nr = rec_get(nxtw, k);   // warp-wide shuffles: before any divergence
+                const int b = gid + k * ngroups;
+                if (b >= Bs2) continue;
+                const uint32_t rows[3] = {nr.u, nr.ip, nr.in};
+                const unsigned tf[3] = {nr.fl & 0xffu, (nr.fl >> 8) & 0xffu, (nr.fl >> 16) & 0xffu};
+
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    if (tf[t] & 2u) continue;  // updated below by some CTA: not safe to copy yet
+                    const trs_table& tb = t ? m.item : m.user;
+                    const size_t ro = (size_t)rows[t] * dim;
+                    pf_issue(k, 3 * t, tb.emb + ro);
+                    if ((tf[t] & 1u) && kind != TRS_OPT_SGD) pf_issue(k, 3 * t + 1, tb.emb_s0 + ro);
+                    if ((tf[t] & 1u) && kind == TRS_OPT_SPARSE_ADAM) pf_issue(k, 3 * t + 2, tb.emb_s1 + ro);
+                    have |= 1u << (3 * k + t);
+                }
+                // width-1 companions (+ their optimizer state where updated in phase A) -> L2: lane t takes table t
+                const unsigned tfl = gl == 0 ? tf[0] : (gl == 1 ? tf[1] : tf[2]);
+                if (gl < 3 && !(tfl & 2u)) {
+                    const trs_table& tb = gl ? m.item : m.user;
+                    const uint32_t row = gl == 0 ? nr.u : (gl == 1 ? nr.ip : nr.in);
+                    if (tb.lin) {
+                        prefetch_l2(tb.lin + row);
+                        if ((tfl & 1u) && kind != TRS_OPT_SGD && tb.lin_s0) prefetch_l2(tb.lin_s0 + row);
+                        if ((tfl & 1u) && kind == TRS_OPT_SPARSE_ADAM && tb.lin_s1) prefetch_l2(tb.lin_s1 + row);
+                    }
+                }
+            }
+            cp_async_commit();
+        }
+        // samples beyond the shared-memory budget (large batches): L2 prefetch hints
+        if (si + 1 < n_steps && !(dbg & 16) && NET != TRS_NET_MLP) {
+            for (int b = gid + (PFETCH ? PF : 0) * ngroups; b < Bs2; b += ngroups) {
+                const uint32_t u = (uint32_t)ep.user[lo2 + b], ip = (uint32_t)ep.pos[lo2 + b],
+                               in = (uint32_t)ep.neg[lo2 + b];
+                prefetch_row<V, G, IT>(m.user.emb + (size_t)u * dim, nch, gl);
+                prefetch_row<V, G, IT>(m.item.emb + (size_t)ip * dim, nch, gl);
+                prefetch_row<V, G, IT>(m.item.emb + (size_t)in * dim, nch, gl);
+                if (kind != TRS_OPT_SGD) {
+                    prefetch_row<V, G, IT>(m.user.emb_s0 + (size_t)u * dim, nch, gl);
+                    prefetch_row<V, G, IT>(m.item.emb_s0 + (size_t)ip * dim, nch, gl);
+                    prefetch_row<V, G, IT>(m.item.emb_s0 + (size_t)in * dim, nch, gl);
+                }
+                if (kind == TRS_OPT_SPARSE_ADAM) {
+                    prefetch_row<V, G, IT>(m.user.emb_s1 + (size_t)u * dim, nch, gl);
+                    prefetch_row<V, G, IT>(m.item.emb_s1 + (size_t)ip * dim, nch, gl);
+                    prefetch_row<V, G, IT>(m.item.emb_s1 + (size_t)in * dim, nch, gl);
+                }
+            }
+        }
         // the step's first ring items: their descriptors landed long ago; fetch param + state rows
         // now (nothing in phase A writes them: they are not single-lookup rows), so only the staged
         // gradients wait for the barrier
@@ -831,53 +891,6 @@ train_kernel(const __grid_constant__ trs_model m, const __grid_constant__ trs_ep
                 for (int n = 0; n < RING; ++n) issue_grad(n_items, n, lo);
             }
             cp_async_commit();
-        }
-        // The next step's rows.  My first PF samples: parameter rows (+ optimizer state where the row will be
-        // updated in phase A) are copied into shared memory NOW, asynchronously, unless this step's phase B
-        // still updates the row (flag bit 1: read it after the barrier instead).  Every row this step's
-        // phase A updated is already visible (the copies are issued after the barrier).
-        have = 0;
-        if (PFETCH && si + 1 < n_steps && !(dbg & 16)) {
-#pragma unroll
-            for (int k = 0; k < PF; ++k) {
-                const SampleRec nr = rec_get(nxtw, k);   // warp-wide shuffles: before any divergence
-                const int b = gid + k * ngroups;
-                if (b >= Bs2) continue;
-                const uint32_t rows[3] = {nr.u, nr.ip, nr.in};
-                const unsigned tf[3] = {nr.fl & 0xffu, (nr.fl >> 8) & 0xffu, (nr.fl >> 16) & 0xffu};
-
-#pragma unroll
-                for (int t = 0; t < 3; ++t) {
-                    if (tf[t] & 2u) continue;  // updated below by some CTA: not safe to copy yet
-                    const trs_table& tb = t ? m.item : m.user;
-                    const size_t ro = (size_t)rows[t] * dim;
-                    pf_issue(k, 3 * t, tb.emb + ro);
-                    if ((tf[t] & 1u) && kind != TRS_OPT_SGD) pf_issue(k, 3 * t + 1, tb.emb_s0 + ro);
-                    if ((tf[t] & 1u) && kind == TRS_OPT_SPARSE_ADAM) pf_issue(k, 3 * t + 2, tb.emb_s1 + ro);
-                    have |= 1u << (3 * k + t);
-                }
-            }
-            cp_async_commit();
-        }
-        // samples beyond the shared-memory budget (large batches): L2 prefetch hints
-        if (si + 1 < n_steps && !(dbg & 16) && NET != TRS_NET_MLP) {
-            for (int b = gid + (PFETCH ? PF : 0) * ngroups; b < Bs2; b += ngroups) {
-                const uint32_t u = (uint32_t)ep.user[lo2 + b], ip = (uint32_t)ep.pos[lo2 + b],
-                               in = (uint32_t)ep.neg[lo2 + b];
-                prefetch_row<V, G, IT>(m.user.emb + (size_t)u * dim, nch, gl);
-                prefetch_row<V, G, IT>(m.item.emb + (size_t)ip * dim, nch, gl);
-                prefetch_row<V, G, IT>(m.item.emb + (size_t)in * dim, nch, gl);
-                if (kind != TRS_OPT_SGD) {
-                    prefetch_row<V, G, IT>(m.user.emb_s0 + (size_t)u * dim, nch, gl);
-                    prefetch_row<V, G, IT>(m.item.emb_s0 + (size_t)ip * dim, nch, gl);
-                    prefetch_row<V, G, IT>(m.item.emb_s0 + (size_t)in * dim, nch, gl);
-                }
-                if (kind == TRS_OPT_SPARSE_ADAM) {
-                    prefetch_row<V, G, IT>(m.user.emb_s1 + (size_t)u * dim, nch, gl);
-                    prefetch_row<V, G, IT>(m.item.emb_s1 + (size_t)ip * dim, nch, gl);
-                    prefetch_row<V, G, IT>(m.item.emb_s1 + (size_t)in * dim, nch, gl);
-                }
-            }
         }
         if (tracing) tr[4] = global_ns();
         // width-1 companions (biases / first-order weights) of the short segments: one THREAD per segment;
