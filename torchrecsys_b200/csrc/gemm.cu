@@ -126,13 +126,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc::idesc_bf16_f32(GEMM_BM, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                tc::mbar_wait(&full[s], ph);
-                tc::tc_fence_after();
+        // the whole warp walks the k blocks (uniform control flow), one elected lane issues the MMAs
+        constexpr uint32_t idesc = tc::idesc_bf16_f32(GEMM_BM, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+            tc::mbar_wait(&full[s], ph);
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
 #pragma unroll
                 for (int k = 0; k < GEMM_BK / 16; ++k) {
                     const uint64_t da = A_MN ? tc::smem_desc_sw128_mn(sA + s * S::A_BYTES + k * 2048, GEMM_BK * 128)
@@ -143,8 +144,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
                 tc::umma_commit(&empty[s]);  // frees the ring slot once these MMAs have read it
             }
-            tc::umma_commit(acc_full);       // accumulator complete
+            __syncwarp();
         }
+        if (tc::elect_one()) tc::umma_commit(acc_full);  // accumulator complete
+        __syncwarp();
     } else {
         // ---- epilogue: quadrant q of the accumulator = TMEM lanes [32q, 32q+32) = tile rows ----
         const int q = warp & 3;

@@ -22,6 +22,9 @@
 // row's running threshold, survivors appended to the row's candidate list in global memory.  When a list
 // nears its capacity the warp compacts its 32 rows (warp-parallel k-th-largest by bisection on the float
 // bit pattern) and raises the thresholds.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "scorer.cuh"
 #include "tc.cuh"
 
@@ -29,11 +32,13 @@ namespace trs {
 
 typedef __nv_bfloat16 bf16;
 constexpr int TK_BM = 128, TK_BN = 128, TK_CAP = 512, TK_THREADS = 192, TK_BOX_BYTES = 128 * 128;
+constexpr int TK_TMEM_COLS = 512;  // 2 x 128 accumulator columns + the user tile (Kp / 2 <= 120 columns)
 constexpr int TK_MAX_SPLITS = 8;
 constexpr int TK_MAX_STAGE2 = 4096;  // candidates one user may bring to phase 2 (>= TK_MAX_SPLITS * TK_CAP)
 
 struct TopkDev {
-    int n_query, n_items, nbox, kslices, stages;
+    int n_query, n_items, nbox, kslices, stages, Kp;
+    const bf16* Ub;       // [user_tiles * TK_BM, Kp] bf16([u, 1, 0..])
     int n_item_tiles, tiles_per_split, splits;
     int k, fm;
     const float* unorm;   // [n_query] |[u,1]|
@@ -43,7 +48,10 @@ struct TopkDev {
     int* cand_i;
     int* cand_cnt;        // [n_query, splits]
     int* overflow;        // [n_query]
+    int trace_t0;
+    long long* trace;     // debug (TRS_TOPK_TRACE): [TK_TRACE_TILES][8] clock64 stamps of CTA (0, 0), else null
 };
+constexpr int TK_TRACE_TILES = 1024;  // traced tiles: [trace_t0, trace_t0 + TILES)
 
 __device__ __forceinline__ uint32_t float_key(float x) {  // order-preserving map float -> uint32
     const uint32_t b = __float_as_uint(x);
@@ -67,12 +75,24 @@ __device__ __forceinline__ int compact_row(float* __restrict__ cs, int* __restri
     }
     float keep = -INFINITY;
     if (n >= k) {
-        // largest T with #{key >= T} >= k  ==  key of the k-th largest score
-        uint32_t lo = 0u, hi = 0xffffffffu;
+        // A lower bound of the k-th largest key, by bisection between the row's smallest and largest key down to
+        // 1/256 of their spread (every candidate already passed the previous threshold, so the spread is small):
+        // invariant #{key >= lo} >= k.  Stopping early only keeps a candidate or two more than the exact
+        // k-th-largest would -- ~9 rounds instead of 32.
         uint32_t key[PER];
+        uint32_t kmin = 0xffffffffu, kmax = 0u;
 #pragma unroll
-        for (int i = 0; i < PER; ++i) key[i] = (i * 32 + lane < n) ? float_key(e[i]) : 0u;
-        while (lo < hi) {
+        for (int i = 0; i < PER; ++i) {
+            const bool in = i * 32 + lane < n;
+            key[i] = in ? float_key(e[i]) : 0u;
+            if (in) {
+                kmin = min(kmin, key[i]);
+                kmax = max(kmax, key[i]);
+            }
+        }
+        uint32_t lo = __reduce_min_sync(0xffffffffu, kmin), hi = __reduce_max_sync(0xffffffffu, kmax);
+        const uint32_t stop = (hi - lo) >> 8;
+        while (hi - lo > stop) {
             const uint32_t mid = lo + ((hi - lo) >> 1) + 1u;  // upper middle: lo < mid <= hi
             int c = 0;
 #pragma unroll
@@ -111,14 +131,12 @@ __device__ __forceinline__ int compact_row(float* __restrict__ cs, int* __restri
 }
 
 __global__ void __launch_bounds__(TK_THREADS, 1)
-topk_score_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_v,
+topk_score_kernel(const __grid_constant__ CUtensorMap tmap_v,
                   const __grid_constant__ TopkDev g) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char* sA = base;
-    unsigned char* sB = base + g.nbox * TK_BOX_BYTES;
+    unsigned char* sB = base;
     uint64_t* bars = (uint64_t*)(sB + g.stages * g.nbox * TK_BOX_BYTES);
-    uint64_t* a_full = bars;
     uint64_t* full = bars + 1;
     uint64_t* empty = full + g.stages;
     uint64_t* acc_full = empty + g.stages;   // [2]
@@ -130,11 +148,10 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_const
     const int split = blockIdx.y;
     const int tile0 = split * g.tiles_per_split;
     const int ntiles = min(g.tiles_per_split, g.n_item_tiles - tile0);
+    const bool tracing = g.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
 
     if (warp == 0 && lane == 0) {
-        tc::tma_prefetch_desc(&tmap_u);
         tc::tma_prefetch_desc(&tmap_v);
-        tc::mbar_init(a_full, 1);
         for (int s = 0; s < g.stages; ++s) {
             tc::mbar_init(&full[s], 1);
             tc::mbar_init(&empty[s], 1);
@@ -145,46 +162,68 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_const
         }
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc(tmem_slot, 2 * TK_BN);
+    if (warp == 1) tc::tmem_alloc(tmem_slot, TK_TMEM_COLS);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // The user tile is the A operand of every MMA of this CTA: it goes into tensor memory once (row = lane, two
+    // bf16 per column), so the tensor core streams only the item tiles from shared memory.
+    const uint32_t tmem_a = tmem + 2 * TK_BN;
+    if (warp >= 2) {
+        const int q = warp & 3;
+        const uint32_t* urow = reinterpret_cast<const uint32_t*>(g.Ub + (size_t)(u0 + q * 32 + lane) * g.Kp);
+        for (int c = 0; c < g.Kp / 2; c += 8) {
+            uint32_t r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __ldg(urow + c + j);
+            tc::tmem_st_32x8(tmem_a + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+        }
+        tc::tmem_st_wait();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
 
     if (warp == 0) {
         if (lane == 0) {
-            tc::mbar_arrive_expect_tx(a_full, g.nbox * TK_BOX_BYTES);
-            for (int b = 0; b < g.nbox; ++b) tc::tma_load_2d(sA + b * TK_BOX_BYTES, &tmap_u, a_full, b * 64, u0);
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t % g.stages;
-                const uint32_t ph = (uint32_t)(t / g.stages) & 1u;
+            int s = 0;
+            uint32_t ph = 0;  // ring slot and its phase parity, advanced without divisions
+            for (int t = 0; t < ntiles; ++t, ++s) {
+                if (s == g.stages) { s = 0; ph ^= 1u; }
                 tc::mbar_wait(&empty[s], ph ^ 1u);
+                if (tracing && t >= g.trace_t0 && t < g.trace_t0 + TK_TRACE_TILES) g.trace[(t - g.trace_t0) * 8 + 0] = clock64();
                 tc::mbar_arrive_expect_tx(&full[s], g.nbox * TK_BOX_BYTES);
                 for (int b = 0; b < g.nbox; ++b)
                     tc::tma_load_2d(sB + (s * g.nbox + b) * TK_BOX_BYTES, &tmap_v, &full[s], b * 64, (tile0 + t) * TK_BN);
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc::idesc_bf16_f32(TK_BM, TK_BN);
-            tc::mbar_wait(a_full, 0);
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t % g.stages;
-                const uint32_t ph = (uint32_t)(t / g.stages) & 1u;
-                const int buf = t & 1;
-                const uint32_t bph = (uint32_t)(t >> 1) & 1u;
-                tc::mbar_wait(&acc_empty[buf], bph ^ 1u);
-                tc::mbar_wait(&full[s], ph);
-                tc::tc_fence_after();
+        // the whole warp walks the tiles (uniform control flow), one elected lane issues the MMAs
+        constexpr uint32_t idesc = tc::idesc_bf16_f32(TK_BM, TK_BN);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = 0; t < ntiles; ++t, ++s) {
+            if (s == g.stages) { s = 0; ph ^= 1u; }
+            const int buf = t & 1;
+            const uint32_t bph = (uint32_t)(t >> 1) & 1u;
+            tc::mbar_wait(&acc_empty[buf], bph ^ 1u);
+            if (tracing && lane == 0 && t >= g.trace_t0 && t < g.trace_t0 + TK_TRACE_TILES) g.trace[(t - g.trace_t0) * 8 + 1] = clock64();
+            tc::mbar_wait(&full[s], ph);
+            if (tracing && lane == 0 && t >= g.trace_t0 && t < g.trace_t0 + TK_TRACE_TILES) g.trace[(t - g.trace_t0) * 8 + 2] = clock64();
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
                 for (int ks = 0; ks < g.kslices; ++ks) {
                     const int box = ks >> 2, kin = (ks & 3) * 16;
-                    const uint64_t da = tc::smem_desc_sw128(sA + box * TK_BOX_BYTES, kin);
                     const uint64_t db = tc::smem_desc_sw128(sB + (s * g.nbox + box) * TK_BOX_BYTES, kin);
-                    tc::umma_bf16(tmem + (uint32_t)(buf * TK_BN), da, db, idesc, ks ? 1u : 0u);
+                    tc::umma_bf16_ts(tmem + (uint32_t)(buf * TK_BN), tmem_a + (uint32_t)(ks * 8), db, idesc, ks ? 1u : 0u);
                 }
                 tc::umma_commit(&empty[s]);
                 tc::umma_commit(&acc_full[buf]);
             }
+            __syncwarp();
+            if (tracing && lane == 0 && (t & 255) == 0 && (t >> 8) < 1024) g.trace[TK_TRACE_TILES * 8 + (t >> 8)] = clock64();
+            if (tracing && lane == 0 && t >= g.trace_t0 && t < g.trace_t0 + TK_TRACE_TILES) g.trace[(t - g.trace_t0) * 8 + 3] = clock64();
         }
     } else {
         const int q = warp & 3;
@@ -203,6 +242,8 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_const
             const int buf = t & 1;
             const uint32_t bph = (uint32_t)(t >> 1) & 1u;
             tc::mbar_wait(&acc_full[buf], bph);
+            const bool etr = tracing && warp == 2 && lane == 0 && t >= g.trace_t0 && t < g.trace_t0 + TK_TRACE_TILES;
+            if (etr) g.trace[(t - g.trace_t0) * 8 + 4] = clock64();
             tc::tc_fence_after();
             const int item0 = (tile0 + t) * TK_BN;
             const int ncols = min(TK_BN, g.n_items - item0);
@@ -216,6 +257,7 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_const
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+            if (etr) g.trace[(t - g.trace_t0) * 8 + 5] = clock64();
             if (valid && !over) {
 #pragma unroll
                 for (int c = 0; c < TK_BN / 32; ++c) {
@@ -244,6 +286,7 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_const
                     }
                 }
             }
+            if (etr) g.trace[(t - g.trace_t0) * 8 + 6] = clock64() + (cnt & 0);
             // a list that could overflow on the next tile -> the warp compacts all of its rows; after the
             // last tile every list is compacted once more, so phase 2 only sees scores >= tau_k - margin
             if (__any_sync(0xffffffffu, cnt > TK_CAP - TK_BN || (t == ntiles - 1 && cnt > g.k))) {
@@ -278,7 +321,7 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_const
     __syncthreads();
     if (warp == 1) {
         tc::tc_fence_after();
-        tc::tmem_dealloc(tmem, 2 * TK_BN);
+        tc::tmem_dealloc(tmem, TK_TMEM_COLS);
     }
 }
 
@@ -439,7 +482,7 @@ static TopkLayout topk_layout(const trs_model* m, int64_t n_query) {
     L.Kp = (m->dim + 1 + 15) / 16 * 16;
     L.kslices = L.Kp / 16;
     L.nbox = (L.Kp + 63) / 64;
-    L.stages = L.nbox <= 3 ? 3 : 2;
+    L.stages = L.nbox <= 3 ? 4 : 3;
     L.n_item_tiles = (int)((m->item.n_rows + TK_BN - 1) / TK_BN);
     L.user_tiles = (int)((n_query + TK_BM - 1) / TK_BM);
     // few users: cut the catalogue into up to TK_MAX_SPLITS item ranges so more SMs work; each range keeps
@@ -461,7 +504,7 @@ static TopkLayout topk_layout(const trs_model* m, int64_t n_query) {
     L.cand_cnt = take((size_t)n_query * L.splits * 4);
     L.overflow = take((size_t)n_query * 4);
     L.total = off;
-    L.smem = 1024 + (size_t)(1 + L.stages) * L.nbox * TK_BOX_BYTES + 8 * (2 * L.stages + 5) + 16;
+    L.smem = 1024 + (size_t)L.stages * L.nbox * TK_BOX_BYTES + 8 * (2 * L.stages + 5) + 16;
     return L;
 }
 
@@ -519,6 +562,8 @@ extern "C" int trs_predict_topk(const trs_model* model, const int64_t* users, in
     g.n_items = (int)n_items;
     g.nbox = L.nbox;
     g.kslices = L.kslices;
+    g.Kp = L.Kp;
+    g.Ub = (const bf16*)(W + L.Ub);
     g.stages = L.stages;
     g.n_item_tiles = L.n_item_tiles;
     g.tiles_per_split = L.tiles_per_split;
@@ -532,12 +577,37 @@ extern "C" int trs_predict_topk(const trs_model* model, const int64_t* users, in
     g.cand_i = (int*)(W + L.cand_i);
     g.cand_cnt = (int*)(W + L.cand_cnt);
     g.overflow = overflow;
-    CUtensorMap tu, tv;
-    if ((rc = make_tmap_bf16(&tu, W + L.Ub, (int64_t)L.user_tiles * TK_BM, L.Kp, L.Kp, TK_BM))) return rc;
+    CUtensorMap tv;
     if ((rc = make_tmap_bf16(&tv, W + L.Vb, n_items, L.Kp, L.Kp, TK_BN))) return rc;
     TRS_CUDA(cudaFuncSetAttribute(topk_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-    topk_score_kernel<<<dim3(L.user_tiles, L.splits), TK_THREADS, L.smem, st>>>(tu, tv, g);
+    const char* trace_env = getenv("TRS_TOPK_TRACE");  // debug: pipeline timeline of CTA (0, 0) -> stderr
+    if (trace_env && atoi(trace_env)) {
+        g.trace_t0 = atoi(trace_env) - 1;  // TRS_TOPK_TRACE = first traced tile + 1
+        TRS_CUDA(cudaMalloc(&g.trace, (TK_TRACE_TILES * 8 + 1024) * sizeof(long long)));
+        TRS_CUDA(cudaMemsetAsync(g.trace, 0, (TK_TRACE_TILES * 8 + 1024) * sizeof(long long), st));
+    }
+    topk_score_kernel<<<dim3(L.user_tiles, L.splits), TK_THREADS, L.smem, st>>>(tv, g);
     TRS_CUDA(cudaGetLastError());
+    if (g.trace) {
+        static long long h[TK_TRACE_TILES * 8 + 1024];
+        TRS_CUDA(cudaStreamSynchronize(st));
+        TRS_CUDA(cudaMemcpy(h, g.trace, sizeof(h), cudaMemcpyDeviceToHost));
+        TRS_CUDA(cudaFree(g.trace));
+        const int a = 200, b = 1000;
+        const char* nm[7] = {"producer: slot free", "mma: accumulator free", "mma: operands landed", "mma: issued + committed",
+                             "epilogue: accumulator full", "epilogue: tmem read, buffer released", "epilogue: filtered"};
+        fprintf(stderr, "topk trace (CTA 0, tiles %d..%d): period %.0f cycles/tile\n", g.trace_t0 + a, g.trace_t0 + b, (double)(h[b * 8 + 3] - h[a * 8 + 3]) / (b - a));
+        for (int e = 0; e < 7; ++e) {
+            double off = 0;
+            for (int t = a; t < b; ++t) off += (double)(h[t * 8 + e] - h[t * 8 + 1]);
+            fprintf(stderr, "  %-40s %+8.0f cycles after 'mma: accumulator free' of the same tile\n", nm[e], off / (b - a));
+        }
+        fprintf(stderr, "  cycles/tile per 256-tile window:");
+        for (int w = 0; w + 1 < 1024 && h[TK_TRACE_TILES * 8 + w + 1]; ++w)
+            fprintf(stderr, " %.0f", (double)(h[TK_TRACE_TILES * 8 + w + 1] - h[TK_TRACE_TILES * 8 + w]) / 256);
+        fprintf(stderr, "\n");
+        g.trace = nullptr;
+    }
     RowShape shape;
     pick_row_shape(model->dim, &shape);
     TRS_DISPATCH_ROW_SHAPE(shape, launch_rescore, model, users, item_meta, &g, item_offset, out_idx, out_score, st);
