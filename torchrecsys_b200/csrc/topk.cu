@@ -207,7 +207,7 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_v,
             if (s == g.stages) { s = 0; ph ^= 1u; }
             const int buf = t & 1;
             const uint32_t bph = (uint32_t)(t >> 1) & 1u;
-            tc::mbar_wait(&acc_empty[buf], bph ^ 1u);
+            tc::mbar_wait_spin(&acc_empty[buf], bph ^ 1u);
             if (tracing && lane == 0 && t >= g.trace_t0 && t < g.trace_t0 + TK_TRACE_TILES) g.trace[(t - g.trace_t0) * 8 + 1] = clock64();
             tc::mbar_wait(&full[s], ph);
             if (tracing && lane == 0 && t >= g.trace_t0 && t < g.trace_t0 + TK_TRACE_TILES) g.trace[(t - g.trace_t0) * 8 + 2] = clock64();
@@ -241,7 +241,7 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_v,
         for (int t = 0; t < ntiles; ++t) {
             const int buf = t & 1;
             const uint32_t bph = (uint32_t)(t >> 1) & 1u;
-            tc::mbar_wait(&acc_full[buf], bph);
+            tc::mbar_wait_spin(&acc_full[buf], bph);
             const bool etr = tracing && warp == 2 && lane == 0 && t >= g.trace_t0 && t < g.trace_t0 + TK_TRACE_TILES;
             if (etr) g.trace[(t - g.trace_t0) * 8 + 4] = clock64();
             tc::tc_fence_after();
@@ -267,20 +267,26 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_v,
 #pragma unroll
                     for (int j = 0; j < 16; ++j) m16[j] = fmaxf(__uint_as_float(r[c][j]), __uint_as_float(r[c][j + 16]));
 #pragma unroll
-                    for (int w = 8; w >= 1; w >>= 1)
+                    for (int w = 8; w >= 4; w >>= 1)
 #pragma unroll
                         for (int j = 0; j < w; ++j) m16[j] = fmaxf(m16[j], m16[j + w]);
-                    if (m16[0] >= thr) {
+                    // m16[jj], jj < 4: the maximum of the 8 columns jj, jj + 4, ..., jj + 28
+                    if (fmaxf(fmaxf(m16[0], m16[1]), fmaxf(m16[2], m16[3])) >= thr) {
                         const int lim = ncols - c * 32;  // columns of this chunk that are real items
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float v = __uint_as_float(r[c][j]);
-                            if (v >= thr && j < lim) {
-                                if (cnt < TK_CAP) {
-                                    cs[cnt] = v;
-                                    ci[cnt] = item0 + c * 32 + j;
+                        for (int jj = 0; jj < 4; ++jj) {
+                            if (m16[jj] < thr) continue;  // while the threshold still rises most of a chunk fails
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int j = jj + 4 * i;
+                                const float v = __uint_as_float(r[c][j]);
+                                if (v >= thr && j < lim) {
+                                    if (cnt < TK_CAP) {
+                                        cs[cnt] = v;
+                                        ci[cnt] = item0 + c * 32 + j;
+                                    }
+                                    ++cnt;
                                 }
-                                ++cnt;
                             }
                         }
                     }
@@ -488,7 +494,9 @@ static TopkLayout topk_layout(const trs_model* m, int64_t n_query) {
     // few users: cut the catalogue into up to TK_MAX_SPLITS item ranges so more SMs work; each range keeps
     // its own candidate list (<= TK_CAP - TK_BN entries after the final compaction), and a range needs
     // enough tiles for the running threshold to bite
-    int want = (2 * device_props().sm_count + L.user_tiles - 1) / L.user_tiles;
+    // (one CTA per SM and no more: every item range pays its own threshold warm-up -- the first ~2000 tiles of a
+    // range run at a third of the steady-state rate -- so a second wave of ranges costs more than it balances)
+    int want = (device_props().sm_count + L.user_tiles - 1) / L.user_tiles;
     if (want > TK_MAX_SPLITS) want = TK_MAX_SPLITS;
     if (want > L.n_item_tiles / 16) want = L.n_item_tiles / 16;
     L.splits = want < 1 ? 1 : want;
