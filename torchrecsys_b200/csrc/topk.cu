@@ -31,8 +31,13 @@
 namespace trs {
 
 typedef __nv_bfloat16 bf16;
-constexpr int TK_BM = 128, TK_BN = 128, TK_CAP = 512, TK_THREADS = 192, TK_BOX_BYTES = 128 * 128;
-constexpr int TK_TMEM_COLS = 512;  // 2 x 128 accumulator columns + the user tile (Kp / 2 <= 120 columns)
+// Item tile = 192 rows: one tcgen05.mma (128 x 192 x 16) runs 96 cycles, so the ~300 cycles the issuing warp
+// needs per tile for barriers and descriptors cost a quarter less than at 128, and two accumulators (2 x 192
+// columns) plus the user tile (<= 120 columns) still fit the 512 columns of tensor memory.
+constexpr int TK_BM = 128, TK_BN = 192, TK_CAP = 512, TK_THREADS = 192, TK_BOX_BYTES = TK_BN * 128;
+constexpr int TK_SYNC_EVERY = 64, TK_SYNC_WINDOW = 768;  // tiles; 768 tiles of 192 x 288 B = 42 MB of the 126 MB L2
+constexpr int TK_HALF = TK_BN / 64;  // 32-column chunks the epilogue holds in registers at a time
+constexpr int TK_TMEM_COLS = 512;  // 2 x 192 accumulator columns + the user tile (Kp / 2 <= 120 columns)
 constexpr int TK_MAX_SPLITS = 8;
 constexpr int TK_MAX_STAGE2 = 4096;  // candidates one user may bring to phase 2 (>= TK_MAX_SPLITS * TK_CAP)
 
@@ -48,6 +53,7 @@ struct TopkDev {
     int* cand_i;
     int* cand_cnt;        // [n_query, splits]
     int* overflow;        // [n_query]
+    int* progress;        // [splits, user_tiles] producer position of every CTA (-1 not started, INT_MAX finished)
     int trace_t0;
     long long* trace;     // debug (TRS_TOPK_TRACE): [TK_TRACE_TILES][8] clock64 stamps of CTA (0, 0), else null
 };
@@ -62,17 +68,25 @@ __device__ __forceinline__ float key_float(uint32_t k) {
 }
 
 // warp-cooperative compaction of one row's candidate list; returns the new count, sets thr
-__device__ __forceinline__ int compact_row(float* __restrict__ cs, int* __restrict__ ci, int n, int k, float margin2,
-                                           float ulin, int fm, int lane, float& thr_out) {
-    constexpr int PER = TK_CAP / 32;
-    float e[PER];
-    int id[PER];
+constexpr int TK_PER = TK_CAP / 32;  // list entries per lane
+struct RowList {
+    float e[TK_PER];
+    int id[TK_PER];
+};
+__device__ __forceinline__ void load_list(const float* __restrict__ cs, const int* __restrict__ ci, int n, int lane,
+                                          RowList& L) {
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
+    for (int i = 0; i < TK_PER; ++i) {
         const int slot = i * 32 + lane;
-        e[i] = slot < n ? cs[slot] : -INFINITY;
-        id[i] = slot < n ? ci[slot] : 0;
+        L.e[i] = slot < n ? cs[slot] : -INFINITY;
+        L.id[i] = slot < n ? ci[slot] : 0;
     }
+}
+__device__ __forceinline__ int compact_row(float* __restrict__ cs, int* __restrict__ ci, const RowList& L, int n, int k,
+                                           float margin2, float ulin, int fm, int lane, float& thr_out) {
+    constexpr int PER = TK_PER;
+    const float (&e)[TK_PER] = L.e;
+    const int (&id)[TK_PER] = L.id;
     float keep = -INFINITY;
     if (n >= k) {
         // A lower bound of the k-th largest key, by bisection between the row's smallest and largest key down to
@@ -186,18 +200,40 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_v,
     tc::tc_fence_after();
 
     if (warp == 0) {
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;  // ring slot and its phase parity, advanced without divisions
-            for (int t = 0; t < ntiles; ++t, ++s) {
-                if (s == g.stages) { s = 0; ph ^= 1u; }
-                tc::mbar_wait(&empty[s], ph ^ 1u);
-                if (tracing && t >= g.trace_t0 && t < g.trace_t0 + TK_TRACE_TILES) g.trace[(t - g.trace_t0) * 8 + 0] = clock64();
+        // Producer.  Every CTA of an item range streams the same tiles: as long as they stay within an L2's reach
+        // of each other one DRAM read serves them all, but a CTA that falls behind (list compactions are
+        // data-dependent) re-reads everything from DRAM at 1/148 of the bandwidth and falls further behind.  So
+        // the ranges run in loose lock-step: each producer publishes its position every TK_SYNC_EVERY tiles and
+        // waits while an active CTA of its range is between TK_SYNC_WINDOW and 4x that many tiles behind it.
+        // (Further behind = a CTA of a later wave: not waited for.  Only CTAs AHEAD ever wait, the last active
+        // one never does, so there is no cycle.)
+        int* prog = g.progress + (size_t)split * gridDim.x;
+        int s = 0;
+        uint32_t ph = 0;  // ring slot and its phase parity, advanced without divisions
+        for (int t = 0; t < ntiles; ++t, ++s) {
+            if (s == g.stages) { s = 0; ph ^= 1u; }
+            if ((t & (TK_SYNC_EVERY - 1)) == 0) {
+                if (lane == 0) *(volatile int*)(prog + blockIdx.x) = t;
+                for (;;) {
+                    int behind = 0;
+                    for (int p = lane; p < (int)gridDim.x; p += 32) {
+                        const int v = *(volatile const int*)(prog + p);
+                        behind |= (v >= 0 && v < t - TK_SYNC_WINDOW && v > t - 4 * TK_SYNC_WINDOW) ? 1 : 0;
+                    }
+                    if (!__any_sync(0xffffffffu, behind)) break;
+                    __nanosleep(500);
+                }
+            }
+            tc::mbar_wait(&empty[s], ph ^ 1u);
+            if (tracing && lane == 0 && t >= g.trace_t0 && t < g.trace_t0 + TK_TRACE_TILES) g.trace[(t - g.trace_t0) * 8 + 0] = clock64();
+            if (tc::elect_one()) {
                 tc::mbar_arrive_expect_tx(&full[s], g.nbox * TK_BOX_BYTES);
                 for (int b = 0; b < g.nbox; ++b)
                     tc::tma_load_2d(sB + (s * g.nbox + b) * TK_BOX_BYTES, &tmap_v, &full[s], b * 64, (tile0 + t) * TK_BN);
             }
+            __syncwarp();
         }
+        if (lane == 0) *(volatile int*)(prog + blockIdx.x) = 0x7fffffff;  // finished: nobody waits for me
     } else if (warp == 1) {
         // the whole warp walks the tiles (uniform control flow), one elected lane issues the MMAs
         constexpr uint32_t idesc = tc::idesc_bf16_f32(TK_BM, TK_BN);
@@ -247,45 +283,51 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_v,
             tc::tc_fence_after();
             const int item0 = (tile0 + t) * TK_BN;
             const int ncols = min(TK_BN, g.n_items - item0);
-            // all four 32-column chunks of the row are fetched back to back (one TMEM round trip), the
-            // buffer is handed back to the MMA warp at once, and the filtering runs from registers
-            uint32_t r[TK_BN / 32][32];
+            // the row's 32-column chunks are fetched in two batches (one TMEM round trip each; 96 registers), the
+            // buffer is handed back to the MMA warp after the second, and the filtering runs from registers
 #pragma unroll
-            for (int c = 0; c < TK_BN / 32; ++c)
-                tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TK_BN + c * 32), r[c]);
-            tc::tmem_ld_wait();
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
-            if (etr) g.trace[(t - g.trace_t0) * 8 + 5] = clock64();
-            if (valid && !over) {
+            for (int half = 0; half < 2; ++half) {
+                uint32_t r[TK_HALF][32];
 #pragma unroll
-                for (int c = 0; c < TK_BN / 32; ++c) {
-                    // steady state: about k/n of the scores pass, so first ask whether ANY of the 32 does
-                    // (branch-free max tree, independent pairs), and only then walk the chunk
-                    float m16[16];
+                for (int c = 0; c < TK_HALF; ++c)
+                    tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TK_BN + (half * TK_HALF + c) * 32), r[c]);
+                tc::tmem_ld_wait();
+                if (half == 1) {
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+                    if (etr) g.trace[(t - g.trace_t0) * 8 + 5] = clock64();
+                }
+                if (valid && !over) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) m16[j] = fmaxf(__uint_as_float(r[c][j]), __uint_as_float(r[c][j + 16]));
+                    for (int c = 0; c < TK_HALF; ++c) {
+                        // steady state: about k/n of the scores pass, so first ask whether ANY of the 32 does
+                        // (branch-free max tree, independent pairs), and only then walk the chunk
+                        float m16[16];
 #pragma unroll
-                    for (int w = 8; w >= 4; w >>= 1)
+                        for (int j = 0; j < 16; ++j) m16[j] = fmaxf(__uint_as_float(r[c][j]), __uint_as_float(r[c][j + 16]));
 #pragma unroll
-                        for (int j = 0; j < w; ++j) m16[j] = fmaxf(m16[j], m16[j + w]);
-                    // m16[jj], jj < 4: the maximum of the 8 columns jj, jj + 4, ..., jj + 28
-                    if (fmaxf(fmaxf(m16[0], m16[1]), fmaxf(m16[2], m16[3])) >= thr) {
-                        const int lim = ncols - c * 32;  // columns of this chunk that are real items
+                        for (int w = 8; w >= 4; w >>= 1)
 #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            if (m16[jj] < thr) continue;  // while the threshold still rises most of a chunk fails
+                            for (int j = 0; j < w; ++j) m16[j] = fmaxf(m16[j], m16[j + w]);
+                        // m16[jj], jj < 4: the maximum of the 8 columns jj, jj + 4, ..., jj + 28
+                        if (fmaxf(fmaxf(m16[0], m16[1]), fmaxf(m16[2], m16[3])) >= thr) {
+                            const int col0 = (half * TK_HALF + c) * 32;
+                            const int lim = ncols - col0;  // columns of this chunk that are real items
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int j = jj + 4 * i;
-                                const float v = __uint_as_float(r[c][j]);
-                                if (v >= thr && j < lim) {
-                                    if (cnt < TK_CAP) {
-                                        cs[cnt] = v;
-                                        ci[cnt] = item0 + c * 32 + j;
+                            for (int jj = 0; jj < 4; ++jj) {
+                                if (m16[jj] < thr) continue;  // while the threshold still rises most of a chunk fails
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const int j = jj + 4 * i;
+                                    const float v = __uint_as_float(r[c][j]);
+                                    if (v >= thr && j < lim) {
+                                        if (cnt < TK_CAP) {
+                                            cs[cnt] = v;
+                                            ci[cnt] = item0 + col0 + j;
+                                        }
+                                        ++cnt;
                                     }
-                                    ++cnt;
                                 }
                             }
                         }
@@ -297,16 +339,32 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_v,
             // last tile every list is compacted once more, so phase 2 only sees scores >= tau_k - margin
             if (__any_sync(0xffffffffu, cnt > TK_CAP - TK_BN || (t == ntiles - 1 && cnt > g.k))) {
                 __syncwarp();
-                for (int rr = 0; rr < 32; ++rr) {
+                const long long c_t0 = tracing ? clock64() : 0;
+                int c_rows = 0;
+                // only the rows that are filling up (every row with more than k entries after the last tile): the
+                // others keep their threshold.  The next row's list is fetched while the current one is compacted.
+                const bool need = valid && !over && cnt > (t == ntiles - 1 ? g.k : TK_CAP / 2);
+                unsigned todo = __ballot_sync(0xffffffffu, need);
+                RowList cur, nxt;
+                auto list_of = [&](int rr) { return ((size_t)(u0 + q * 32 + rr) * g.splits + split) * TK_CAP; };
+                if (todo) {
+                    const int rr = __ffs(todo) - 1;
+                    load_list(g.cand_s + list_of(rr), g.cand_i + list_of(rr), min(__shfl_sync(0xffffffffu, cnt, rr), TK_CAP), lane, cur);
+                }
+                while (todo) {
+                    const int rr = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    if (todo) {
+                        const int r2 = __ffs(todo) - 1;
+                        load_list(g.cand_s + list_of(r2), g.cand_i + list_of(r2), min(__shfl_sync(0xffffffffu, cnt, r2), TK_CAP), lane, nxt);
+                    }
+                    ++c_rows;
                     const int n_r = __shfl_sync(0xffffffffu, cnt, rr);
-                    const int row_r = u0 + q * 32 + rr;
-                    if (row_r >= g.n_query || n_r == 0) continue;
                     const float m_r = __shfl_sync(0xffffffffu, margin2, rr);
                     const float ul_r = __shfl_sync(0xffffffffu, ulin, rr);
-                    const size_t l_r = ((size_t)row_r * g.splits + split) * TK_CAP;
                     float thr_r;
-                    const int new_n = compact_row(g.cand_s + l_r, g.cand_i + l_r, min(n_r, TK_CAP), g.k, m_r, ul_r, g.fm,
-                                                  lane, thr_r);
+                    const int new_n = compact_row(g.cand_s + list_of(rr), g.cand_i + list_of(rr), cur, min(n_r, TK_CAP), g.k, m_r,
+                                                  ul_r, g.fm, lane, thr_r);
                     if (lane == rr) {
                         if (n_r > TK_CAP || new_n > TK_CAP - TK_BN) {
                             // the margin admits more candidates than a list holds: this user takes the
@@ -317,6 +375,11 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_v,
                         cnt = over ? 0 : new_n;
                         thr = thr_r;
                     }
+                    cur = nxt;
+                }
+                if (tracing && lane == 0 && (t >> 8) < 1024) {
+                    atomicAdd((unsigned long long*)&g.trace[TK_TRACE_TILES * 8 + 1024 + (t >> 8)], (unsigned long long)c_rows);
+                    atomicAdd((unsigned long long*)&g.trace[TK_TRACE_TILES * 8 + 2048 + (t >> 8)], (unsigned long long)(clock64() - c_t0));
                 }
             }
         }
@@ -474,7 +537,7 @@ static void launch_rescore(const trs_model* m, const int64_t* users, const int64
 
 struct TopkLayout {
     int Kp, nbox, kslices, stages, n_item_tiles, user_tiles, splits, tiles_per_split;
-    size_t Ub, Vb, unorm, ulin, vmax2, cand_s, cand_i, cand_cnt, overflow, total;
+    size_t Ub, Vb, unorm, ulin, vmax2, cand_s, cand_i, cand_cnt, overflow, progress, total;
     size_t smem;
 };
 static TopkLayout topk_layout(const trs_model* m, int64_t n_query) {
@@ -488,7 +551,7 @@ static TopkLayout topk_layout(const trs_model* m, int64_t n_query) {
     L.Kp = (m->dim + 1 + 15) / 16 * 16;
     L.kslices = L.Kp / 16;
     L.nbox = (L.Kp + 63) / 64;
-    L.stages = L.nbox <= 3 ? 4 : 3;
+    L.stages = L.nbox <= 3 ? 3 : 2;
     L.n_item_tiles = (int)((m->item.n_rows + TK_BN - 1) / TK_BN);
     L.user_tiles = (int)((n_query + TK_BM - 1) / TK_BM);
     // few users: cut the catalogue into up to TK_MAX_SPLITS item ranges so more SMs work; each range keeps
@@ -511,6 +574,7 @@ static TopkLayout topk_layout(const trs_model* m, int64_t n_query) {
     L.cand_i = take((size_t)n_query * L.splits * TK_CAP * 4);
     L.cand_cnt = take((size_t)n_query * L.splits * 4);
     L.overflow = take((size_t)n_query * 4);
+    L.progress = take((size_t)L.splits * L.user_tiles * 4);
     L.total = off;
     L.smem = 1024 + (size_t)L.stages * L.nbox * TK_BOX_BYTES + 8 * (2 * L.stages + 5) + 16;
     return L;
@@ -585,19 +649,21 @@ extern "C" int trs_predict_topk(const trs_model* model, const int64_t* users, in
     g.cand_i = (int*)(W + L.cand_i);
     g.cand_cnt = (int*)(W + L.cand_cnt);
     g.overflow = overflow;
+    g.progress = (int*)(W + L.progress);
+    TRS_CUDA(cudaMemsetAsync(g.progress, 0xff, (size_t)L.splits * L.user_tiles * 4, st));
     CUtensorMap tv;
     if ((rc = make_tmap_bf16(&tv, W + L.Vb, n_items, L.Kp, L.Kp, TK_BN))) return rc;
     TRS_CUDA(cudaFuncSetAttribute(topk_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     const char* trace_env = getenv("TRS_TOPK_TRACE");  // debug: pipeline timeline of CTA (0, 0) -> stderr
     if (trace_env && atoi(trace_env)) {
         g.trace_t0 = atoi(trace_env) - 1;  // TRS_TOPK_TRACE = first traced tile + 1
-        TRS_CUDA(cudaMalloc(&g.trace, (TK_TRACE_TILES * 8 + 1024) * sizeof(long long)));
-        TRS_CUDA(cudaMemsetAsync(g.trace, 0, (TK_TRACE_TILES * 8 + 1024) * sizeof(long long), st));
+        TRS_CUDA(cudaMalloc(&g.trace, (TK_TRACE_TILES * 8 + 3072) * sizeof(long long)));
+        TRS_CUDA(cudaMemsetAsync(g.trace, 0, (TK_TRACE_TILES * 8 + 3072) * sizeof(long long), st));
     }
     topk_score_kernel<<<dim3(L.user_tiles, L.splits), TK_THREADS, L.smem, st>>>(tv, g);
     TRS_CUDA(cudaGetLastError());
     if (g.trace) {
-        static long long h[TK_TRACE_TILES * 8 + 1024];
+        static long long h[TK_TRACE_TILES * 8 + 3072];
         TRS_CUDA(cudaStreamSynchronize(st));
         TRS_CUDA(cudaMemcpy(h, g.trace, sizeof(h), cudaMemcpyDeviceToHost));
         TRS_CUDA(cudaFree(g.trace));
@@ -613,6 +679,9 @@ extern "C" int trs_predict_topk(const trs_model* model, const int64_t* users, in
         fprintf(stderr, "  cycles/tile per 256-tile window:");
         for (int w = 0; w + 1 < 1024 && h[TK_TRACE_TILES * 8 + w + 1]; ++w)
             fprintf(stderr, " %.0f", (double)(h[TK_TRACE_TILES * 8 + w + 1] - h[TK_TRACE_TILES * 8 + w]) / 256);
+        fprintf(stderr, "\n  rows compacted / kcycles spent compacting per window (4 epilogue warps):");
+        for (int w = 0; w + 1 < 1024 && h[TK_TRACE_TILES * 8 + w + 1]; ++w)
+            fprintf(stderr, " %lld/%lld", h[TK_TRACE_TILES * 8 + 1024 + w], h[TK_TRACE_TILES * 8 + 2048 + w] / 1000);
         fprintf(stderr, "\n");
         g.trace = nullptr;
     }
