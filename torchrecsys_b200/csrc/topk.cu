@@ -53,6 +53,7 @@ struct TopkDev {
     int* cand_i;
     int* cand_cnt;        // [n_query, splits]
     int* overflow;        // [n_query]
+    int sync_window;      // tiles a producer may run ahead of the slowest active CTA of its range
     int* progress;        // [splits, user_tiles] producer position of every CTA (-1 not started, INT_MAX finished)
     int trace_t0;
     long long* trace;     // debug (TRS_TOPK_TRACE): [TK_TRACE_TILES][8] clock64 stamps of CTA (0, 0), else null
@@ -218,7 +219,7 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_v,
                     int behind = 0;
                     for (int p = lane; p < (int)gridDim.x; p += 32) {
                         const int v = *(volatile const int*)(prog + p);
-                        behind |= (v >= 0 && v < t - TK_SYNC_WINDOW && v > t - 4 * TK_SYNC_WINDOW) ? 1 : 0;
+                        behind |= (v >= 0 && v < t - g.sync_window && v > t - 4 * g.sync_window) ? 1 : 0;
                     }
                     if (!__any_sync(0xffffffffu, behind)) break;
                     __nanosleep(500);
@@ -395,32 +396,59 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_v,
 }
 
 // ---- operand preparation ------------------------------------------------------------------------------
-// one warp per item: Vb[i] = bf16([w_i, c_i, 0...]) and max |[w_i, c_i]|^2
+// one warp per item: Vb[i] = bf16([w_i, c_i, 0...]) and max |[w_i, c_i]|^2.  VEC: n_factors % 4 == 0 -- every lane
+// moves four consecutive factors per access (16-byte loads, 8-byte bf16 stores).
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 topk_prep_items_kernel(const __grid_constant__ trs_model m, const int64_t* __restrict__ item_meta, int64_t n_items,
                        int Kp, bf16* __restrict__ Vb, unsigned* __restrict__ vmax2_bits) {
     const int lane = threadIdx.x & 31;
     const int D = m.dim, F = m.n_meta;
+    constexpr int W = VEC ? 4 : 1;
     float wmax = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < n_items; i += (int64_t)gridDim.x * 8) {
         float c = m.item.lin ? m.item.lin[i] : 0.f;
         float half = 0.f, n2 = 0.f;
-        for (int d = lane; d < Kp; d += 32) {
-            float w = 0.f;
-            if (d < D) {
-                const float v = m.item.emb[(size_t)i * D + d];
-                w = v;
-                float q = v * v;
-                for (int f = 0; f < F; ++f) {
-                    const float e = m.meta[f].emb[(size_t)item_meta[i * F + f] * D + d];
-                    w += e;
-                    q = fmaf(e, e, q);
+        bf16* out = Vb + (size_t)i * Kp;
+        for (int d = lane * W; d < D; d += 32 * W) {
+            float w[W], q[W];
+            if (VEC) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(m.item.emb + (size_t)i * D + d));
+                w[0] = v.x; w[W > 1 ? 1 : 0] = v.y; w[W > 2 ? 2 : 0] = v.z; w[W > 3 ? 3 : 0] = v.w;
+            } else {
+                w[0] = m.item.emb[(size_t)i * D + d];
+            }
+#pragma unroll
+            for (int x = 0; x < W; ++x) q[x] = w[x] * w[x];
+            for (int f = 0; f < F; ++f) {
+                const float* mrow = m.meta[f].emb + (size_t)item_meta[i * F + f] * D + d;
+                float e[W];
+                if (VEC) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(mrow));
+                    e[0] = v.x; e[W > 1 ? 1 : 0] = v.y; e[W > 2 ? 2 : 0] = v.z; e[W > 3 ? 3 : 0] = v.w;
+                } else {
+                    e[0] = mrow[0];
                 }
-                half += w * w - q;
-                n2 = fmaf(w, w, n2);
-                Vb[(size_t)i * Kp + d] = __float2bfloat16_rn(w);
-            } else if (d > D) {
-                Vb[(size_t)i * Kp + d] = __float2bfloat16_rn(0.f);
+#pragma unroll
+                for (int x = 0; x < W; ++x) {
+                    w[x] += e[x];
+                    q[x] = fmaf(e[x], e[x], q[x]);
+                }
+            }
+#pragma unroll
+            for (int x = 0; x < W; ++x) {
+                half += w[x] * w[x] - q[x];
+                n2 = fmaf(w[x], w[x], n2);
+            }
+            if (VEC) {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(w[0], w[W > 1 ? 1 : 0]);
+                const __nv_bfloat162 hi = __floats2bfloat162_rn(w[W > 2 ? 2 : 0], w[W > 3 ? 3 : 0]);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(out + d) = pk;
+            } else {
+                out[d] = __float2bfloat16_rn(w[0]);
             }
         }
         half = warp_sum(half);
@@ -430,7 +458,8 @@ topk_prep_items_kernel(const __grid_constant__ trs_model m, const int64_t* __res
                 if (m.meta[f].lin) c += m.meta[f].lin[item_meta[i * F + f]];
             c += 0.5f * half;
         }
-        if (lane == 0) Vb[(size_t)i * Kp + D] = __float2bfloat16_rn(c);
+        // the extra K column and the zero padding up to Kp
+        for (int d = D + lane; d < Kp; d += 32) out[d] = __float2bfloat16_rn(d == D ? c : 0.f);
         wmax = fmaxf(wmax, n2 + c * c);
     }
     if (lane == 0) atomicMax(vmax2_bits, __float_as_uint(wmax));  // non-negative floats order like their bits
@@ -624,8 +653,12 @@ extern "C" int trs_predict_topk(const trs_model* model, const int64_t* users, in
     {
         long long blocks = (n_items + 7) / 8;
         const long long cap = (long long)device_props().sm_count * 32;
-        topk_prep_items_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(
-            *model, item_meta, n_items, L.Kp, (bf16*)(W + L.Vb), (unsigned*)(W + L.vmax2));
+        if (model->dim % 4 == 0)
+            topk_prep_items_kernel<true><<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(
+                *model, item_meta, n_items, L.Kp, (bf16*)(W + L.Vb), (unsigned*)(W + L.vmax2));
+        else
+            topk_prep_items_kernel<false><<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(
+                *model, item_meta, n_items, L.Kp, (bf16*)(W + L.Vb), (unsigned*)(W + L.vmax2));
         topk_prep_users_kernel<<<(int)((n_query + 7) / 8), 256, 0, st>>>(*model, users, (int)n_query, L.Kp, (bf16*)(W + L.Ub),
                                                                          (float*)(W + L.unorm), (float*)(W + L.ulin));
     }
@@ -650,6 +683,10 @@ extern "C" int trs_predict_topk(const trs_model* model, const int64_t* users, in
     g.cand_cnt = (int*)(W + L.cand_cnt);
     g.overflow = overflow;
     g.progress = (int*)(W + L.progress);
+    {
+        const char* w_env = getenv("TRS_TOPK_WINDOW");  // tuning hook
+        g.sync_window = (w_env && atoi(w_env) > 0) ? atoi(w_env) : TK_SYNC_WINDOW;
+    }
     TRS_CUDA(cudaMemsetAsync(g.progress, 0xff, (size_t)L.splits * L.user_tiles * 4, st));
     CUtensorMap tv;
     if ((rc = make_tmap_bf16(&tv, W + L.Vb, n_items, L.Kp, L.Kp, TK_BN))) return rc;
