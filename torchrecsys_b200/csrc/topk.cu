@@ -36,7 +36,8 @@ typedef __nv_bfloat16 bf16;
 // columns) plus the user tile (<= 120 columns) still fit the 512 columns of tensor memory.
 constexpr int TK_BM = 128, TK_BN = 192, TK_CAP = 512, TK_THREADS = 192, TK_BOX_BYTES = TK_BN * 128;
 constexpr int TK_SYNC_EVERY = 64, TK_SYNC_WINDOW = 768;  // tiles; 768 tiles of 192 x 288 B = 42 MB of the 126 MB L2
-constexpr int TK_HALF = TK_BN / 64;  // 32-column chunks the epilogue holds in registers at a time
+constexpr int TK_HALF = 2;  // 32-column chunks the epilogue holds in registers at a time
+constexpr int TK_BATCHES = TK_BN / (32 * TK_HALF);
 constexpr int TK_TMEM_COLS = 512;  // 2 x 192 accumulator columns + the user tile (Kp / 2 <= 120 columns)
 constexpr int TK_MAX_SPLITS = 8;
 constexpr int TK_MAX_STAGE2 = 4096;  // candidates one user may bring to phase 2 (>= TK_MAX_SPLITS * TK_CAP)
@@ -164,6 +165,8 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_v,
     const int tile0 = split * g.tiles_per_split;
     const int ntiles = min(g.tiles_per_split, g.n_item_tiles - tile0);
     const bool tracing = g.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+    __shared__ int s_compact_req;  // last tile (+1) at which an epilogue warp asked for a list compaction
+    if (threadIdx.x == 0) s_compact_req = 0;
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmap_v);
@@ -244,7 +247,7 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_v,
             if (s == g.stages) { s = 0; ph ^= 1u; }
             const int buf = t & 1;
             const uint32_t bph = (uint32_t)(t >> 1) & 1u;
-            tc::mbar_wait_spin(&acc_empty[buf], bph ^ 1u);
+            tc::mbar_wait(&acc_empty[buf], bph ^ 1u);
             if (tracing && lane == 0 && t >= g.trace_t0 && t < g.trace_t0 + TK_TRACE_TILES) g.trace[(t - g.trace_t0) * 8 + 1] = clock64();
             tc::mbar_wait(&full[s], ph);
             if (tracing && lane == 0 && t >= g.trace_t0 && t < g.trace_t0 + TK_TRACE_TILES) g.trace[(t - g.trace_t0) * 8 + 2] = clock64();
@@ -272,28 +275,30 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_v,
         const float vmax = sqrtf(__ldg(g.vmax2));
         const float margin2 = valid ? 0.015625f * 1.004f * __ldg(g.unorm + row) * vmax : 0.f;
         const float ulin = valid ? __ldg(g.ulin + row) : 0.f;
-        int cnt = 0;
+        int cnt = 0, joined = 0;
         float thr = -INFINITY;
         bool over = false;
         for (int t = 0; t < ntiles; ++t) {
             const int buf = t & 1;
             const uint32_t bph = (uint32_t)(t >> 1) & 1u;
-            tc::mbar_wait_spin(&acc_full[buf], bph);
+            tc::mbar_wait(&acc_full[buf], bph);
             const bool etr = tracing && warp == 2 && lane == 0 && t >= g.trace_t0 && t < g.trace_t0 + TK_TRACE_TILES;
             if (etr) g.trace[(t - g.trace_t0) * 8 + 4] = clock64();
             tc::tc_fence_after();
             const int item0 = (tile0 + t) * TK_BN;
             const int ncols = min(TK_BN, g.n_items - item0);
-            // the row's 32-column chunks are fetched in two batches (one TMEM round trip each; 96 registers), the
-            // buffer is handed back to the MMA warp after the second, and the filtering runs from registers
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            // the row's 32-column chunks are fetched in batches (one TMEM round trip each; 64 registers), the buffer
+            // is handed back to the MMA warp after the last, and the filtering runs from registers.  The batch
+            // loop is NOT unrolled: the filter's rarely taken append path is ~250 instructions per chunk, and the
+            // MMA-issuing warp shares the instruction cache with this code.
+#pragma unroll 1
+            for (int half = 0; half < TK_BATCHES; ++half) {
                 uint32_t r[TK_HALF][32];
 #pragma unroll
                 for (int c = 0; c < TK_HALF; ++c)
                     tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TK_BN + (half * TK_HALF + c) * 32), r[c]);
                 tc::tmem_ld_wait();
-                if (half == 1) {
+                if (half == TK_BATCHES - 1) {
                     tc::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
@@ -338,7 +343,16 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_v,
             if (etr) g.trace[(t - g.trace_t0) * 8 + 6] = clock64() + (cnt & 0);
             // a list that could overflow on the next tile -> the warp compacts all of its rows; after the
             // last tile every list is compacted once more, so phase 2 only sees scores >= tau_k - margin
-            if (__any_sync(0xffffffffu, cnt > TK_CAP - TK_BN || (t == ntiles - 1 && cnt > g.k))) {
+            // The four epilogue warps compact TOGETHER: a compaction stalls the whole pipeline (the MMA warp
+            // needs all four to release an accumulator), so four events at different tiles cost four stalls.
+            // The warp that must compact posts the tile number; the others join at their next tile.
+            const bool trig = __any_sync(0xffffffffu, cnt > TK_CAP - TK_BN || (t == ntiles - 1 && cnt > g.k));
+            if (etr) g.trace[(t - g.trace_t0) * 8 + 7] = clock64();
+            if (trig && lane == 0) atomicMax(&s_compact_req, t + 1);
+            __syncwarp();
+            const int req = *(volatile int*)&s_compact_req;
+            if (trig || req > joined) {
+                joined = max(req, t + 1);
                 __syncwarp();
                 const long long c_t0 = tracing ? clock64() : 0;
                 int c_rows = 0;
@@ -705,10 +719,11 @@ extern "C" int trs_predict_topk(const trs_model* model, const int64_t* users, in
         TRS_CUDA(cudaMemcpy(h, g.trace, sizeof(h), cudaMemcpyDeviceToHost));
         TRS_CUDA(cudaFree(g.trace));
         const int a = 200, b = 1000;
-        const char* nm[7] = {"producer: slot free", "mma: accumulator free", "mma: operands landed", "mma: issued + committed",
-                             "epilogue: accumulator full", "epilogue: tmem read, buffer released", "epilogue: filtered"};
+        const char* nm[8] = {"producer: slot free", "mma: accumulator free", "mma: operands landed", "mma: issued + committed",
+                             "epilogue: accumulator full", "epilogue: tmem read, buffer released", "epilogue: filtered (lane 0)",
+                             "epilogue: warp reconverged"};
         fprintf(stderr, "topk trace (CTA 0, tiles %d..%d): period %.0f cycles/tile\n", g.trace_t0 + a, g.trace_t0 + b, (double)(h[b * 8 + 3] - h[a * 8 + 3]) / (b - a));
-        for (int e = 0; e < 7; ++e) {
+        for (int e = 0; e < 8; ++e) {
             double off = 0;
             for (int t = a; t < b; ++t) off += (double)(h[t * 8 + e] - h[t * 8 + 1]);
             fprintf(stderr, "  %-40s %+8.0f cycles after 'mma: accumulator free' of the same tile\n", nm[e], off / (b - a));
