@@ -131,3 +131,23 @@ def test_saturated_fm_scores_overflow_and_fall_back_to_the_exact_path(dev):
     assert int(over.sum()) == 4
     top = model.predict(2, top_k=10)
     assert top.tolist() == list(range(10))  # every score is 1.0: lowest ids first
+
+
+def test_topk_long_item_stream_many_user_tiles(dev):
+    """A catalogue long enough (> 768 tiles of 192 items) for the producers' lock-step window to engage, more user
+    tiles than one wave of CTAs shares an item range with, a ragged last tile; checked for a sample of users."""
+    from torchrecsys_b200 import _lib
+    U, I, D, k = 40000, 400_003, 32, 20
+    net = _make("linear", U, I, D, 0, dev, scale=0.3, seed=11)
+    users = torch.arange(0, U, 2, device=dev)  # 20000 users = 157 user tiles: more CTAs than SMs
+    idx, score, over = _lib.predict_topk(net.abi_model(), users, k)
+    torch.cuda.synchronize()
+    assert int(over.sum()) == 0
+    pick = torch.tensor([0, 1, 127, 128, 9999, 19871, 19999], device=dev)
+    want_idx, want_score = _exact(net, users[pick], I, None, k, dev)
+    assert torch.equal(idx[pick], want_idx)
+    assert torch.equal(score[pick], want_score)
+    # every row is a descending list of distinct valid items
+    assert bool((score[:, :-1] >= score[:, 1:]).all())
+    assert int(idx.min()) >= 0 and int(idx.max()) < I
+    assert bool((torch.sort(idx, dim=1).values[:, 1:] != torch.sort(idx, dim=1).values[:, :-1]).all())
