@@ -728,6 +728,12 @@ extern "C" int trs_predict_topk(const trs_model* model, const int64_t* users, in
             for (int t = a; t < b; ++t) off += (double)(h[t * 8 + e] - h[t * 8 + 1]);
             fprintf(stderr, "  %-40s %+8.0f cycles after 'mma: accumulator free' of the same tile\n", nm[e], off / (b - a));
         }
+        {
+            int last = 0;
+            while (last + 1 < 1024 && h[TK_TRACE_TILES * 8 + last + 1]) ++last;
+            fprintf(stderr, "  CTA 0 total: %.2f Mcycles over %d tiles\n",
+                    (double)(h[TK_TRACE_TILES * 8 + last] - h[TK_TRACE_TILES * 8]) / 1e6, last * 256);
+        }
         fprintf(stderr, "  cycles/tile per 256-tile window:");
         for (int w = 0; w + 1 < 1024 && h[TK_TRACE_TILES * 8 + w + 1]; ++w)
             fprintf(stderr, " %.0f", (double)(h[TK_TRACE_TILES * 8 + w + 1] - h[TK_TRACE_TILES * 8 + w]) / 256);
