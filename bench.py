@@ -173,13 +173,16 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 for bit, name in self.REASONS.items():
                     if r & bit:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            # NVML queries take a driver lock: dense at first (short timed regions still get a few samples), sparse
+            # afterwards (a long region with many launches is not disturbed)
+            time.sleep(0.002 if len(self.samples) < 6 else 0.01)
 
     def __enter__(self):
         if self.nv is not None:
@@ -195,7 +198,7 @@ class ClockSampler:
     def summary(self):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(s)}
+                "reasons": sorted(self.reasons), "samples": len(s), "sm_mhz_min": s[0] if s else None}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -492,6 +495,13 @@ def predict_bench(args, wl):
     users_h = torch.from_numpy(rng.integers(0, wl["n_users"], (K + W) * B)).pin_memory()
     users = users_h.to(dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    # clock ramp (not steps): keep the GPU busy ~0.3 s so the timed region does not start at idle clocks
+    scratch = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    t0 = time.time()
+    while time.time() - t0 < 0.3:
+        scratch.copy_(scratch.flip(0))
+        torch.cuda.synchronize()
+    del scratch
     for s in range(W):
         _lib.predict_topk(model, users[s * B:(s + 1) * B], k)
     torch.cuda.synchronize()
