@@ -101,3 +101,31 @@ def test_training_is_bit_identical_on_either_plan(opt_name):
     assert np.array_equal(out[0][0], out[1][0])
     for k in out[0][1]:
         assert np.array_equal(out[0][1][k], out[1][1][k]), k
+
+
+def test_long_epoch_is_cut_into_calls_of_whole_steps(monkeypatch):
+    """More steps than one plan launch indexes (gridDim.y): EpochRunner.run runs them as consecutive calls;
+    the result is bit-identical to a single call."""
+    from torchrecsys_b200 import engine
+    from torchrecsys_b200.collaborative.linear import Linear
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(9)
+    U, I, B, D = 500, 300, 2, 8
+    n = B * 1000 + 1
+    ids = {"user": rng.integers(0, U, n), "pos": rng.integers(0, I, n), "neg": rng.integers(0, I, n)}
+    t = {k: torch.from_numpy(v).to(dev) for k, v in ids.items()}
+    out = []
+    for cap in (1 << 20, 64):  # one call / 16 calls of 64 steps
+        monkeypatch.setattr(engine, "MAX_STEPS_PER_CALL", cap)
+        torch.manual_seed(4)
+        net = Linear(U, I, {}, D, use_metadata=False, use_cuda=True).to(dev)
+        opt = torch.optim.Adagrad(net.parameters(), lr=0.05)
+        loss = engine.EpochRunner(net, opt).run(t, B)
+        torch.cuda.synchronize()
+        assert loss.shape[0] == 1001
+        out.append((loss.cpu().numpy(), {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()},
+                    int(opt.state[next(iter(net.parameters()))]["step"])))
+    assert out[0][2] == out[1][2] == 1001
+    assert np.array_equal(out[0][0], out[1][0])
+    for k in out[0][1]:
+        assert np.array_equal(out[0][1][k], out[1][1][k]), k

@@ -131,7 +131,23 @@ def plan_launches(model, batch_size: int, n_steps: int) -> int:
                 + sum(passes(model.meta[f].n_rows) for f in range(n_meta))) + 2 + n_meta + dirty
 
 
-class EpochRunner:
+MAX_STEPS_PER_CALL = 32768  # the plan kernels index steps with gridDim.y (<= 65535)
+
+
+class _Chunked:
+    """An epoch with more steps than one plan launch can index is cut into consecutive runs of whole steps."""
+
+    def run(self, samples: Dict[str, torch.Tensor], batch_size: int) -> torch.Tensor:
+        n = samples["user"].shape[0]
+        per_call = MAX_STEPS_PER_CALL * batch_size
+        if n <= per_call:
+            return self._run(samples, batch_size)
+        losses = [self._run({k: v[lo:lo + per_call] for k, v in samples.items()}, batch_size)
+                  for lo in range(0, n, per_call)]
+        return torch.cat(losses)
+
+
+class EpochRunner(_Chunked):
     """Runs the steps of one epoch's (already ordered) samples through the fused kernel."""
 
     def __init__(self, net, optimizer):
@@ -152,7 +168,7 @@ class EpochRunner:
                 for nbytes in _lib.train_buffer_bytes(model, shape)]  # all three alive at once, like in run()
         del held  # back to torch's pool
 
-    def run(self, samples: Dict[str, torch.Tensor], batch_size: int) -> torch.Tensor:
+    def _run(self, samples: Dict[str, torch.Tensor], batch_size: int) -> torch.Tensor:
         """samples: device tensors user/pos/neg[/pos_meta/neg_meta] of one epoch.  Returns the
         per-step batch-mean hinge losses (device, [n_steps]); nothing here syncs with the host."""
         b = self.binding
@@ -177,7 +193,7 @@ class EpochRunner:
         return loss
 
 
-class MlpEpochRunner:
+class MlpEpochRunner(_Chunked):
     """EpochRunner for net_type='mlp': every step runs the tower forward/backward on the tcgen05 GEMMs,
     the dense SGD / Adagrad update and the row-wise embedding update inside libtrs_b200
     (trs_mlp_train_steps); the host only launches."""
@@ -196,7 +212,7 @@ class MlpEpochRunner:
             p.grad = g  # the last step's dense gradient stays visible to user code
         self.launches = 0
 
-    def run(self, samples: Dict[str, torch.Tensor], batch_size: int) -> torch.Tensor:
+    def _run(self, samples: Dict[str, torch.Tensor], batch_size: int) -> torch.Tensor:
         b = self.binding
         dev = samples["user"].device
         key = b.keys[0]
