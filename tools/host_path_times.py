@@ -1,3 +1,5 @@
+"""Stage-wise CUDA-event timing of one epoch through the public host path (negatives -> gather -> plan -> train kernel),
+first call at a new epoch shape vs repeated calls (run on the GPU box: PYTHONPATH=. python tools/host_path_times.py)."""
 import time, torch, numpy as np
 from torchrecsys_b200 import _lib
 from torchrecsys_b200.collaborative.fm import FM
