@@ -126,7 +126,8 @@ int trs_validate_ids(const int64_t* ids, int64_t n, int64_t n_rows, int32_t* bad
 /* ---- a7 (K5): the sort half of coalesce(), for a whole epoch at once ---------------------- */
 /* For every step and every id space, a stable sort of that step's lookups by row id (what
  * grad.coalesce() does per step, torch: optim/_functional.py:44).  `plan` receives the sorted
- * (row, lookup) pairs; `tmp` is scratch of trs_plan_tmp_bytes(). */
+ * (row, lookup) pairs; `tmp` is scratch of trs_plan_tmp_bytes().  One call takes at most 65535 steps
+ * (TRS_ERR_ARG beyond): a longer epoch is passed as consecutive runs of whole steps, as the host mirror does. */
 size_t trs_plan_bytes(const trs_model* model, const trs_epoch* epoch);
 size_t trs_plan_tmp_bytes(const trs_model* model, const trs_epoch* epoch);
 int trs_plan_build(const trs_model* model, const trs_epoch* epoch, void* plan, size_t plan_bytes,

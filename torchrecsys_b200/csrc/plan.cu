@@ -602,6 +602,8 @@ extern "C" int trs_plan_build(const trs_model* model, const trs_epoch* ep, void*
     TRS_REQUIRE(model->user.n_rows > 0 && model->user.n_rows <= 0xFFFFFFFFll &&
                 model->item.n_rows > 0 && model->item.n_rows <= 0xFFFFFFFFll, "n_rows out of range");
     if (ep->n_samples == 0) return TRS_OK;
+    TRS_REQUIRE(n_steps_of(ep) <= 65535, "plan_build: %lld steps in one call (limit 65535): pass the epoch in runs of whole steps",
+                (long long)n_steps_of(ep));
     const PlanLayout L = plan_layout(ep->n_samples, ep->batch, model->n_meta);
     if (plan_bytes < L.total || tmp_bytes < trs_plan_tmp_bytes(model, ep)) {
         set_error("plan workspace too small: plan %zu < %zu or tmp %zu < %zu", plan_bytes, L.total,
@@ -628,7 +630,7 @@ extern "C" int trs_plan_build(const trs_model* model, const trs_epoch* ep, void*
     };
     // TRS_PLAN_TILED=1 (tests): take the tiled multi-launch path at every batch size
     const char* tiled_env = getenv("TRS_PLAN_TILED");
-    const bool fused = 2ll * ep->batch <= FS_MAX && steps <= 65535 && !(tiled_env && atoi(tiled_env));
+    const bool fused = 2ll * ep->batch <= FS_MAX && !(tiled_env && atoi(tiled_env));
     if (fused) {
         FusedArgs A = {};
         auto space_of = [&](const int64_t* a, const int64_t* b, int stride, int off, int mult, int64_t n_rows,
