@@ -66,6 +66,8 @@ def parse_args():
     ap.add_argument("--workload", default="c2_fm", choices=sorted(WORKLOADS))
     ap.add_argument("--users", type=int, default=0, help="override the workload's user count (memory-bound hosts)")
     ap.add_argument("--batch", type=int, default=0, help="override the workload's batch size")
+    ap.add_argument("--dim", type=int, default=0, help="override the workload's n_factors")
+    ap.add_argument("--zipf", type=float, default=0.0, help="draw training ids from Zipf(A), A > 1, instead of uniformly")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -75,8 +77,14 @@ def parse_args():
 # synthetic data: uniform ids, rng seed 1234, category(item) = item mod n_cat
 # ------------------------------------------------------------------------------------------------
 def synth_ids(wl, n, seed=1234):
+    """Uniform i.i.d. ids, or with --zipf A: rank-frequency Zipf(A) ids (hot rows, many duplicates)."""
     import numpy as np
     rng = np.random.default_rng(seed)
+    a = wl.get("zipf", 0.0)
+    if a > 1.0:
+        user = ((rng.zipf(a, n) - 1) % wl["n_users"]).astype(np.int64)
+        pos = ((rng.zipf(a, n) - 1) % wl["n_items"]).astype(np.int64)
+        return user, pos
     user = rng.integers(0, wl["n_users"], n, dtype=np.int64)
     pos = rng.integers(0, wl["n_items"], n, dtype=np.int64)
     return user, pos
@@ -652,6 +660,12 @@ def main():
         wl["batch"] = args.batch
     if args.users:
         wl["n_users"] = args.users
+    if args.dim:
+        wl["dim"] = args.dim
+        wl["desc"] += f" [n_factors overridden: {args.dim}]"
+    if args.zipf:
+        wl["zipf"] = args.zipf
+        wl["desc"] += f" [ids drawn from Zipf({args.zipf})]"
     rank = int(os.environ.get("RANK", "0"))
     if wl.get("predict"):
         if rank != 0 and args.impl == "reference":

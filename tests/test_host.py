@@ -166,3 +166,25 @@ def test_canonical_meta_accepts_reference_layouts():
     assert canonical_meta(torch.stack([bag, bag + 1], 1), 2).tolist() == [[3, 4], [4, 5]]  # (B, F, L)
     assert canonical_meta(torch.tensor([[1, 2], [3, 4]]), 2).tolist() == [[1, 2], [3, 4]]   # canonical
     assert canonical_meta(None, 0) is None
+
+
+def test_precision_recall_at_k_matches_the_reference_loop():
+    """helper/evaluate.py:53-76 restated as the per-user set loop it is, against the tensor version."""
+    import numpy as np
+    import torch
+    from torchrecsys_b200.evaluate.metrics import Metrics
+    rng = np.random.default_rng(3)
+    n_users, n_items, k = 40, 60, 7
+    tu, ti = rng.integers(0, n_users - 5, 300), rng.integers(0, n_items, 300)  # the last 5 users have no truth
+    scored = rng.permutation(n_users)[:25]
+    rec = np.stack([rng.permutation(n_items)[:k] for _ in scored])
+    rec[3, -2:] = -1  # padded row
+    want_p, want_r = [], []
+    for row, u in enumerate(scored):
+        truth = set(ti[tu == u].tolist())
+        if truth:
+            n = len(truth & set(rec[row].tolist()))
+            want_p.append(n / k)
+            want_r.append(n / len(truth))
+    p, r = Metrics().precision_recall_at_k(torch.from_numpy(scored), torch.from_numpy(rec), tu, ti)
+    assert abs(p - np.mean(want_p)) < 1e-12 and abs(r - np.mean(want_r)) < 1e-12

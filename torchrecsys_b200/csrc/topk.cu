@@ -4,7 +4,9 @@
 //
 // Why two phases: the reference ranks fp32 scores; tensor cores multiply bf16.  Phase 1 therefore only
 // has to produce, per user, a SUPERSET of the exact top-k:
-//   |s_bf16(u,i) - s_exact(u,i)| <= eps_u := 2^-7 (1+2^-9) * |[u,1]| * max_i |[w_i,c_i]|   (Cauchy-Schwarz)
+//   |s_bf16(u,i) - s_exact(u,i)| <= eps_u := 2^-7 (1+2^-9) * |u| * max_i |w_i| + 2^-8 * max_i |c_i|
+//   (bf16 unit roundoff 2^-8 on both factors of every product u_d w_id, Cauchy-Schwarz over d; the constant 1
+//   that multiplies c_i is exact, so the extra column only contributes the rounding of c_i itself)
 //   so every exact top-k item has s_bf16 >= tau_k - 2 eps_u, tau_k = the k-th best bf16 score seen.
 // Phase 2 recomputes the candidates' scores with the same fp32 code path as trs_scores and ranks them by
 // (score descending, item id ascending) == torch.sort(stable=True, descending=True) on the reference's
@@ -47,9 +49,9 @@ struct TopkDev {
     const bf16* Ub;       // [user_tiles * TK_BM, Kp] bf16([u, 1, 0..])
     int n_item_tiles, tiles_per_split, splits;
     int k, fm;
-    const float* unorm;   // [n_query] |[u,1]|
+    const float* unorm;   // [n_query] |u|
     const float* ulin;    // [n_query] lin_user (FM) or 0
-    const float* vmax2;   // [1] max_i |[w_i,c_i]|^2
+    const float* vmax2;   // [2] max_i |w_i|^2, max_i |c_i|
     float* cand_s;        // [n_query, splits, TK_CAP]
     int* cand_i;
     int* cand_cnt;        // [n_query, splits]
@@ -272,8 +274,9 @@ topk_score_kernel(const __grid_constant__ CUtensorMap tmap_v,
         const size_t lst = ((size_t)(valid ? row : 0) * g.splits + split) * TK_CAP;
         float* cs = g.cand_s + lst;
         int* ci = g.cand_i + lst;
-        const float vmax = sqrtf(__ldg(g.vmax2));
-        const float margin2 = valid ? 0.015625f * 1.004f * __ldg(g.unorm + row) * vmax : 0.f;
+        const float wmax = sqrtf(__ldg(g.vmax2)), cmax = __ldg(g.vmax2 + 1);
+        // 2 eps_u, with 0.4 % of slack for the fp32 accumulation and the fp32 evaluation of c_i
+        const float margin2 = valid ? 1.004f * (0.015625f * __ldg(g.unorm + row) * wmax + 0.0078125f * cmax) : 0.f;
         const float ulin = valid ? __ldg(g.ulin + row) : 0.f;
         int cnt = 0, joined = 0;
         float thr = -INFINITY;
@@ -419,7 +422,7 @@ topk_prep_items_kernel(const __grid_constant__ trs_model m, const int64_t* __res
     const int lane = threadIdx.x & 31;
     const int D = m.dim, F = m.n_meta;
     constexpr int W = VEC ? 4 : 1;
-    float wmax = 0.f;
+    float wmax = 0.f, cmax = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < n_items; i += (int64_t)gridDim.x * 8) {
         float c = m.item.lin ? m.item.lin[i] : 0.f;
         float half = 0.f, n2 = 0.f;
@@ -474,9 +477,13 @@ topk_prep_items_kernel(const __grid_constant__ trs_model m, const int64_t* __res
         }
         // the extra K column and the zero padding up to Kp
         for (int d = D + lane; d < Kp; d += 32) out[d] = __float2bfloat16_rn(d == D ? c : 0.f);
-        wmax = fmaxf(wmax, n2 + c * c);
+        wmax = fmaxf(wmax, n2);
+        cmax = fmaxf(cmax, fabsf(c));
     }
-    if (lane == 0) atomicMax(vmax2_bits, __float_as_uint(wmax));  // non-negative floats order like their bits
+    if (lane == 0) {  // non-negative floats order like their bits
+        atomicMax(vmax2_bits, __float_as_uint(wmax));
+        atomicMax(vmax2_bits + 1, __float_as_uint(cmax));
+    }
 }
 
 // one warp per query user: Ub[q] = bf16([u, 1, 0...]), |[u,1]|, lin_user
@@ -491,7 +498,7 @@ topk_prep_users_kernel(const __grid_constant__ trs_model m, const int64_t* __res
     float n2 = 0.f;
     for (int d = lane; d < Kp; d += 32) {
         float v = d < D ? m.user.emb[(size_t)u * D + d] : (d == D ? 1.0f : 0.f);
-        n2 = fmaf(v, v, n2);
+        if (d < D) n2 = fmaf(v, v, n2);
         Ub[(size_t)q * Kp + d] = __float2bfloat16_rn(v);
     }
     n2 = warp_sum(n2);
