@@ -188,3 +188,37 @@ def test_precision_recall_at_k_matches_the_reference_loop():
             want_r.append(n / len(truth))
     p, r = Metrics().precision_recall_at_k(torch.from_numpy(scored), torch.from_numpy(rec), tu, ti)
     assert abs(p - np.mean(want_p)) < 1e-12 and abs(r - np.mean(want_r)) < 1e-12
+
+
+def test_long_epochs_are_cut_into_runs_of_whole_steps(monkeypatch):
+    """engine._Chunked.run: consecutive slices of MAX_STEPS_PER_CALL * batch samples, losses concatenated."""
+    import torch
+    from torchrecsys_b200 import engine
+
+    class Fake(engine._Chunked):
+        def __init__(self):
+            self.calls = []
+
+        def _run(self, samples, batch_size):
+            n = samples["user"].shape[0]
+            self.calls.append((int(samples["user"][0]), n, tuple(samples["meta"].shape)))
+            return torch.full((-(-n // batch_size),), float(len(self.calls)))
+
+    monkeypatch.setattr(engine, "MAX_STEPS_PER_CALL", 4)
+    n, B = 4 * 3 * 2 + 5, 3  # two full runs of 4 steps and a rest of 5 samples (2 steps)
+    smp = {"user": torch.arange(n), "meta": torch.arange(2 * n).view(n, 2)}
+    f = Fake()
+    loss = f.run(smp, B)
+    assert f.calls == [(0, 12, (12, 2)), (12, 12, (12, 2)), (24, 5, (5, 2))]
+    assert loss.tolist() == [1.0] * 4 + [2.0] * 4 + [3.0] * 2
+    g = Fake()
+    g.run({k: v[:12] for k, v in smp.items()}, B)
+    assert len(g.calls) == 1
+
+
+def test_plan_launch_count_follows_the_batch_size():
+    from types import SimpleNamespace as NS
+    from torchrecsys_b200 import engine, _lib
+    m = NS(n_meta=1, net=_lib.NET_FM, user=NS(n_rows=1_000_000), item=NS(n_rows=200_000), meta=[NS(n_rows=100)])
+    assert engine.plan_launches(m, 8192, 200) == 1            # one CTA per (step, id space)
+    assert engine.plan_launches(m, 16384, 200) == 2 * (3 + 3 + 1) + 2 + 1 + 2  # tiled sort + items + flags
