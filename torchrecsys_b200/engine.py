@@ -162,6 +162,7 @@ class EpochRunner(_Chunked):
         workspace are allocated once and returned to torch's caching allocator, so that no epoch -- not even the
         first -- pays a cudaMalloc between its launches."""
         dev = self.params[0].device
+        n_samples = min(n_samples, MAX_STEPS_PER_CALL * batch_size)  # longer epochs run in calls of this size
         model = self.net.abi_model(self.optimizer.state, self.binding.keys)
         shape = _lib.Epoch(None, None, None, None, None, n_samples, batch_size, 0)  # the size queries read no ids
         held = [torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=dev)

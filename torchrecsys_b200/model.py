@@ -162,6 +162,8 @@ class TorchRecSys(torch.nn.Module):
         # (dataset.py:359-373); consuming the CPU generator the same way keeps seeded runs comparable
         if n:
             torch.randperm(n)
+            if hasattr(runner, "reserve"):
+                runner.reserve(n, batch_size)  # plan / workspace blocks of an epoch of this shape, once
         for epoch in range(epochs):
             self.net = self.net.train()
 
