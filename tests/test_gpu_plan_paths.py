@@ -1,6 +1,8 @@
 """The two plan builders -- one CTA per (step, id space) in shared memory (batches up to 8192) and the tiled
 multi-launch radix sort (any batch) -- must agree: identical sorted (row, lookup) pairs, identical singleton
-flags and work-item sets, and bit-identical parameters after training on either plan (``-m gpu``)."""
+flags and work-item sets, and bit-identical parameters after training on either plan (``-m gpu``).  The plan is
+integer work: it is also compared, entry by entry, with a numpy restatement (stable argsort per step and id space --
+the order coalesce() sums duplicates in, torch: optim/_functional.py:44 --, run lengths, flag bytes)."""
 import os
 
 import numpy as np
@@ -60,6 +62,41 @@ def test_fused_plan_equals_tiled_plan(B, n, F, U, I):
     for name, o in spans.items():
         nb = 4 * n * (1 if name.startswith("user") else 2)
         assert np.array_equal(a[o:o + nb], b[o:o + nb]), name
+    # ... and against a numpy restatement: stable argsort per step and id space, segment lengths, flags
+    lookups_of = {"user": lambda lo, hi: ids["user"][lo:hi],
+                  "item": lambda lo, hi: np.concatenate([ids["pos"][lo:hi], ids["neg"][lo:hi]])}
+    for f in range(F):
+        lookups_of[f"meta{f}"] = (lambda lo, hi, f=f: np.concatenate([ids["pos_meta"][lo:hi, f], ids["neg_meta"][lo:hi, f]]))
+    want_single = {"user": np.zeros(n, np.uint8), "item": np.zeros(2 * n, np.uint8)}
+    want_items, want_long = [set() for _ in range(steps)], [set() for _ in range(steps)]
+    for sp_i, (name, mult) in enumerate([("user", 1), ("item", 2)] + [(f"meta{f}", 2) for f in range(F)]):
+        key_name = {"user": "user_key", "item": "item_key"}.get(name, name.replace("meta", "meta_key"))
+        perm_name = key_name.replace("key", "perm")
+        got_k = a[spans[key_name]:spans[key_name] + 4 * mult * n].view(np.uint32)
+        got_p = a[spans[perm_name]:spans[perm_name] + 4 * mult * n].view(np.uint32)
+        prev_rows = None
+        for st in range(steps):
+            lo, hi = st * B, min((st + 1) * B, n)
+            look = lookups_of[name](lo, hi).astype(np.int64)
+            order = np.argsort(look, kind="stable")
+            base = mult * st * B
+            assert np.array_equal(got_k[base:base + len(look)], look[order].astype(np.uint32)), (name, st)
+            assert np.array_equal(got_p[base:base + len(look)], order.astype(np.uint32)), (name, st)
+            rows, first, cnt = np.unique(look[order], return_index=True, return_counts=True)
+            for r, k0, c in zip(rows.tolist(), first.tolist(), cnt.tolist()):
+                if c > 8:
+                    want_long[st].add((sp_i, k0, c, r))
+                elif c > 1 or name not in want_single:
+                    want_items[st].add((sp_i | (c << 8), k0, r, int(order[k0])))
+            if name in want_single:
+                flags = np.zeros(len(look), np.uint8)
+                flags[order[first[cnt == 1]]] |= 1
+                if prev_rows is not None:
+                    flags[np.isin(look, prev_rows)] |= 2
+                want_single[name][base:base + len(look)] = flags
+            prev_rows = rows
+    assert np.array_equal(a[single_user:single_user + n], want_single["user"])
+    assert np.array_equal(a[single_item:single_item + 2 * n], want_single["item"])
     assert np.array_equal(a[item_cnt:single_user], b[item_cnt:single_user]), "segment counts"
     assert np.array_equal(a[single_user:single_user + n], b[single_user:single_user + n])
     assert np.array_equal(a[single_item:single_item + 2 * n], b[single_item:single_item + 2 * n])
@@ -72,6 +109,8 @@ def test_fused_plan_equals_tiled_plan(B, n, F, U, I):
             ka = np.lexsort(xa.T[::-1])
             kb = np.lexsort(xb.T[::-1])
             assert np.array_equal(xa[ka], xb[kb]), f"step {s}"
+            want = want_items[s] if o == items else want_long[s]
+            assert set(map(tuple, xa.tolist())) == want, f"step {s}: work items differ from the numpy restatement"
 
 
 @pytest.mark.parametrize("opt_name", ["adagrad", "sparse_adam"])
