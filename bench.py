@@ -1,32 +1,44 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the TorchRecSys hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2_fm|c1_linear|c4_linear]
+    python bench.py --gpus N --steps K --warmup W [--impl reference|torch_cuda] [--workload NAME]
 
-A "step" is one training step of the named workload: forward x2 + hinge + backward + sparse
-optimizer update over one batch (reference model.py:274-284).  Default workload = BASELINE.json
-configs[1] ("C2"): FM + 1 metadata feature (100 categories), dynamic negatives, 1M users x 200k
-items, dim 64, batch 8192, SparseAdam, synthetic uniform ids.
+A "step" is one training step of the named workload: forward x2 + hinge + backward + sparse optimizer update
+over one batch (reference model.py:274-284).
 
-  value      whole-job samples/s over K steps, every input already resident in HBM, timed with CUDA
-             events; the timed region contains EVERYTHING a step needs: Philox negatives, the sort
-             plan (coalesce's sort), and the persistent fused kernel.
-  e2e        the same K steps with the ids starting in pinned HOST memory (H2D inside the timed
-             region) and the per-step losses read back to the host (D2H inside).
-  roofline   the fused train kernel alone: algorithmic HBM bytes (ids + each unique
-             touched row's param+state read once and written once) / its CUDA-event duration,
-             against the measured HBM peak of MEASURED_PEAKS.json.
-  cpu_baseline  the reference's CPU op stream (oracle/torch_port.py, kind "port": /root/reference
-             is not on the GPU box) on a bounded sample of the same workload on the host cores.
+Default workload ("c4") = BASELINE.json configs[3], the large-table config north_star scales: Linear 50M users x
+5M items, dim 128, SparseAdam, batch 16384 PER GPU (weak scaling: the global batch is 16384 * N).
+  N = 1   the whole tables (84.5 GB with optimizer state) on one GPU through the fused persistent kernel
+          (csrc/train.cu).
+  N > 1   (under torchrun, one rank per GPU) the tables are ROW-SHARDED: row r lives on rank r % N; every rank
+          maps its peers' shards (CUDA IPC) and one persistent kernel per rank reads item rows from / stores
+          gradient rows into the owners' HBM over NVLink (csrc/shard.cu).  NCCL carries the per-epoch id
+          all-gather and the loss all-reduce; nothing per step.
+The other BASELINE configs ride along in the same JSON line under "other_workloads" (N = 1: C2 FM, C3 MLP, C5
+predict, and the sharded kernel hosting a 1-rank group; N > 1: item-sharded C5 predict).  `--workload c2_fm`,
+`c3_mlp`, `c5_predict`, `c1_linear`, `c4_fused`, `c4_linear` select one of them as the headline instead.
 
---impl reference runs only that CPU arm and prints it as the main line.
-Multi-GPU (N>1, under torchrun): table rows are sharded by `row mod N`... see DESIGN.md (e);
-each rank trains its own sample shard, weak scaling.
+  value      whole-job samples/s, every input already resident in HBM, CUDA events, max over ranks.  The K-step
+             block is repeated `config.repeats` times inside the timed region so that it lasts >= ~100 ms; the
+             timed region contains EVERYTHING a step needs: (N > 1: the id all-gather,) Philox negatives, the
+             sort plan (coalesce's sort) and the persistent kernel.
+  e2e        the same blocks with the ids starting in pinned HOST memory (H2D inside the timed region) and the
+             per-step losses read back to the host (D2H inside).
+  roofline   the persistent kernel alone: algorithmic HBM bytes (ids + each unique touched row's
+             param+state read once and written once) / its CUDA-event duration, against the measured HBM peak of
+             MEASURED_PEAKS.json; N > 1 adds the NVLink figure (bytes that must cross / 770 GB/s per direction).
+  cpu_baseline  the reference's CPU op stream (oracle/torch_port.py, kind "port": /root/reference is not on the
+             GPU box) on a bounded sample of the same workload on the host cores (N = 1 only).
+
+--impl reference runs only that CPU arm and prints it as the main line.  --impl torch_cuda (secondary baseline,
+SURVEY.md §2.1) runs the same port with its tables on the GPU: the stock ATen CUDA kernels the reference's
+use_cuda=True path would launch.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -49,27 +61,34 @@ WORKLOADS = {
                        opt=None, lr=0.0, predict=True, desc="BASELINE configs[4]: batched predict top-100 against a "
                        "5M-item table (linear scorer, dim 128); a step = 18944 users (148 user tiles)"),
     "c4_fused": dict(net="linear", n_users=50_000_000, n_items=5_000_000, dim=128, n_cat=0, batch=16384,
-                     opt="sparse_adam", lr=1e-3, desc="BASELINE configs[3] tables (linear 50M x 5M, dim 128, batch 16384, "
-                     "SparseAdam) on ONE GPU through the fused persistent kernel (84.5 GB of tables + state)"),
+                     opt="sparse_adam", lr=1e-3,
+                     desc="BASELINE configs[3]: linear 50M x 5M, dim 128, batch 16384/GPU, SparseAdam"),
     "c4_linear": dict(net="linear", n_users=50_000_000, n_items=5_000_000, dim=128, n_cat=0, batch=16384,
                       opt="sparse_adam", lr=1e-3, sharded=True,
-                      desc="BASELINE configs[3]: linear 50M x 5M, dim 128, batch 16384/GPU, tables row-sharded"),
+                      desc="BASELINE configs[3]: linear 50M x 5M, dim 128, batch 16384/GPU, SparseAdam"),
 }
+C4_DESC = "BASELINE configs[3]: linear 50M x 5M, dim 128, batch 16384/GPU, SparseAdam"
+NVLINK_GBS = 770.0  # measured peer copy per direction on this pool (B200_PROFILING.md); 900 nominal
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2_fm", choices=sorted(WORKLOADS))
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_cuda"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + ["c4"])
     ap.add_argument("--users", type=int, default=0, help="override the workload's user count (memory-bound hosts)")
-    ap.add_argument("--batch", type=int, default=0, help="override the workload's batch size")
+    ap.add_argument("--items", type=int, default=0, help="override the workload's item count")
+    ap.add_argument("--batch", type=int, default=0, help="override the workload's batch size (per GPU)")
     ap.add_argument("--dim", type=int, default=0, help="override the workload's n_factors")
     ap.add_argument("--zipf", type=float, default=0.0, help="draw training ids from Zipf(A), A > 1, instead of uniformly")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the CPU baseline sample")
+    ap.add_argument("--min-ms", type=float, default=100.0, help="the K-step block is repeated until the timed region lasts this long")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the other_workloads sub-results")
+    ap.add_argument("--emulate-world", type=int, default=0,
+                    help="c4_linear on ONE GPU: host a group of this many ranks in one launch (structure check, no NVLink)")
     return ap.parse_args()
 
 
@@ -90,52 +109,61 @@ def synth_ids(wl, n, seed=1234):
     return user, pos
 
 
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the reference's op stream on the host cores
+# baseline arms: the reference's op stream on the host cores (or, --impl torch_cuda, on the GPU)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference(wl, steps, warmup, budget_s):
-    """Times oracle/torch_port.py (same ATen CPU ops as the reference's use_cuda=False path) on a
-    bounded sample: `steps` steps of the workload's batch size, thread count swept, best kept."""
+def port_reference(wl, steps, warmup, budget_s, device="cpu"):
+    """Times oracle/torch_port.py (the ATen ops of the reference's scorer + hinge + torch optimizer) on a bounded
+    sample: `steps` steps of the workload's batch size.  CPU: thread count swept, best kept."""
     import numpy as np
     import torch
     from oracle import cf_oracle as O
     from oracle import torch_port as TP
     B = wl["batch"]
     cap_note = ""
-    if wl["n_users"] > 5_000_000:  # host RAM: 50M x 128 fp32 + SparseAdam state would be 77 GB
+    if device == "cpu" and wl["n_users"] > 5_000_000:  # host RAM: 50M x 128 fp32 + SparseAdam state would be 77 GB
         wl = dict(wl, n_users=5_000_000)
         cap_note = " (user table cut to 5M rows on the host: 25.6 GB + optimizer state does not fit; row access stays random)"
     n = (steps + warmup) * B
     user, pos = synth_ids(wl, n)
     neg = O.philox_negatives(1234, 0, pos, wl["n_items"])
-    batch_of = lambda s: {"user": torch.from_numpy(user[s * B:(s + 1) * B]),
-                          "pos": torch.from_numpy(pos[s * B:(s + 1) * B]),
-                          "neg": torch.from_numpy(neg[s * B:(s + 1) * B])}
+    dev = torch.device(device)
+    ids = {k: torch.from_numpy(v).to(dev) for k, v in (("user", user), ("pos", pos), ("neg", neg))}
+    batch_of = lambda s: {k: v[s * B:(s + 1) * B] for k, v in ids.items()}
     metas = [wl["n_cat"]] if wl["n_cat"] else []
     ncores = len(os.sched_getaffinity(0))
-    best = None
+    threads = sorted({1, 2, 4, 8, 16, 32, ncores} & set(range(1, ncores + 1))) if device == "cpu" else [ncores]
+    torch.manual_seed(1234)
+    kw = dict(hidden=wl["hidden"], batch_norm=True) if wl["net"] == "mlp" else {}
+    net = TP.make_net(wl["net"], wl["n_users"], wl["n_items"], metas, wl["dim"], **kw).to(dev)
+    net.train()
+    opt = TP.make_optimizer(wl["opt"], net, wl["lr"])
+
+    def run(s):
+        b = batch_of(s)
+        if metas:
+            b["pos_meta"] = (b["pos"] % wl["n_cat"]).view(-1, 1)
+            b["neg_meta"] = (b["neg"] % wl["n_cat"]).view(-1, 1)
+        return TP.train_step(net, opt, b)
+
+    sync = torch.cuda.synchronize if device != "cpu" else (lambda: None)
+    best, tried = None, {}
     t_start = time.time()
-    threads = sorted({1, 2, 4, 8, 16, 32, ncores} & set(range(1, ncores + 1)))
-    tried = {}
     for nt in threads:
-        if time.time() - t_start > budget_s:
+        if time.time() - t_start > budget_s and best is not None:
             break
-        torch.set_num_threads(nt)
-        torch.manual_seed(1234)
-        kw = dict(hidden=wl["hidden"], batch_norm=True) if wl["net"] == "mlp" else {}
-        net = TP.make_net(wl["net"], wl["n_users"], wl["n_items"], metas, wl["dim"], **kw)
-        net.train()
-        opt = TP.make_optimizer(wl["opt"], net, wl["lr"])
-
-        def run(s):
-            b = batch_of(s)
-            if metas:
-                b["pos_meta"] = (b["pos"] % wl["n_cat"]).view(-1, 1)
-                b["neg_meta"] = (b["neg"] % wl["n_cat"]).view(-1, 1)
-            return TP.train_step(net, opt, b)
-
+        if device == "cpu":
+            torch.set_num_threads(nt)
         for s in range(warmup):
             run(s)
+        sync()
         t0 = time.perf_counter()
         done = 0
         for s in range(warmup, warmup + steps):
@@ -143,16 +171,18 @@ def cpu_reference(wl, steps, warmup, budget_s):
             done += 1
             if time.perf_counter() - t0 > budget_s / max(len(threads), 1) and done >= 2:
                 break
+        sync()
         dt = time.perf_counter() - t0
         tried[nt] = done * B / dt
         if best is None or tried[nt] > best[0]:
             best = (tried[nt], nt, done, dt)
-        del net, opt
     value, nt, done, dt = best
+    where = (f"torch {torch.__version__} CPU, threads swept { {k: round(v) for k, v in tried.items()} } on {ncores} "
+             "cores, best kept") if device == "cpu" else \
+        f"torch {torch.__version__} stock ATen CUDA kernels on {torch.cuda.get_device_name(0)} (per-step loss.item() as the reference)"
     return {"value": value, "unit": "samples/s", "cores": nt, "kind": "port",
             "sample": f"{done} steps of batch {B} ({done * B} samples) of the same workload after "
-                      f"{warmup} warm-up steps, torch {torch.__version__} CPU, threads swept "
-                      f"{ {k: round(v) for k, v in tried.items()} } on {ncores} cores, best kept" + cap_note,
+                      f"{warmup} warm-up steps, {where}" + cap_note,
             "ms_per_step": dt / done * 1e3, "steps": done}
 
 
@@ -181,7 +211,6 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 for bit, name in self.REASONS.items():
                     if r & bit:
@@ -209,8 +238,40 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(s), "sm_mhz_min": s[0] if s else None}
 
 
+def clock_ramp(dev, seconds=0.3):
+    """Not steps: keep the GPU busy so the timed region does not start at idle clocks."""
+    import torch
+    scratch = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    t0 = time.time()
+    while time.time() - t0 < seconds:
+        scratch.copy_(scratch.flip(0))
+        torch.cuda.synchronize()
+    del scratch
+
+
+def pick_repeats(probe_ms, min_ms, world, dev):
+    """How often the K-step block runs inside a timed region so that it lasts >= min_ms (same on every rank)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([probe_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return int(max(1, min(200, math.ceil(min_ms / max(float(t.item()), 1e-3)))))
+
+
+def traffic_of(workload, K):
+    """dram bytes of the dominant kernel per launch, from the committed ncu --set full capture (STATIC: it is not
+    measured by this run; profiles/traffic.json holds bytes per step, one launch = K steps)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return None, None
+    v = t.get(workload)
+    return (v * K if v else None), t.get("_source", "profiles/traffic.json")
+
+
 # ------------------------------------------------------------------------------------------------
-# GPU arm
+# single-GPU training through the fused persistent kernel (and N independent replicas of it)
 # ------------------------------------------------------------------------------------------------
 def algorithmic_bytes(wl, user, pos, neg, n_steps, B, S):
     """8 B per id consumed + per unique touched row (param + S state tensors) read once
@@ -230,23 +291,23 @@ def algorithmic_bytes(wl, user, pos, neg, n_steps, B, S):
     return total
 
 
-def gpu_bench(args, wl):
+def gpu_bench(args, wl, name):
     import torch
     import torch.distributed as dist
     from torchrecsys_b200 import _lib
     from torchrecsys_b200.collaborative.fm import FM
     from torchrecsys_b200.collaborative.linear import Linear
     from torchrecsys_b200.collaborative.mlp import MLP
-    from torchrecsys_b200.engine import EpochRunner, MlpEpochRunner
+    from torchrecsys_b200.engine import EpochRunner, MlpEpochRunner, advance_steps, step_scales
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
-    K, W, B = args.steps, max(args.warmup, 3), args.batch or wl["batch"]
+    K, W, B = args.steps, max(args.warmup, 3), wl["batch"]
     F = 1 if wl["n_cat"] else 0
 
     torch.manual_seed(1234 + rank)
@@ -256,8 +317,10 @@ def gpu_bench(args, wl):
                   hidden_layers=wl["hidden"], use_cuda=True).to(dev).train()
     else:
         cls = FM if wl["net"] == "fm" else Linear
-        net = cls(wl["n_users"], wl["n_items"], {"product_category": wl["n_cat"]} if F else {}, wl["dim"],
-                  use_metadata=bool(F), use_cuda=True).to(dev)
+        with torch.device(dev):  # the big tables are created on the device (50M x 128 does not visit the host)
+            net = cls(wl["n_users"], wl["n_items"], {"product_category": wl["n_cat"]} if F else {}, wl["dim"],
+                      use_metadata=bool(F), use_cuda=True)
+        net = net.to(dev)
     if wl["opt"] == "sparse_adam":
         opt = torch.optim.SparseAdam(list(net.parameters()), lr=wl["lr"])
         S = 2
@@ -284,51 +347,63 @@ def gpu_bench(args, wl):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     sync_all = (lambda: (torch.cuda.synchronize(), dist.barrier(), torch.cuda.synchronize())) if world > 1 \
         else torch.cuda.synchronize
+    clock_ramp(dev)
 
-    # clock ramp (not steps): keep the GPU busy ~0.3 s so the timed region does not start at idle clocks
-    scratch = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    t0 = time.time()
-    while time.time() - t0 < 0.3:
-        scratch.copy_(scratch.flip(0))
-        torch.cuda.synchronize()
-    del scratch
-
-    # W warm-up steps
+    # W warm-up steps, then the memory pool: an epoch of K steps needs other buffer sizes than the W warm-up steps
+    # did.  Reserve them now, so that the timed region measures the steps and not torch's first cudaMalloc of each
+    # size (in a real fit() every epoch has the same shape and reuses the blocks of the one before)
     step_block(user[:W * B], pos[:W * B], 0)
     sync_all()
-
-    # memory pool: an epoch of K steps needs other buffer sizes than the W warm-up steps did.  Reserve them now, so
-    # that the timed region measures the steps and not torch's first cudaMalloc of each size (in a real fit() every
-    # epoch has the same shape and reuses the blocks of the one before)
     if hasattr(runner, "reserve"):
         runner.reserve(K * B, B)
-    pool = [torch.empty(K * B, dtype=torch.int64, device=dev) for _ in range(1 + 2 * F)] + [torch.empty(K, device=dev)]
-    del pool
-    sync_all()
-
-    # ---- timed: K steps, inputs resident in HBM ----
     uK, pK = user[W * B:], pos[W * B:]
-    launches0 = runner.launches
-    e0, e1 = ev(), ev()
-    with ClockSampler(local) as clocks:
+    uK_h, pK_h = user_h[W * B:], pos_h[W * B:]
+    loss_host = torch.empty(K, dtype=torch.float32).pin_memory()
+    seen = [W * B]
+
+    def resident_block():
+        loss = step_block(uK, pK, seen[0])
+        seen[0] += K * B
+        return loss
+
+    def e2e_block():
+        u_d = uK_h.to(dev, non_blocking=True)
+        p_d = pK_h.to(dev, non_blocking=True)
+        loss = step_block(u_d, p_d, seen[0])
+        seen[0] += K * B
+        loss_host.copy_(loss, non_blocking=True)
+        return loss
+
+    def timed(block, R):
+        e0, e1 = ev(), ev()
         sync_all()
         e0.record()
-        loss = step_block(uK, pK, W * B)
+        for _ in range(R):
+            loss = block()
         e1.record()
         sync_all()
-    ms = e0.elapsed_time(e1)
-    launches = runner.launches - launches0 + 1  # + the Philox kernel
-    mean_loss = float(loss.mean().item())
+        return e0.elapsed_time(e1), loss
 
-    # ---- the fused kernel alone (roofline): same K steps again on the now-further-trained model ----
-    neg, neg_meta = _lib.philox_negatives(1234, W * B, pK, wl["n_items"], item_meta)
+    # both regions are warmed the same way: one untimed block each (allocator sizes), then R timed blocks
+    resident_block()
+    e2e_block()
+    probe_ms, _ = timed(resident_block, 1)
+    R = pick_repeats(probe_ms, args.min_ms, world, dev)
+    launches0 = runner.launches
+    with ClockSampler(local) as clocks:
+        ms, loss = timed(resident_block, R)
+    launches = (runner.launches - launches0) // R + 1  # per K-step block; + the Philox kernel
+    mean_loss = float(loss.mean().item())
+    e2e_ms, _ = timed(e2e_block, R)
+
+    # ---- the fused kernel alone (roofline): the same K steps once more ----
+    neg, neg_meta = _lib.philox_negatives(1234, seen[0], pK, wl["n_items"], item_meta)
     smp = {"user": uK, "pos": pK, "neg": neg}
     if F:
         smp["pos_meta"], smp["neg_meta"] = item_meta[pK], neg_meta
     b = runner.binding
     model = net.abi_model(opt.state, b.keys)
     epoch = _lib.make_epoch(smp["user"], smp["pos"], smp["neg"], smp.get("pos_meta"), smp.get("neg_meta"), B)
-    from torchrecsys_b200.engine import step_scales, advance_steps
     scales = torch.tensor(step_scales(b, K), dtype=torch.float64).float().to(dev)
     optim_c = _lib.Optim(b.kind, 0, b.beta1, b.beta2, b.eps, scales.data_ptr())
     p0, p1, k0, k1 = ev(), ev(), ev(), ev()
@@ -353,38 +428,19 @@ def gpu_bench(args, wl):
     kernel_ms, plan_ms = k0.elapsed_time(k1), p0.elapsed_time(p1)
     alg_bytes = algorithmic_bytes(wl, uK, pK, neg, K, B, S)
 
-    # ---- e2e: ids start in pinned host memory, losses end on the host ----
-    loss_host = torch.empty(K, dtype=torch.float32).pin_memory()
-    e2e_ms = None
-    for attempt in range(2):  # first pass untimed: it warms the allocator for this region's buffer sizes
-        x0, x1 = ev(), ev()
-        sync_all()
-        x0.record()
-        u_d = user_h[W * B:].to(dev, non_blocking=True)
-        p_d = pos_h[W * B:].to(dev, non_blocking=True)
-        loss3 = step_block(u_d, p_d, (W + K * (1 + attempt)) * B)
-        loss_host.copy_(loss3, non_blocking=True)
-        x1.record()
-        sync_all()
-        e2e_ms = x0.elapsed_time(x1)
-    assert loss_host.numel() == K
-
     times = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms, e2e_ms, kernel_ms = (float(x) for x in times.cpu())
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    peaks = load_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "kernel": "trs::train_kernel (one persistent launch, K steps)",
                 "kernel_ms_per_step": kernel_ms / K, "plan_ms_per_step": plan_ms / K,
                 "algorithmic_bytes_per_step": alg_bytes / K,
+                "whole_step_frac": alg_bytes / (ms / R * 1e-3) / 1e9 / peak,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650"}
     if is_mlp:
         # the tower's GEMMs bound this workload: 3 x 2 x MACs per row, 2 rows per sample
@@ -396,43 +452,41 @@ def gpu_bench(args, wl):
         tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         tach = flops_step * K / (kernel_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s", "frac": tach / tpeak,
-                    "kernel": "trs::gemm_tn_kernel (9 tcgen05 GEMMs per step) timed inside the whole fused step: "
+                    "kernel": "trs::gemm_tn_kernel (tcgen05 GEMMs) timed inside the whole fused step: "
                               "every kernel of trs_mlp_train_steps is in the denominator",
                     "kernel_ms_per_step": kernel_ms / K, "plan_ms_per_step": plan_ms / K,
                     "algorithmic_flops_per_step": flops_step,
                     "embedding_bytes_per_step": alg_bytes / K,
                     "peak_source": "measured sustained bf16 (MEASURED_PEAKS.json)" if peaks else "fallback 1400"}
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-    except Exception:
-        pass
+    traffic, traffic_src = traffic_of(name, K)
+    roofline["traffic"] = traffic
+    roofline["traffic_source"] = f"static: {traffic_src} (ncu capture of an earlier run, not measured here)" if traffic else None
     out = {
-        "metric": "train samples/sec (fwd+bwd+sparse update)", "value": world * K * B / (ms * 1e-3),
-        "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+        "metric": "train samples/sec (fwd+bwd+sparse update)", "value": world * R * K * B / (ms * 1e-3),
+        "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / (R * K),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if is_mlp else "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "name": args.workload, "batch_per_gpu": B, "global_batch": B * world,
-                   "optimizer": wl["opt"], "l2": "inputs larger than L2: tables+optimizer state "
+        "config": {"workload": wl["desc"], "name": name, "batch_per_gpu": B, "global_batch": B * world,
+                   "optimizer": wl["opt"], "repeats": R, "l2": "inputs larger than L2: tables+optimizer state "
                    f"{(wl['n_users'] + wl['n_items']) * (wl['dim'] + 1) * 4 * (1 + S) / 1e9:.2f} GB, rows hit at random",
-                   "timed_region": ("Philox negatives + sort plan + K fused MLP steps (one C call, ~40 kernels per step)"
+                   "timed_region": ("Philox negatives + sort plan + K fused MLP steps (one C call), x repeats"
                                     if is_mlp else
-                                    "Philox negatives + sort plan + persistent fused train kernel, K steps in one launch"),
-                   "parallelism": f"dp{world} (independent replicas)" if world > 1 else "single GPU",
+                                    "Philox negatives + sort plan + persistent fused train kernel (K steps in one "
+                                    "launch), x repeats"),
+                   "parallelism": (f"{world} INDEPENDENT REPLICAS of a single-GPU workload (no data-path collective: "
+                                   "not a scaling result)") if world > 1 else "single GPU",
                    "clock_ramp": "0.3 s of device copies before the warm-up steps",
                    "memory_pool": "buffer sizes of a K-step epoch reserved before the timed region (no cudaMalloc inside)",
                    "mean_loss": mean_loss},
-        "e2e": {"value": world * K * B / (e2e_ms * 1e-3), "unit": "samples/s",
+        "e2e": {"value": world * R * K * B / (e2e_ms * 1e-3), "unit": "samples/s",
                 "h2d_bytes_per_step": 16 * B, "d2h_bytes_per_step": 4,
                 "note": "user+positive ids from pinned host memory; metadata ids and negatives are derived on the device"},
         "gpu_launches": launches,
-        # traffic: dram bytes of the dominant kernel per launch, from the committed ncu --set full capture
-        # (profiles/traffic.json holds bytes per step; one launch = K steps)
-        "roofline": dict(roofline, traffic=(traffic * K if traffic else None)),
+        "roofline": roofline,
         "clocks": clocks.summary(),
     }
-    if world > 1:
-        dist.destroy_process_group()
+    del runner, opt, net, plan, ws
+    torch.cuda.empty_cache()
     return out, rank
 
 
@@ -459,65 +513,53 @@ def cpu_predict(wl, budget_s):
             "ms_per_step": dt / done * 1e3, "steps": done}
 
 
-def _traffic(workload):
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
-    except Exception:
-        return None
-
-
-def predict_bench(args, wl):
+def predict_bench(args, wl, name, K=None, W=None):
+    import numpy as np
     import torch
-    from torchrecsys_b200 import _lib
-    from torchrecsys_b200.collaborative.linear import Linear
     import torch.distributed as dist
+    from torchrecsys_b200 import _lib
     from torchrecsys_b200 import sharded as S
+    from torchrecsys_b200.collaborative.linear import Linear
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
-    K, W, B, k = args.steps, max(args.warmup, 3), args.batch or wl["batch"], wl["k"]
+    K = K or args.steps
+    W = W or max(args.warmup, 3)
+    B, k = wl["batch"], wl["k"]
     torch.manual_seed(1234)
     # N > 1: the item table is cut into contiguous blocks, one per rank; user rows are replicated
     lo_item, hi_item = S.item_block(wl["n_items"], rank, world)
-    net = Linear(wl["n_users"], hi_item - lo_item, {}, wl["dim"], use_metadata=False, use_cuda=True).to(dev).eval()
+    with torch.device(dev):
+        net = Linear(wl["n_users"], hi_item - lo_item, {}, wl["dim"], use_metadata=False, use_cuda=True)
+    net = net.to(dev).eval()
     with torch.no_grad():
         net.item_bias.weight.normal_(0, 0.01)
     model = net.abi_model()
     if world > 1:
-        single = _lib.predict_topk
-
         def local_topk(u, kk, offset):
-            idx, score, over = single(model, u, kk, item_offset=offset)
+            idx, score, over = _lib.predict_topk(model, u, kk, item_offset=offset)
             return idx, score
 
-        class _Sharded:  # same call shape as _lib.predict_topk
-            @staticmethod
-            def predict_topk(_model, u, kk):
-                idx, score = S.sharded_predict_topk(local_topk, u, kk, wl["n_items"])
-                return idx, score, torch.zeros(1, dtype=torch.int32, device=dev)
-        _lib = _Sharded
-    import numpy as np
+        def predict(u):
+            idx, score = S.sharded_predict_topk(local_topk, u, k, wl["n_items"])
+            return idx, score, torch.zeros(1, dtype=torch.int32, device=dev)
+    else:
+        predict = lambda u: _lib.predict_topk(model, u, k)
     rng = np.random.default_rng(1234)
     users_h = torch.from_numpy(rng.integers(0, wl["n_users"], (K + W) * B)).pin_memory()
     users = users_h.to(dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    # clock ramp (not steps): keep the GPU busy ~0.3 s so the timed region does not start at idle clocks
-    scratch = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    t0 = time.time()
-    while time.time() - t0 < 0.3:
-        scratch.copy_(scratch.flip(0))
-        torch.cuda.synchronize()
-    del scratch
+    clock_ramp(dev)
     for s in range(W):
-        _lib.predict_topk(model, users[s * B:(s + 1) * B], k)
+        predict(users[s * B:(s + 1) * B])
     torch.cuda.synchronize()
     e0, e1 = ev(), ev()
     with ClockSampler(dev.index) as clocks:
         e0.record()
         for s in range(W, W + K):
-            idx, score, over = _lib.predict_topk(model, users[s * B:(s + 1) * B], k)
+            idx, score, over = predict(users[s * B:(s + 1) * B])
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -527,29 +569,27 @@ def predict_bench(args, wl):
     x0.record()
     for s in range(W, W + K):
         u = users_h[s * B:(s + 1) * B].to(dev, non_blocking=True)
-        idx, score, over = _lib.predict_topk(model, u, k)
+        idx, score, over = predict(u)
         out_h.copy_(idx, non_blocking=True)
     x1.record()
     torch.cuda.synchronize()
     e2e_ms = x0.elapsed_time(x1)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    peaks = load_peaks()
     tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     flops = 2.0 * wl["n_items"] * wl["dim"] * B * K
-    tach = flops / (ms * 1e-3) / 1e12 / world   # per GPU
     if world > 1:
         t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_ms = (float(x) for x in t.cpu())
-        dist.destroy_process_group()
+    tach = flops / (ms * 1e-3) / 1e12 / world   # per GPU
+    traffic, traffic_src = traffic_of(name, 1)
+    del net
+    torch.cuda.empty_cache()
     return {
         "metric": "predict top-k users/sec", "value": K * B / (ms * 1e-3), "unit": "users/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": wl["desc"], "name": args.workload, "users_per_step": B, "top_k": k,
+        "config": {"workload": wl["desc"], "name": name, "users_per_step": B, "top_k": k,
                    "parallelism": (f"item table in {world} contiguous blocks, local top-k per rank, all-gather + "
                                    "k-way merge (the same users on every rank)") if world > 1 else "single GPU",
                    "l2": "inputs larger than L2: bf16 item operand 1.44 GB streamed per user wave",
@@ -559,7 +599,9 @@ def predict_bench(args, wl):
                 "d2h_bytes_per_step": 8 * B * k},
         "gpu_launches": 7 * K,
         "roofline": {"bound": "tensor", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s", "frac": tach / tpeak,
-                     "traffic": _traffic(args.workload), "kernel": "trs::topk_score_kernel, timed inside the whole predict call "
+                     "traffic": traffic,
+                     "traffic_source": f"static: {traffic_src} (not measured here)" if traffic else None,
+                     "kernel": "trs::topk_score_kernel, timed inside the whole predict call "
                      "(preparation and re-scoring are in the denominator)",
                      "algorithmic_flops_per_step": flops / K,
                      "peak_source": "measured sustained bf16 (MEASURED_PEAKS.json)" if peaks else "fallback 1400"},
@@ -570,146 +612,299 @@ def predict_bench(args, wl):
 # ------------------------------------------------------------------------------------------------
 # row-sharded large-table training (BASELINE configs[3]) -- torchrun, one rank per GPU
 # ------------------------------------------------------------------------------------------------
-def sharded_bench(args, wl):
+def shard_parity_check(dev, world, rank):
+    """Before anything is timed: a small problem through the SAME multi-rank path (IPC-mapped shards, NVLink loads
+    and stores, flag barriers) against the fused single-GPU kernel on the same ids and initial tables.  The fused
+    kernel is pinned to the reference by tests/ (golden vectors); this closes the loop for the sharded path on the
+    box the numbers come from."""
+    import numpy as np
+    import torch
+    from torchrecsys_b200.collaborative.linear import Linear
+    from torchrecsys_b200.engine import EpochRunner
+    from torchrecsys_b200.sharded import ShardedLinearTrainer
+    U, I, D, B, steps = 20011, 3001, 128, 2048, 4
+    rng = np.random.default_rng(77)
+    full = {"user.weight": rng.normal(0, .3, (U, D)).astype(np.float32),
+            "item.weight": rng.normal(0, .3, (I, D)).astype(np.float32),
+            "user_bias.weight": np.zeros((U, 1), np.float32),
+            "item_bias.weight": rng.normal(0, .1, (I, 1)).astype(np.float32)}
+    full = {k: torch.from_numpy(v) for k, v in full.items()}
+    ids = [torch.from_numpy(rng.integers(0, m, B * steps)).to(dev) for m in (U, I, I)]
+    tr = ShardedLinearTrainer(U, I, D, global_batch=B, optimizer="sparse_adam", lr=0.01, device=dev)
+    tr.load_state_dict(full)
+    loss_s = tr.train_epoch(*ids, B)
+    sd = tr.state_dict()
+    out = {"ok": True}
+    if rank == 0:
+        net = Linear(U, I, {}, D, use_metadata=False, use_cuda=True)
+        net.load_state_dict(full)
+        net = net.to(dev)
+        opt = torch.optim.SparseAdam(list(net.parameters()), lr=0.01)
+        loss_f = EpochRunner(net, opt).run({"user": ids[0], "pos": ids[1], "neg": ids[2]}, B)
+        dl = float((loss_s - loss_f).abs().max())
+        dw = max(float((sd[k] - v).abs().max()) for k, v in net.state_dict().items())
+        out = {"ok": bool(dl < 1e-5 and dw < 2e-4), "max_abs_loss_diff": dl, "max_abs_param_diff": dw,
+               "what": f"{steps} SparseAdam steps of a {U}x{I} dim-{D} Linear, batch {B}, on {world} ranks over "
+                       "IPC-mapped shards vs the fused single-GPU kernel (same ids, same initial tables)"}
+        del net, opt
+    tr.close()
+    del tr
+    torch.cuda.empty_cache()
+    return out
+
+
+def sharded_bench(args, wl, name):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from torchrecsys_b200 import sharded as S
+    from torchrecsys_b200 import _lib
+    from torchrecsys_b200.sharded import ShardedLinearTrainer
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if not dist.is_initialized():
-        if world == 1:
-            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            os.environ.setdefault("MASTER_PORT", "29533")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    K, W, B = args.steps, max(args.warmup, 3), args.batch or wl["batch"]
-    tr = S.ShardedLinearTrainer(wl["n_users"], wl["n_items"], wl["dim"], optimizer=wl["opt"], lr=wl["lr"], device=dev)
-    rng = np.random.default_rng(1234 + rank)
-    ids_h = [torch.from_numpy(rng.integers(0, n, (K + W) * B)).pin_memory()
-             for n in (wl["n_users"], wl["n_items"], wl["n_items"])]
-    ids = [t.to(dev) for t in ids_h]
-    step = lambda src, s: tr.train_step(*(t[s * B:(s + 1) * B] for t in src))
+    emu = args.emulate_world if world == 1 else 0
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    G = emu or world                       # ranks of the group
+    K, W, B = args.steps, max(args.warmup, 3), wl["batch"]
+    Bg = B * G
+    D = wl["dim"]
+    parity = shard_parity_check(dev, world, rank) if world > 1 else None
+    tr = ShardedLinearTrainer(wl["n_users"], wl["n_items"], D, global_batch=Bg, optimizer=wl["opt"], lr=wl["lr"],
+                              device=dev, emulate_world=emu or (1 if world == 1 else None))
+    # every rank's loader output: (K + W) steps of its own B samples (in emulation this process holds all G of them)
+    mine = list(range(G)) if world == 1 else [rank]
+    ids_h = {q: [torch.from_numpy(a).pin_memory() for a in synth_ids(wl, (K + W) * B, seed=1234 + q)] for q in mine}
+    ids_d = {q: [t.to(dev) for t in v] for q, v in ids_h.items()}
+
+    def global_epoch(src, lo_step, n_steps):
+        """All ranks' samples of steps [lo_step, lo_step + n_steps) in loader order: step-major, rank-major inside a
+        step.  One all-gather per id column and epoch (NCCL) -- the only collective besides the loss all-reduce."""
+        cols = []
+        for c in range(2):
+            if world > 1:
+                part = src[rank][c][lo_step * B:(lo_step + n_steps) * B]
+                if not part.is_cuda:
+                    part = part.to(dev, non_blocking=True)
+                allr = torch.empty(world * n_steps * B, dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(allr, part.contiguous())
+            else:
+                allr = torch.cat([src[q][c][lo_step * B:(lo_step + n_steps) * B].to(dev, non_blocking=True) for q in mine])
+            cols.append(allr.view(G, n_steps, B).permute(1, 0, 2).reshape(-1))
+        return cols
+
+    seen = [0]
+
+    def block(src, lo_step, n_steps, timing=False):
+        gu, gp = global_epoch(src, lo_step, n_steps)
+        neg, _ = _lib.philox_negatives(1234, seen[0], gp, wl["n_items"])
+        seen[0] += n_steps * Bg
+        return tr.train_epoch(gu, gp, neg, Bg, check=False, timing=timing), (gu, gp, neg)
+
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    sync_all = lambda: (torch.cuda.synchronize(), dist.barrier(), torch.cuda.synchronize())
-    for s in range(W):
-        step(ids, s)
-    e0, e1 = ev(), ev()
-    hs = torch.zeros(1, device=dev)
-    with ClockSampler(local) as clocks:
+    sync_all = (lambda: (torch.cuda.synchronize(), dist.barrier(), torch.cuda.synchronize())) if world > 1 \
+        else torch.cuda.synchronize
+    clock_ramp(dev)
+    block(ids_d, 0, W)
+    sync_all()
+    tr.check_status()
+    loss_host = torch.empty(K, dtype=torch.float32).pin_memory()
+
+    def resident_block():
+        return block(ids_d, W, K)[0]
+
+    def e2e_block():
+        loss = block(ids_h, W, K)[0]
+        loss_host.copy_(loss, non_blocking=True)
+        return loss
+
+    def timed(fn, R):
+        e0, e1 = ev(), ev()
         sync_all()
         e0.record()
-        for s in range(W, W + K):
-            hs += step(ids, s)
+        for _ in range(R):
+            loss = fn()
         e1.record()
         sync_all()
-    ms = e0.elapsed_time(e1)
-    x0, x1 = ev(), ev()
-    hs2 = torch.zeros(1, device=dev)
+        return e0.elapsed_time(e1), loss
+
+    resident_block()
+    e2e_block()
+    probe_ms, _ = timed(resident_block, 1)
+    R = pick_repeats(probe_ms, args.min_ms, world, dev)
+    launches0 = tr.launches
+    with ClockSampler(local) as clocks:
+        ms, loss = timed(resident_block, R)
+    launches = (tr.launches - launches0) // R + 1
+    tr.check_status()
+    mean_loss = float(loss.mean().item())
+    e2e_ms, _ = timed(e2e_block, R)
+    # the persistent kernel (and the plan) alone
     sync_all()
-    x0.record()
-    for s in range(W, W + K):
-        hs2 += step([t[s * B:(s + 1) * B].to(dev, non_blocking=True) for t in ids_h], 0)
-    loss_h = hs2.cpu()
-    x1.record()
+    _, (gu, gp, neg) = block(ids_d, W, K, timing=True)
     sync_all()
-    e2e_ms = x0.elapsed_time(x1)
-    times = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
-    dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dist.all_reduce(hs)
-    ms, e2e_ms = (float(x) for x in times.cpu())
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
+    tr.check_status()
+    p0, p1, k0, k1 = tr.events
+    kernel_ms, plan_ms = k0.elapsed_time(k1), p0.elapsed_time(p1)
+    times = torch.tensor([ms, e2e_ms, kernel_ms, plan_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, kernel_ms, plan_ms = (float(x) for x in times.cpu())
+
     S_ = {"sgd": 0, "adagrad": 1, "sparse_adam": 2}[wl["opt"]]
-    # no-duplicate bound (uniform ids over 50M / 5M rows): 3 rows of (dim+1) floats, param + S states, read + write
-    alg = K * B * (24 + 3 * (wl["dim"] + 1) * 4 * (2 + 2 * S_))
-    ach = alg / (ms * 1e-3) / 1e9
-    nvl = K * B * 3 * (8 + 2 * (wl["dim"] + 1) * 4) * (world - 1) / world  # ids out, rows back, gradient rows out
+    alg = algorithmic_bytes(wl, gu, gp, neg, K, Bg, S_)        # of the GLOBAL batch; every rank owns 1/G of the rows
+    # bytes that must cross NVLink per rank and direction: item rows (+ bias) whose owner is not the sample's rank,
+    # read in phase A and their gradient rows (+ bias gradient) stored back; a rank serves as much as it asks for
+    remote = int(((gp % G) != (gu % G)).sum() + ((neg % G) != (gu % G)).sum())
+    nvl_dir = 2.0 * remote * (4 * D + 4) / G
+    peaks = load_peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = alg / G / (kernel_ms * 1e-3) / 1e9
+    nvl_ach = nvl_dir / (kernel_ms * 1e-3) / 1e9
+    t_hbm, t_nvl = alg / G / (peak * 1e9), nvl_dir / (NVLINK_GBS * 1e9)
     out = {
-        "metric": "train samples/sec (fwd+bwd+sparse update)", "value": world * K * B / (ms * 1e-3), "unit": "samples/s",
-        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "name": args.workload, "batch_per_gpu": B, "global_batch": B * world,
-                   "optimizer": wl["opt"], "parallelism": f"tables row-sharded over {world} ranks (row % G), "
-                   "all_to_all of ids / rows / gradient rows per step, owner-side coalesce + update",
-                   "l2": f"inputs larger than L2: {(wl['n_users'] + wl['n_items']) * (wl['dim'] + 1) * 4 * (1 + S_) / world / 1e9:.1f} "
+        "metric": "train samples/sec (fwd+bwd+sparse update)", "value": R * K * Bg / (ms * 1e-3), "unit": "samples/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / (R * K), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "name": name, "batch_per_gpu": B, "global_batch": Bg, "optimizer": wl["opt"],
+                   "repeats": R,
+                   "parallelism": (f"user / item tables ROW-SHARDED over {G} ranks (row % {G}); samples run on their "
+                                   "user row's owner; item rows read from and gradient rows stored into the owner's "
+                                   "HBM over NVLink by one persistent kernel per rank (CUDA-IPC mapped shards, flag "
+                                   "barriers); NCCL: id all-gather per epoch + loss all-reduce")
+                   + (f" [EMULATED: all {G} ranks hosted by one launch on ONE GPU, no NVLink]" if emu else ""),
+                   "l2": f"inputs larger than L2: {(wl['n_users'] + wl['n_items']) * (D + 1) * 4 * (1 + S_) / G / 1e9:.1f} "
                          "GB of tables + optimizer state per rank, rows hit at random",
-                   "mean_loss": float(hs) / (world * K * B)},
-        "e2e": {"value": world * K * B / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": 24 * B,
-                "d2h_bytes_per_step": 4},
-        "gpu_launches": K * 14,
+                   "timed_region": "id all-gather (NCCL) + Philox negatives + routing / sort plan + persistent sharded "
+                                   "kernel (K steps in one launch) + loss all-reduce, x repeats",
+                   "clock_ramp": "0.3 s of device copies before the warm-up steps",
+                   "mean_loss": mean_loss},
+        "e2e": {"value": R * K * Bg / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": 16 * B,
+                "d2h_bytes_per_step": 4,
+                "note": "each rank's user+positive ids from pinned host memory; negatives are drawn on the device"},
+        "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                     "kernel": "per rank: gather + trs_linear_rows_step + trs_sparse_row_update (the whole step incl. "
-                               "routing and NCCL is in the denominator)",
-                     "algorithmic_bytes_per_step": alg / K, "nvlink_bytes_per_step_per_rank": nvl / K,
+                     "kernel": "trs::shard_train_kernel (one persistent launch per rank, K steps)",
+                     "kernel_ms_per_step": kernel_ms / K, "plan_ms_per_step": plan_ms / K,
+                     "algorithmic_bytes_per_step": alg / K / G,
+                     "whole_step_frac": alg / G / (ms / R * 1e-3) / 1e9 / peak,
+                     "nvlink": {"bytes_per_step_per_direction": nvl_dir / K, "achieved": nvl_ach, "peak": NVLINK_GBS,
+                                "unit": "GB/s per direction per GPU", "frac": nvl_ach / NVLINK_GBS,
+                                "peak_source": "measured peer copy on this pool (B200_PROFILING.md); 900 nominal"},
+                     "limiter": "nvlink" if t_nvl > t_hbm else "hbm",
+                     "frac_of_binding_roofline": max(t_hbm, t_nvl) / (kernel_ms * 1e-3),
                      "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650"},
         "clocks": clocks.summary(),
     }
-    dist.destroy_process_group()
+    if parity is not None:
+        out["parity_check"] = parity
+    tr.close()
+    del tr
+    torch.cuda.empty_cache()
     return out, rank
 
 
-def main():
-    args = parse_args()
-    wl = dict(WORKLOADS[args.workload])
+# ------------------------------------------------------------------------------------------------
+def brief(line):
+    """The part of a full bench line that other_workloads keeps."""
+    r = line.get("roofline", {})
+    return {"metric": line["metric"], "value": line["value"], "unit": line["unit"], "ms_per_step": line["ms_per_step"],
+            "steps": line["steps"], "repeats": line["config"].get("repeats"), "workload": line["config"]["workload"],
+            "parallelism": line["config"].get("parallelism"), "e2e": line["e2e"]["value"],
+            "roofline": {k: r.get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "kernel_ms_per_step",
+                                               "plan_ms_per_step", "limiter", "frac_of_binding_roofline") if k in r},
+            "gpu_launches": line.get("gpu_launches"), "clocks": line.get("clocks")}
+
+
+def resolve(args):
+    name = args.workload
+    if name == "c4":
+        name = "c4_fused" if args.gpus == 1 and not args.emulate_world else "c4_linear"
+    wl = dict(WORKLOADS[name])
     if args.batch:
         wl["batch"] = args.batch
     if args.users:
         wl["n_users"] = args.users
+        wl["desc"] += f" [users overridden: {args.users}]"
+    if args.items:
+        wl["n_items"] = args.items
+        wl["desc"] += f" [items overridden: {args.items}]"
     if args.dim:
         wl["dim"] = args.dim
         wl["desc"] += f" [n_factors overridden: {args.dim}]"
     if args.zipf:
         wl["zipf"] = args.zipf
         wl["desc"] += f" [ids drawn from Zipf({args.zipf})]"
-    rank = int(os.environ.get("RANK", "0"))
+    return name, wl
+
+
+def reference_line(args, wl, name, device):
+    impl = "reference" if device == "cpu" else "torch_cuda"
     if wl.get("predict"):
-        if rank != 0 and args.impl == "reference":
-            return
-        if args.impl == "reference":
-            r = cpu_predict(wl, max(args.cpu_seconds, 20.0) * 3)
-            print(json.dumps({"impl": "reference", "metric": "predict top-k users/sec", "value": r["value"],
-                              "unit": "users/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": 0,
-                              "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-                              "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                              "config": {"workload": wl["desc"], "name": args.workload},
-                              "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                              "e2e": {"value": r["value"], "unit": "users/s", "h2d_bytes_per_step": 0,
-                                      "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
-            return
-        out = predict_bench(args, wl)
-        if rank != 0:
-            return
-        if not args.no_cpu_baseline and args.gpus == 1:
-            r = cpu_predict(wl, args.cpu_seconds)
-            out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(out))
+        r = cpu_predict(wl, max(args.cpu_seconds, 20.0) * 3)
+        metric, unit, W = "predict top-k users/sec", "users/s", 0
+    else:
+        W = max(1, min(args.warmup, 3))
+        r = port_reference(wl, max(1, args.steps), W, budget_s=max(args.cpu_seconds, 20.0) * 3, device=device)
+        metric, unit = "train samples/sec (fwd+bwd+sparse update)", "samples/s"
+    return {"impl": impl, "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
+            "steps": r["steps"], "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "name": name, "batch_per_gpu": wl["batch"]},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+def main():
+    args = parse_args()
+    name, wl = resolve(args)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl in ("reference", "torch_cuda"):
+        if rank == 0:
+            print(json.dumps(reference_line(args, wl, name, "cpu" if args.impl == "reference" else "cuda")))
         return
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        steps = max(1, args.steps)
-        r = cpu_reference(wl, steps, max(1, min(args.warmup, 3)), budget_s=max(args.cpu_seconds, 20.0) * 3)
-        line = {"impl": "reference", "metric": "train samples/sec (fwd+bwd+sparse update)", "value": r["value"],
-                "unit": "samples/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(1, min(args.warmup, 3)),
-                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": wl["desc"], "name": args.workload, "batch_per_gpu": wl["batch"]},
-                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line))
+    if wl.get("predict"):
+        out = predict_bench(args, wl, name)
+    elif wl.get("sharded"):
+        out, _ = sharded_bench(args, wl, name)
+    else:
+        out, _ = gpu_bench(args, wl, name)
+    # ---- the other BASELINE configs, in the same line ----
+    others = {}
+    if args.workload == "c4" and not args.no_others:
+        import copy
+        import gc
+        import torch
+        sub = copy.copy(args)
+        gc.collect()
+        torch.cuda.empty_cache()
+        try:
+            if world == 1 and not args.emulate_world:
+                sub.steps, sub.warmup = max(args.steps, 20), max(args.warmup, 5)
+                others["c2_fm"] = brief(gpu_bench(sub, dict(WORKLOADS["c2_fm"]), "c2_fm")[0])
+                others["c3_mlp"] = brief(gpu_bench(sub, dict(WORKLOADS["c3_mlp"]), "c3_mlp")[0])
+                others["c5_predict"] = brief(predict_bench(sub, dict(WORKLOADS["c5_predict"]), "c5_predict", K=5, W=3))
+                sub.steps, sub.warmup, sub.emulate_world = args.steps, args.warmup, 1
+                others["c4_sharded_kernel_1rank"] = brief(sharded_bench(sub, dict(WORKLOADS["c4_linear"]), "c4_linear")[0])
+            elif world > 1:
+                others["c5_predict"] = brief(predict_bench(sub, dict(WORKLOADS["c5_predict"]), "c5_predict", K=5, W=3))
+        except Exception as e:  # a sub-result must never cost the headline line
+            others["error"] = f"{type(e).__name__}: {e}"
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    if rank != 0:
         return
-    out, rank = sharded_bench(args, wl) if wl.get("sharded") else gpu_bench(args, wl)
-    if rank == 0:
-        if args.gpus == 1 and not args.no_cpu_baseline:
-            r = cpu_reference(wl, steps=8, warmup=1, budget_s=args.cpu_seconds)
-            out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(out))
+    if others:
+        out["other_workloads"] = others
+    if args.gpus == 1 and not args.no_cpu_baseline:
+        r = cpu_predict(wl, args.cpu_seconds) if wl.get("predict") else \
+            port_reference(wl, steps=8, warmup=1, budget_s=args.cpu_seconds)
+        out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(out))
 
 
 if __name__ == "__main__":

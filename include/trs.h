@@ -276,6 +276,65 @@ int trs_linear_rows_step(int dim, int64_t batch, float inv_batch, const float* u
 int trs_topk_merge(const float* score, const int64_t* idx, int n_lists, int k, int64_t n_query,
                    int64_t* out_idx, float* out_score, trs_stream_t stream);
 
+/* ---- e1: row-sharded training over PEER-MAPPED table shards (BASELINE configs[3]) ------------ */
+/* The reference is single-device (model.py:74); this is the multi-GPU form of model.py:274-284 for
+ * net_type='linear'.  Row r of the user / item table lives on rank r % world at local row r / world.  Every rank
+ * maps every other rank's shard, gradient staging buffer and barrier words into its own address space (CUDA IPC,
+ * trs_ipc_* below) and ONE persistent kernel per rank runs K steps:
+ *   phase A  the rank's samples of the step (those whose USER row it owns: user rows never cross NVLink): item
+ *            rows are read straight from their owner's HBM over NVLink (cp.async from the peer pointer), both
+ *            scores, hinge over the GLOBAL batch, and each lookup's gradient row is stored straight into its
+ *            owner's staging buffer at slot = the lookup's index in the global batch
+ *   cross-rank barrier (flag words in peer memory)
+ *   phase B  every owner reduces the staged rows of each of ITS touched rows in slot order (what coalesce() gives;
+ *            deterministic) and applies SGD / Adagrad / SparseAdam to its shard
+ *   cross-rank barrier
+ * No NCCL call on the step path: the exchange IS the kernel's loads and stores. */
+#define TRS_MAX_RANKS 8
+#define TRS_SHARD_SYNC_BYTES 4096 /* barrier words of one rank; zeroed ONCE when allocated, never afterwards */
+
+typedef struct {
+    int32_t rank, world;
+    int32_t dim, reserved;
+    int64_t n_users, n_items;      /* GLOBAL row counts */
+    trs_table user[TRS_MAX_RANKS]; /* rank q's shard as mapped into THIS process (q == rank: plain device memory); */
+    trs_table item[TRS_MAX_RANKS]; /*   n_rows = rows of that shard; lin = user_bias / item_bias                  */
+    void* stage[TRS_MAX_RANKS];    /* rank q's gradient staging buffer, trs_shard_stage_bytes() */
+    void* sync[TRS_MAX_RANKS];     /* rank q's barrier words, TRS_SHARD_SYNC_BYTES */
+} trs_shard;
+
+/* `epoch` below is always the GLOBAL epoch: the ids of every rank's samples in loader order, identical on all
+ * ranks (an all-gather of the loader output, once per epoch); epoch->batch is the GLOBAL batch.  Metadata is not
+ * supported on this path. */
+size_t trs_shard_stage_bytes(int dim, int global_batch);
+/* The rank's plan: which samples it runs (user % world == rank) and, per step, the (local row, slot) pairs of the
+ * lookups it OWNS, stably sorted by row. */
+size_t trs_shard_plan_bytes(const trs_epoch* epoch);
+size_t trs_shard_plan_tmp_bytes(const trs_epoch* epoch);
+int trs_shard_plan_build(const trs_shard* shard, const trs_epoch* epoch, void* plan, size_t plan_bytes, void* tmp,
+                         size_t tmp_bytes, trs_stream_t stream);
+/* Steps [first_step, first_step + n_steps) for the n_local ranks this launch hosts: 1 in production (one process
+ * per GPU); all `world` ranks when a single GPU emulates the group (tests: one cooperative launch, the SMs split
+ * between the ranks -- separate launches must never wait on each other on one device).
+ *  - sync_epoch: cross-rank barriers the group has passed so far (2 per step); the caller adds 2 * n_steps after
+ *    every call, identically on every rank.
+ *  - loss_sum[i][s]: sum of the hinges of rank i's samples of step first_step + s (all-reduce and divide by the
+ *    step's global sample count for the value loss.item() returns at model.py:200).
+ *  - status (device int32, zeroed by the caller): set non-zero if a peer did not arrive within timeout_ms (the
+ *    kernel then stops waiting and finishes; the tables are garbage and the caller must raise). */
+size_t trs_shard_workspace_bytes(const trs_epoch* epoch, int n_local);
+int trs_shard_train_steps(const trs_shard* shards, int n_local, const trs_epoch* epoch, const trs_optim* optim,
+                          const void* const* plans_host, void* workspace, size_t workspace_bytes, int first_step,
+                          int n_steps, uint64_t sync_epoch, float* const* loss_sum_host, int32_t* status,
+                          int timeout_ms, trs_stream_t stream);
+
+/* CUDA IPC plumbing for the peer mapping (the only entry points that touch address spaces; they never allocate
+ * device memory).  export: 64-byte handle of the allocation that contains `ptr` + the offset of ptr inside it;
+ * open: maps that allocation into this process (peer access enabled lazily) and returns its base; close unmaps. */
+int trs_ipc_export(const void* ptr, void* handle64_host, uint64_t* offset_host);
+int trs_ipc_open(const void* handle64_host, void** base_host);
+int trs_ipc_close(void* base);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,176 @@
+"""Row-sharded Linear training over peer-mapped shards (csrc/shard.cu, torchrecsys_b200/sharded.py) on ONE B200
+(``-m gpu``): a single cooperative launch hosts all G ranks of the group (the SMs are split between them), so the
+whole multi-rank path -- sample placement by user owner, loads from / gradient stores into "peer" arenas, the flag
+barriers, owner-side coalesce + update -- runs on a 1-GPU box exactly as it does over NVLink, minus the wires.
+
+Oracle: the numpy restatement's single-process step on the GLOBAL batch (oracle/cf_oracle.py: train_step), i.e.
+model.py:274-284 of the reference.  Tolerances as tests/test_gpu_train_shapes.py (fp32; the order of a duplicate
+row's summands differs from numpy's for rows with many lookups)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _skewed(rng, n_rows, n):
+    hot = rng.integers(0, 3, n)
+    warm = rng.integers(0, min(n_rows, 64), n)
+    cold = rng.integers(0, n_rows, n)
+    pick = rng.random(n)
+    return np.where(pick < 0.10, hot, np.where(pick < 0.35, warm, cold)).astype(np.int64)
+
+
+def _full_params(rng, U, I, D):
+    return {"user.weight": rng.normal(0, .4, (U, D)).astype(np.float32),
+            "item.weight": rng.normal(0, .4, (I, D)).astype(np.float32),
+            "user_bias.weight": rng.normal(0, .1, (U, 1)).astype(np.float32),
+            "item_bias.weight": rng.normal(0, .1, (I, 1)).astype(np.float32)}
+
+
+def _trainer(dev, world, U, I, D, B, opt, lr, params):
+    from torchrecsys_b200.sharded import ShardedLinearTrainer
+    tr = ShardedLinearTrainer(U, I, D, global_batch=B, optimizer=opt, lr=lr, device=dev, emulate_world=world,
+                              timeout_ms=5000)
+    tr.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    return tr
+
+
+def _to(dev, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("dim", [16, 64, 128, 256])
+@pytest.mark.parametrize("opt", ["sgd", "adagrad", "sparse_adam"])
+def test_sharded_steps_match_the_oracle_on_the_global_batch(dev, world, dim, opt):
+    if opt != "sparse_adam" and (dim in (16, 256) or world in (3, 8)):
+        pytest.skip("optimizer variants are covered on the other shapes")
+    U, I, steps = 3001, 701, 4
+    B = 1500 if opt == "sgd" else 1024   # power-of-two batch: g = 1/B sums exactly (see test_gpu_train_shapes)
+    lr = 0.05
+    rng = np.random.default_rng(dim * 11 + world)
+    params = _full_params(rng, U, I, dim)
+    n = B * steps - (37 if opt == "sgd" else 0)   # SGD: short last batch
+    user, pos, neg = _skewed(rng, U, n), _skewed(rng, I, n), _skewed(rng, I, n)
+    tr = _trainer(dev, world, U, I, dim, B, opt, lr, params)
+    loss = tr.train_epoch(_to(dev, user), _to(dev, pos), _to(dev, neg), B).cpu().numpy()
+
+    spec = O.OptSpec(opt, lr=lr)
+    state = O.init_opt_state(params, spec)
+    want = []
+    for s in range(steps):
+        batch = {"user": user[s * B:(s + 1) * B], "pos": pos[s * B:(s + 1) * B], "neg": neg[s * B:(s + 1) * B]}
+        want.append(O.train_step("linear", params, state, batch, spec, s + 1))
+    np.testing.assert_allclose(loss[0], want[0], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(loss, np.array(want), rtol=2e-5 if opt == "sgd" else 5e-4, atol=2e-6)
+    tol = dict(rtol=2e-3, atol=2e-3 * lr * 20) if opt == "sparse_adam" else dict(rtol=1e-4, atol=2e-5)
+    got = {k: v.cpu().numpy() for k, v in tr.state_dict().items()}
+    for k in params:
+        np.testing.assert_allclose(got[k], params[k], err_msg=k, **tol)
+    gst = tr.optimizer_state_dict()
+    for k in params:
+        for sname, want_s in state[k].items():
+            if k == "user_bias.weight":
+                continue  # its gradient is exactly 0: state stays 0 here; the oracle decays nothing either
+            np.testing.assert_allclose(gst[k][sname].cpu().numpy(), want_s, err_msg=f"{k}.{sname}", **tol)
+    # rows nobody looked up are bit-identical to the initial tables
+    untouched = np.setdiff1d(np.arange(I), np.concatenate([pos, neg]))
+    assert untouched.size and np.array_equal(got["item.weight"][untouched], params["item.weight"][untouched])
+
+
+def test_group_sizes_agree_bit_for_bit_and_split_launches_equal_one(dev):
+    """The result does not depend on how many ranks share the work (every sum has a fixed association: slot order)
+    nor on where an epoch is cut into launches."""
+    U, I, D, B, steps = 2000, 500, 64, 512, 6
+    rng = np.random.default_rng(3)
+    params = _full_params(rng, U, I, D)
+    n = B * steps
+    user, pos, neg = (_to(dev, _skewed(rng, m, n)) for m in (U, I, I))
+    ref = None
+    for world in (1, 2, 4):
+        tr = _trainer(dev, world, U, I, D, B, "sparse_adam", 0.05, params)
+        loss = tr.train_epoch(user, pos, neg, B)
+        sd = tr.state_dict()
+        tr2 = _trainer(dev, world, U, I, D, B, "sparse_adam", 0.05, params)
+        h = (steps // 2) * B
+        l2 = torch.cat([tr2.train_epoch(user[:h], pos[:h], neg[:h], B), tr2.train_epoch(user[h:], pos[h:], neg[h:], B)])
+        sd2 = tr2.state_dict()
+        assert torch.equal(loss, l2)
+        for k in sd:
+            assert torch.equal(sd[k], sd2[k]), k
+        if ref is None:
+            ref = sd
+        else:
+            for k in sd:
+                assert torch.equal(sd[k], ref[k]), (world, k)
+
+
+def test_sharded_training_equals_the_fused_single_gpu_kernel(dev):
+    """Same ids, same init: the peer-mapped path and trs_train_steps (one GPU, whole tables) end in the same
+    tables up to the order of duplicate sums."""
+    from torchrecsys_b200.collaborative.linear import Linear
+    from torchrecsys_b200.engine import EpochRunner
+    U, I, D, B, steps = 5000, 900, 128, 1024, 5
+    rng = np.random.default_rng(9)
+    params = _full_params(rng, U, I, D)
+    n = B * steps
+    user, pos, neg = (_to(dev, rng.integers(0, m, n)) for m in (U, I, I))
+    net = Linear(U, I, {}, D, use_metadata=False, use_cuda=True)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    net = net.to(dev)
+    opt = torch.optim.SparseAdam(list(net.parameters()), lr=0.01)
+    loss_f = EpochRunner(net, opt).run({"user": user, "pos": pos, "neg": neg}, B)
+    tr = _trainer(dev, 4, U, I, D, B, "sparse_adam", 0.01, params)
+    loss_s = tr.train_epoch(user, pos, neg, B)
+    np.testing.assert_allclose(loss_s.cpu().numpy(), loss_f.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    sd = tr.state_dict()
+    for k, v in net.state_dict().items():
+        np.testing.assert_allclose(sd[k].cpu().numpy(), v.cpu().numpy(), rtol=2e-3, atol=2e-4, err_msg=k)
+
+
+def test_checkpoint_moves_between_group_sizes_and_the_single_gpu_model(dev):
+    """state_dict() / optimizer_state_dict() are in the reference's single-process layout: train on 2 ranks, reload on
+    3 ranks (parameters AND SparseAdam moments), continue -- equals 4 uninterrupted steps on 1 rank."""
+    U, I, D, B = 1200, 300, 32, 256
+    rng = np.random.default_rng(5)
+    params = _full_params(rng, U, I, D)
+    n = B * 4
+    user, pos, neg = (_to(dev, _skewed(rng, m, n)) for m in (U, I, I))
+    one = _trainer(dev, 1, U, I, D, B, "sparse_adam", 0.05, params)
+    one.train_epoch(user, pos, neg, B)
+    a = _trainer(dev, 2, U, I, D, B, "sparse_adam", 0.05, params)
+    h = 2 * B
+    a.train_epoch(user[:h], pos[:h], neg[:h], B)
+    b = _trainer(dev, 3, U, I, D, B, "sparse_adam", 0.05, params)
+    b.load_state_dict(a.state_dict(), a.optimizer_state_dict())
+    assert b.binding.step0 == 2
+    b.train_epoch(user[h:], pos[h:], neg[h:], B)
+    for k, v in one.state_dict().items():
+        assert torch.equal(b.state_dict()[k], v), k
+    so, sb = one.optimizer_state_dict(), b.optimizer_state_dict()
+    for k in so:
+        for name in ("exp_avg", "exp_avg_sq"):
+            assert torch.equal(so[k][name], sb[k][name]), (k, name)
+    # and into the single-GPU module of the drop-in API
+    from torchrecsys_b200.collaborative.linear import Linear
+    net = Linear(U, I, {}, D, use_metadata=False, use_cuda=True)
+    net.load_state_dict(b.state_dict())
+    assert torch.equal(net.item.weight.detach().cpu(), one.state_dict()["item.weight"].cpu())
+
+
+def test_bad_arguments_raise(dev):
+    from torchrecsys_b200.sharded import ShardedLinearTrainer
+    with pytest.raises(ValueError):
+        ShardedLinearTrainer(10, 10, 6, global_batch=8, device=dev, emulate_world=2)      # dim % 4
+    tr = ShardedLinearTrainer(100, 50, 8, global_batch=16, device=dev, emulate_world=2)
+    ids = torch.zeros(64, dtype=torch.int64, device=dev)
+    with pytest.raises(ValueError):
+        tr.train_epoch(ids, ids, ids, 32)                                                  # batch > staging size

@@ -54,7 +54,7 @@ def _worker(rank, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=WORLD)
     try:
-        from torchrecsys_b200 import sharded as S
+        from torchrecsys_b200 import routed as R, sharded as S
         torch.set_num_threads(1)
         rng = np.random.default_rng(7)
         full = {"user.weight": rng.normal(0, .5, (U, D)).astype(np.float32),
@@ -62,7 +62,7 @@ def _worker(rank, port, q):
                 "user_bias.weight": np.zeros((U, 1), np.float32),
                 "item_bias.weight": rng.normal(0, .1, (I, 1)).astype(np.float32)}
         batch = {k: rng.integers(0, n, WORLD * B) for k, n in (("user", U), ("pos", I), ("neg", I))}
-        tr = S.ShardedLinearTrainer(U, I, D, optimizer="sgd", lr=0.3, device=torch.device("cpu"))
+        tr = R.RoutedLinearTrainer(U, I, D, optimizer="sgd", lr=0.3, device=torch.device("cpu"))
         tr._gather, tr._compute, tr._update = (_torch_hooks(tr)[k] for k in ("gather", "compute", "update"))
         for name, key, bkey in (("user", "user.weight", "user_bias.weight"), ("item", "item.weight", "item_bias.weight")):
             emb, bias = tr.tables[name]
@@ -70,8 +70,8 @@ def _worker(rank, port, q):
             bias.copy_(torch.from_numpy(full[bkey][rank::WORLD]))
         # routing round trip: what comes back for lookup j is the row of id j
         ids = torch.from_numpy(batch["user"][rank * B:(rank + 1) * B])
-        route = S.make_route(ids, torch.zeros_like(ids), 2, WORLD)
-        back = S.exchange_back(route, tr._gather("user", route.recv_rows))
+        route = R.make_route(ids, torch.zeros_like(ids), 2, WORLD)
+        back = R.exchange_back(route, tr._gather("user", route.recv_rows))
         assert torch.equal(back[:, :D], torch.from_numpy(full["user.weight"])[ids])
         # one sharded step == one oracle step on the global batch
         sl = slice(rank * B, (rank + 1) * B)

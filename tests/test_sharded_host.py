@@ -1,0 +1,114 @@
+"""Host logic of the peer-mapped row-sharded trainer (torchrecsys_b200/sharded.py) without a GPU: the arena layout,
+shard ownership (row r -> rank r % G, local row r // G), checkpoint scatter / gather in the reference's
+single-process layout -- in-process (``emulate_world``) and over a world-size-2 gloo group -- and that training
+without CUDA raises instead of falling back."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from torchrecsys_b200.sharded import ShardedLinearTrainer, shard_rows
+
+
+def _full(rng, U, I, D):
+    return {"user.weight": torch.from_numpy(rng.normal(0, 1, (U, D)).astype(np.float32)),
+            "item.weight": torch.from_numpy(rng.normal(0, 1, (I, D)).astype(np.float32)),
+            "user_bias.weight": torch.from_numpy(rng.normal(0, 1, (U, 1)).astype(np.float32)),
+            "item_bias.weight": torch.from_numpy(rng.normal(0, 1, (I, 1)).astype(np.float32))}
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_shard_rows_partition_every_table(world):
+    for n in (0, 1, 7, 8, 9, 1000, 50_000_000):
+        assert sum(shard_rows(n, r, world) for r in range(world)) == n
+        for r in range(world):
+            assert shard_rows(n, r, world) == len(range(r, n, world))
+
+
+@pytest.mark.parametrize("world,opt", [(1, "sgd"), (2, "adagrad"), (3, "sparse_adam"), (8, "sparse_adam")])
+def test_checkpoint_round_trip_on_cpu_arenas(world, opt):
+    U, I, D = 103, 41, 8
+    rng = np.random.default_rng(world)
+    full = _full(rng, U, I, D)
+    tr = ShardedLinearTrainer(U, I, D, global_batch=64, optimizer=opt, device="cpu", emulate_world=world)
+    # arenas: every piece 256-byte aligned, nothing overlaps, staging and barrier words inside
+    L = tr.layout
+    offs = sorted([L.emb["user"], L.emb["item"], L.lin["user"], L.lin["item"], L.stage, L.sync]
+                  + L.emb_state["user"] + L.emb_state["item"] + L.lin_state["user"] + L.lin_state["item"])
+    assert all(o % 256 == 0 for o in offs) and len(set(offs)) == len(offs) and L.total >= L.sync + 4096
+    for r in range(world):
+        assert not tr.arenas[r][L.sync:L.sync + 4096].any()
+    state = {k: {name: torch.from_numpy(rng.random(tuple(v.shape)).astype(np.float32))
+                 for name in {"sgd": (), "adagrad": ("sum",), "sparse_adam": ("exp_avg", "exp_avg_sq")}[opt]}
+             for k, v in full.items()}
+    for k in state:
+        state[k]["step"] = 17
+    tr.load_state_dict(full, state)
+    assert tr.binding.step0 == 17
+    for r in range(world):  # ownership: local row l of rank r is global row l * G + r
+        assert torch.equal(tr.tables[r]["item"][0], full["item.weight"][r::world])
+        assert torch.equal(tr.tables[r]["user"][1], full["user_bias.weight"][r::world])
+    back, sback = tr.state_dict(), tr.optimizer_state_dict()
+    for k in full:
+        assert torch.equal(back[k], full[k]), k
+        for name, v in state[k].items():
+            if name != "step":
+                assert torch.equal(sback[k][name], v), (k, name)
+    # a different group size reads the same checkpoint
+    other = ShardedLinearTrainer(U, I, D, global_batch=64, optimizer=opt, device="cpu", emulate_world=world % 3 + 1)
+    other.load_state_dict(back, sback)
+    assert torch.equal(other.state_dict()["user.weight"], full["user.weight"])
+
+
+def test_training_without_cuda_raises():
+    tr = ShardedLinearTrainer(10, 10, 8, global_batch=4, device="cpu", emulate_world=2)
+    ids = torch.zeros(8, dtype=torch.int64)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tr.train_epoch(ids, ids, ids, 4)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=2)
+    try:
+        torch.set_num_threads(1)
+        U, I, D = 57, 23, 4
+        full = _full(np.random.default_rng(1), U, I, D)
+        tr = ShardedLinearTrainer(U, I, D, global_batch=16, optimizer="adagrad", device="cpu")
+        assert (tr.rank, tr.world, tr.local_ranks) == (rank, 2, [rank])
+        tr.load_state_dict(full)
+        assert torch.equal(tr.tables[rank]["user"][0], full["user.weight"][rank::2])
+        tr.state[rank]["item"][0][0].fill_(float(rank + 1))        # Adagrad sums differ per rank
+        sd, osd = tr.state_dict(), tr.optimizer_state_dict()       # all_gather over gloo
+        ok = all(torch.equal(sd[k], full[k]) for k in full)
+        want = torch.tensor([1.0, 2.0]).repeat(I)[:I, None].expand(I, D)
+        ok = ok and torch.equal(osd["item.weight"]["sum"], want)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_checkpoint_gather_over_a_gloo_group_of_two():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = dict(q.get(timeout=5) for _ in range(2))
+    assert got == {0: True, 1: True}

@@ -25,7 +25,9 @@ SYMBOLS = [
     "trs_gemm_bf16_tn", "trs_mlp_forward_workspace_bytes", "trs_mlp_forward",
     "trs_mlp_train_workspace_bytes", "trs_mlp_train_steps", "trs_predict_topk_workspace_bytes",
     "trs_predict_topk", "trs_sparse_update_workspace_bytes", "trs_sparse_row_update", "trs_linear_rows_step",
-    "trs_topk_merge",
+    "trs_topk_merge", "trs_shard_stage_bytes", "trs_shard_plan_bytes", "trs_shard_plan_tmp_bytes",
+    "trs_shard_plan_build", "trs_shard_workspace_bytes", "trs_shard_train_steps", "trs_ipc_export",
+    "trs_ipc_open", "trs_ipc_close",
 ]
 
 
@@ -71,7 +73,8 @@ def lib() -> C.CDLL:
                 "(there is no CPU / eager fallback for the hot path)")
         L = C.CDLL(LIB_PATH)
         L.trs_last_error.restype = C.c_char_p
-        for name in ("trs_plan_bytes", "trs_plan_tmp_bytes", "trs_train_workspace_bytes"):
+        for name in ("trs_plan_bytes", "trs_plan_tmp_bytes", "trs_train_workspace_bytes", "trs_shard_stage_bytes",
+                     "trs_shard_plan_bytes", "trs_shard_plan_tmp_bytes", "trs_shard_workspace_bytes"):
             getattr(L, name).restype = C.c_size_t
         if L.trs_abi_version() != 1:
             raise RuntimeError("libtrs_b200.so ABI version mismatch")
@@ -360,3 +363,72 @@ def topk_merge(score, idx, k: int):
                                 n_lists, k, C.c_int64(nq), C.c_void_p(out_idx.data_ptr()),
                                 C.c_void_p(out_score.data_ptr()), _stream()))
     return out_idx, out_score
+
+
+# ---- row-sharded training over peer-mapped shards (include/trs.h: trs_shard) ---------------------------
+MAX_RANKS = 8
+SHARD_SYNC_BYTES = 4096
+
+
+class Shard(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("dim", C.c_int32), ("reserved", C.c_int32),
+                ("n_users", C.c_int64), ("n_items", C.c_int64), ("user", Table * MAX_RANKS),
+                ("item", Table * MAX_RANKS), ("stage", C.c_void_p * MAX_RANKS), ("sync", C.c_void_p * MAX_RANKS)]
+
+
+def table_at(base: int, emb_off, s0_off, s1_off, lin_off, lin_s0_off, lin_s1_off, n_rows: int) -> Table:
+    """A trs_table from raw device addresses: ``base`` + byte offsets (None = absent)."""
+    at = lambda o: None if o is None else base + o
+    return Table(at(emb_off), at(s0_off), at(s1_off), at(lin_off), at(lin_s0_off), at(lin_s1_off), n_rows)
+
+
+def shard_stage_bytes(dim: int, global_batch: int) -> int:
+    return lib().trs_shard_stage_bytes(dim, global_batch)
+
+
+def shard_plan_build(shard: Shard, epoch: Epoch, device, plan=None, tmp=None) -> torch.Tensor:
+    L = lib()
+    plan = _grown(plan, L.trs_shard_plan_bytes(C.byref(epoch)), device)
+    tmp = _grown(tmp, L.trs_shard_plan_tmp_bytes(C.byref(epoch)), device)
+    _check(L.trs_shard_plan_build(C.byref(shard), C.byref(epoch), C.c_void_p(plan.data_ptr()), C.c_size_t(plan.numel()),
+                                  C.c_void_p(tmp.data_ptr()), C.c_size_t(tmp.numel()), _stream()))
+    return plan
+
+
+def shard_train_steps(shards: Sequence[Shard], epoch: Epoch, optim: Optim, plans: Sequence[torch.Tensor],
+                      first_step: int, n_steps: int, sync_epoch: int, loss_sums: Sequence[torch.Tensor],
+                      status: torch.Tensor, workspace=None, timeout_ms: int = 20000) -> torch.Tensor:
+    """One persistent launch for the local ranks (1 in production, the whole group when one GPU emulates it).
+    Returns the workspace so the caller can keep it for the next call."""
+    L = lib()
+    n = len(shards)
+    arr = (Shard * n)(*shards)
+    nbytes = L.trs_shard_workspace_bytes(C.byref(epoch), n)
+    if nbytes == 0:
+        raise RuntimeError("libtrs_b200: bad shard workspace query")
+    workspace = _grown(workspace, nbytes, status.device)
+    plan_ptrs = (C.c_void_p * n)(*[p.data_ptr() for p in plans])
+    loss_ptrs = (C.c_void_p * n)(*[_ptr(t, torch.float32) for t in loss_sums])
+    _check(L.trs_shard_train_steps(arr, n, C.byref(epoch), C.byref(optim), plan_ptrs, C.c_void_p(workspace.data_ptr()),
+                                   C.c_size_t(workspace.numel()), first_step, n_steps, C.c_uint64(sync_epoch), loss_ptrs,
+                                   C.c_void_p(_ptr(status, torch.int32)), timeout_ms, _stream()))
+    return workspace
+
+
+def ipc_export(t: torch.Tensor):
+    """(64-byte handle, offset) of the CUDA allocation that holds tensor ``t`` -- for a peer process to map."""
+    handle = (C.c_ubyte * 64)()
+    off = C.c_uint64()
+    _check(lib().trs_ipc_export(C.c_void_p(t.data_ptr()), handle, C.byref(off)))
+    return bytes(handle), int(off.value)
+
+
+def ipc_open(handle: bytes) -> int:
+    base = C.c_void_p()
+    buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+    _check(lib().trs_ipc_open(buf, C.byref(base)))
+    return int(base.value)
+
+
+def ipc_close(base: int) -> None:
+    _check(lib().trs_ipc_close(C.c_void_p(base)))

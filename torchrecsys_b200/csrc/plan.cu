@@ -58,12 +58,13 @@ __device__ __forceinline__ void load_pair(const SortSrc& s, int64_t step, int B,
 template <bool FIRST>
 __global__ void __launch_bounds__(SORT_THREADS)
 sort_hist_kernel(SortSrc src, uint32_t* __restrict__ hist, int tiles, int64_t n_samples, int B,
-                 int mult, int shift) {
+                 int mult, int shift, const uint32_t* __restrict__ len_arr, int len_stride) {
     __shared__ uint32_t s_hist[256];
     const int64_t step = blockIdx.y;
     const int tile = blockIdx.x;
     const int Bs = (int)min((int64_t)B, n_samples - step * B);
-    const int len = mult * Bs;
+    // len_arr (pairs only): the segment of step s holds len_arr[s * len_stride] pairs instead of mult * B_s
+    const int len = len_arr ? (int)len_arr[step * len_stride] : mult * Bs;
     s_hist[threadIdx.x] = 0;
     __syncthreads();
 #pragma unroll
@@ -83,7 +84,7 @@ template <bool FIRST>
 __global__ void __launch_bounds__(SORT_THREADS)
 sort_scatter_kernel(SortSrc src, uint32_t* __restrict__ dst_key, uint32_t* __restrict__ dst_val,
                     const uint32_t* __restrict__ hist, int tiles, int64_t n_samples, int B, int mult,
-                    int shift) {
+                    int shift, const uint32_t* __restrict__ len_arr, int len_stride) {
     __shared__ uint32_t s_base[256];
     __shared__ uint32_t s_run[256];
     __shared__ uint32_t s_wcnt[SORT_THREADS / 32][256];
@@ -91,7 +92,7 @@ sort_scatter_kernel(SortSrc src, uint32_t* __restrict__ dst_key, uint32_t* __res
     const int64_t step = blockIdx.y;
     const int tile = blockIdx.x;
     const int Bs = (int)min((int64_t)B, n_samples - step * B);
-    const int len = mult * Bs;
+    const int len = len_arr ? (int)len_arr[step * len_stride] : mult * Bs;
     const int64_t base = (int64_t)mult * step * B;
     const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
 
@@ -172,16 +173,38 @@ int sort_space(const int64_t* a, const int64_t* b, int stride, int off, int mult
         uint32_t* dv = to_out ? out_val : tmp_val;
         SortSrc src = {a, b, stride, off, to_out ? tmp_key : out_key, to_out ? tmp_val : out_val};
         if (p == 0) {
-            sort_hist_kernel<true><<<grid, SORT_THREADS, 0, st>>>(src, hist, tiles, ep->n_samples, ep->batch, mult, 0);
-            sort_scatter_kernel<true><<<grid, SORT_THREADS, 0, st>>>(src, dk, dv, hist, tiles, ep->n_samples, ep->batch, mult, 0);
+            sort_hist_kernel<true><<<grid, SORT_THREADS, 0, st>>>(src, hist, tiles, ep->n_samples, ep->batch, mult, 0, nullptr, 0);
+            sort_scatter_kernel<true><<<grid, SORT_THREADS, 0, st>>>(src, dk, dv, hist, tiles, ep->n_samples, ep->batch, mult, 0, nullptr, 0);
         } else {
-            sort_hist_kernel<false><<<grid, SORT_THREADS, 0, st>>>(src, hist, tiles, ep->n_samples, ep->batch, mult, 8 * p);
-            sort_scatter_kernel<false><<<grid, SORT_THREADS, 0, st>>>(src, dk, dv, hist, tiles, ep->n_samples, ep->batch, mult, 8 * p);
+            sort_hist_kernel<false><<<grid, SORT_THREADS, 0, st>>>(src, hist, tiles, ep->n_samples, ep->batch, mult, 8 * p, nullptr, 0);
+            sort_scatter_kernel<false><<<grid, SORT_THREADS, 0, st>>>(src, dk, dv, hist, tiles, ep->n_samples, ep->batch, mult, 8 * p, nullptr, 0);
         }
     }
     TRS_CUDA(cudaGetLastError());
     return TRS_OK;
 }
+
+// Stable sort of (key, value) PAIRS that are already in memory: the segment of step s starts at mult * s * B and
+// holds len_arr[s * len_stride] pairs (the row-sharded plan: only the lookups a rank owns).  Pass p reads
+// buf[p & 1] and writes buf[(p + 1) & 1]; returns the number of passes so the caller knows where the result is.
+int sort_pairs(uint32_t* key0, uint32_t* val0, uint32_t* key1, uint32_t* val1, int mult, int64_t n_rows,
+               const trs_epoch* ep, const uint32_t* len_arr, int len_stride, uint32_t* hist, cudaStream_t st) {
+    const int64_t steps = n_steps_of(ep);
+    const int tiles = (int)(((int64_t)mult * ep->batch + SORT_TILE - 1) / SORT_TILE);
+    const int npass = (bits_for(n_rows) + 7) / 8;
+    dim3 grid(tiles, (unsigned)steps);
+    for (int p = 0; p < npass; ++p) {
+        SortSrc src = {nullptr, nullptr, 0, 0, (p & 1) ? key1 : key0, (p & 1) ? val1 : val0};
+        uint32_t* dk = (p & 1) ? key0 : key1;
+        uint32_t* dv = (p & 1) ? val0 : val1;
+        sort_hist_kernel<false><<<grid, SORT_THREADS, 0, st>>>(src, hist, tiles, ep->n_samples, ep->batch, mult, 8 * p,
+                                                              len_arr, len_stride);
+        sort_scatter_kernel<false><<<grid, SORT_THREADS, 0, st>>>(src, dk, dv, hist, tiles, ep->n_samples, ep->batch, mult,
+                                                                 8 * p, len_arr, len_stride);
+    }
+    return npass;
+}
+int sort_passes(int64_t n_rows) { return (bits_for(n_rows) + 7) / 8; }
 
 // After the sort: turn every segment (run of equal row ids) into work items.  Sorted keys make
 // "longer than T" one probe (K[k+T] == K[k]) and the exact length a binary search.

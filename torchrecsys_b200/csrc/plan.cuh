@@ -42,5 +42,9 @@ int sort_space(const int64_t* a, const int64_t* b, int stride, int off, int mult
                const trs_epoch* ep, uint32_t* out_key, uint32_t* out_val, uint32_t* tmp_key, uint32_t* tmp_val,
                uint32_t* hist, cudaStream_t st);
 size_t hist_bytes(const trs_epoch* ep);
+// the same sort on (key, value) pairs already in memory, with per-step segment lengths read from the device
+int sort_pairs(uint32_t* key0, uint32_t* val0, uint32_t* key1, uint32_t* val1, int mult, int64_t n_rows,
+               const trs_epoch* ep, const uint32_t* len_arr, int len_stride, uint32_t* hist, cudaStream_t st);
+int sort_passes(int64_t n_rows);
 
 }  // namespace trs

@@ -1,0 +1,792 @@
+// shard.cu -- row-sharded training of the Linear scorer over PEER-MAPPED table shards (BASELINE
+// configs[3]: 50M users x 5M items, dim 128, 1/2/4/8 GPUs).  Reference semantics: model.py:274-284 on ONE global
+// batch per step (forward x2, hinge_loss, backward, optimizer.step()); the reference itself is single-device.
+//
+// Row r of a table lives on rank r % W at local row r / W.  Every rank maps every peer's shard, gradient staging
+// buffer and barrier words (CUDA IPC) and runs ONE persistent cooperative kernel for K steps -- the exchange step
+// of the sharded path is the kernel's own loads and stores over NVLink, there is no collective call per step:
+//
+//   phase A  the samples PLACED on this rank (those whose user row it owns: user rows never cross NVLink; the
+//            step's global batch is the same set of samples whichever rank runs which).  A row group (dim/4
+//            lanes) per sample; the rows of up to 8 samples per group are in flight at once (cp.async straight
+//            from the owner's HBM -- local or peer -- into thread-private shared-memory slots).  Both scores,
+//            the hinge with g = [h >= 0] / B_global, and each lookup's gradient row goes straight into its
+//            OWNER's staging buffer at slot = the lookup's position in the global batch (remote store).
+//   cross-rank barrier: per rank a grid barrier, then its last CTA posts the barrier number into every peer's
+//            flag words (st.release.sys after __threadfence_system) and everybody waits for W flags locally.
+//   phase B  every owner walks the (local row, slot) pairs of the lookups it owns -- stably sorted by row: the
+//            plan, built once per epoch -- sums the staged rows of a row in slot order (what coalesce() gives,
+//            deterministic), applies SGD / Adagrad / SparseAdam to parameter + state rows of ITS shard.
+//   cross-rank barrier (updates visible before the next step's reads).
+//
+// HBM per step and rank: each owned touched row's parameter + state read once and written once, the staged
+// gradient rows written (by NVLink or locally) and read once, ids.  NVLink per step and rank: 2 item rows in and
+// 2 gradient rows out per sample whose item lives elsewhere ((W-1)/W of them).
+//
+// One GPU can host all W ranks of a group in ONE cooperative launch (n_local = W, the SMs split between the
+// ranks): that is how the parity tests run on a single-GPU box -- kernels that wait on each other must never be
+// separate launches on one device.
+#include <cuda.h>
+#include <string.h>
+
+#include "plan.cuh"
+#include "scorer.cuh"
+#include "train.cuh"
+
+namespace trs {
+
+// ------------------------------------------------------------------------------------------------------------
+// plan: sample placement + the owner's sorted (local row, slot) pairs
+// ------------------------------------------------------------------------------------------------------------
+struct ShardPlanLayout {
+    size_t samp_cnt;  // [steps]      samples placed on this rank
+    size_t own_cnt;   // [steps][2]   lookups this rank owns: user space, item space
+    size_t samp;      // [n]          step s at s*B: position b of each placed sample in the step, ascending
+    size_t ukey, uval;  // [n]        sorted (local row, slot) pairs of the owned user lookups; step s at s*B
+    size_t ikey, ival;  // [2n]       ... item lookups (slot b: positive of sample b, B_s + b: its negative); 2*s*B
+    size_t total;
+};
+static ShardPlanLayout shard_plan_layout(int64_t n, int B) {
+    ShardPlanLayout L;
+    size_t off = 0;
+    auto take = [&](size_t n_elems) {
+        size_t o = off;
+        off += (n_elems * sizeof(uint32_t) + 255) / 256 * 256;
+        return o;
+    };
+    const int64_t steps = (n + B - 1) / B;
+    L.samp_cnt = take((size_t)steps);
+    L.own_cnt = take((size_t)2 * steps);
+    L.samp = take((size_t)n);
+    L.ukey = take((size_t)n);
+    L.uval = take((size_t)n);
+    L.ikey = take((size_t)2 * n);
+    L.ival = take((size_t)2 * n);
+    L.total = off;
+    return L;
+}
+
+constexpr int RT_THREADS = 256;
+constexpr int RT_ROWS = 8;
+constexpr int RT_TILE = RT_THREADS * RT_ROWS;
+
+__device__ __forceinline__ uint32_t route_id(const int64_t* a, const int64_t* b, int64_t s0, int Bs, int j) {
+    return (uint32_t)((j < Bs) ? a[s0 + j] : b[s0 + j - Bs]);
+}
+
+// lookups of every tile that this rank owns
+__global__ void __launch_bounds__(RT_THREADS)
+route_count_kernel(const int64_t* __restrict__ a, const int64_t* __restrict__ b, int mult, int64_t n_samples, int B,
+                   uint32_t world, uint32_t rank, uint32_t* __restrict__ tile_cnt, int tiles) {
+    __shared__ uint32_t s_w[RT_THREADS / 32];
+    const int64_t step = blockIdx.y;
+    const int tile = blockIdx.x;
+    const int Bs = (int)min((int64_t)B, n_samples - step * B);
+    const int len = mult * Bs;
+    const int64_t s0 = step * (int64_t)B;
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int r = 0; r < RT_ROWS; ++r) {
+        const int j = tile * RT_TILE + r * RT_THREADS + threadIdx.x;
+        if (j < len) cnt += (route_id(a, b, s0, Bs, j) % world == rank) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < RT_THREADS / 32; ++w) t += s_w[w];
+        tile_cnt[step * tiles + tile] = t;
+    }
+}
+
+// stable compaction of the owned lookups of a step: (local row, slot) pairs in slot order
+__global__ void __launch_bounds__(RT_THREADS)
+route_scatter_kernel(const int64_t* __restrict__ a, const int64_t* __restrict__ b, int mult, int64_t n_samples, int B,
+                     uint32_t world, uint32_t rank, const uint32_t* __restrict__ tile_cnt, int tiles,
+                     uint32_t* __restrict__ out_key, uint32_t* __restrict__ out_val, uint32_t* __restrict__ samp,
+                     uint32_t* __restrict__ own_cnt, uint32_t* __restrict__ samp_cnt) {
+    __shared__ uint32_t s_w[RT_THREADS / 32];
+    __shared__ uint32_t s_base;
+    const int64_t step = blockIdx.y;
+    const int tile = blockIdx.x;
+    const int Bs = (int)min((int64_t)B, n_samples - step * B);
+    const int len = mult * Bs;
+    const int64_t s0 = step * (int64_t)B;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // pairs of the tiles before mine (tile 0 also publishes the step's total)
+    {
+        uint32_t before = 0, total = 0;
+        for (int t = threadIdx.x; t < tiles; t += RT_THREADS) {
+            const uint32_t c = tile_cnt[step * tiles + t];
+            total += c;
+            if (t < tile) before += c;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            before += __shfl_xor_sync(0xffffffffu, before, o);
+            total += __shfl_xor_sync(0xffffffffu, total, o);
+        }
+        __shared__ uint32_t s_b[RT_THREADS / 32], s_t[RT_THREADS / 32];
+        if (lane == 0) { s_b[warp] = before; s_t[warp] = total; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t bb = 0, tt = 0;
+            for (int w = 0; w < RT_THREADS / 32; ++w) { bb += s_b[w]; tt += s_t[w]; }
+            s_base = bb;
+            if (tile == 0) {
+                own_cnt[step * 2] = tt;
+                if (samp_cnt) samp_cnt[step] = tt;
+            }
+        }
+        __syncthreads();
+    }
+    uint32_t run = s_base;
+    const int64_t seg = (int64_t)mult * step * B;
+    for (int r = 0; r < RT_ROWS; ++r) {
+        const int j = tile * RT_TILE + r * RT_THREADS + threadIdx.x;
+        uint32_t id = 0;
+        bool own = false;
+        if (j < len) {
+            id = route_id(a, b, s0, Bs, j);
+            own = (id % world) == rank;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, own);
+        if (lane == 0) s_w[warp] = __popc(m);
+        __syncthreads();
+        uint32_t wbase = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < RT_THREADS / 32; ++w) {
+            const uint32_t c = s_w[w];
+            if (w < warp) wbase += c;
+            tot += c;
+        }
+        if (own) {
+            const uint32_t p = run + wbase + __popc(m & ((1u << lane) - 1u));
+            out_key[seg + p] = id / world;
+            out_val[seg + p] = (uint32_t)j;
+            if (samp) samp[s0 + p] = (uint32_t)j;
+        }
+        run += tot;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SH_SB = 8;  // samples whose rows are in flight per row group in phase A
+
+struct ShardCtx {  // everything one (virtual) rank needs; copied to shared memory by each of its CTAs
+    int rank, world, dim, pad;
+    trs_table user[TRS_MAX_RANKS];
+    trs_table item[TRS_MAX_RANKS];
+    float* stage_u[TRS_MAX_RANKS];  // [B, dim]   gradient rows of the user lookups, slot = sample position in the step
+    float* stage_i[TRS_MAX_RANKS];  // [2B, dim]  positives then negatives
+    float* stage_b[TRS_MAX_RANKS];  // [2B]       d item_bias
+    unsigned* sync[TRS_MAX_RANKS];
+    const uint32_t *samp_cnt, *own_cnt, *samp, *ukey, *uval, *ikey, *ival;
+    float* loss_part;  // [n_steps][cta_per_rank]
+    float* loss_out;   // [n_steps]
+    int* status;
+};
+
+// sync words of one rank: word 0 = its own grid-barrier counter (memset before every launch: no peer touches it),
+// word 64 + 32 * q = the number of the last cross-rank barrier rank q has reached (monotonic over launches)
+__device__ __forceinline__ unsigned* flag_of(unsigned* sync, int q) { return sync + 64 + 32 * q; }
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long shard_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)::"memory");
+    return t;
+}
+__device__ __forceinline__ void sh_cp_async16(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void sh_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// at most n copy groups still pending (n is a compile-time constant after unrolling)
+__device__ __forceinline__ void sh_cp_async_wait(int n) {
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+    }
+}
+
+template <int IT>
+constexpr int shard_threads() { return IT == 1 ? 512 : (IT == 2 ? 256 : 128); }
+template <int IT>
+constexpr size_t shard_smem_bytes() { return (size_t)shard_threads<IT>() * SH_SB * 3 * IT * 16; }
+
+// Cross-rank barrier number e (1-based over the life of the group).  Every CTA of the rank arrives on the rank's
+// own counter; the last one posts e into every rank's flag words; everybody waits until all W flags of ITS OWN
+// sync words have reached e.  Writes of all threads (including stores into peer memory) happen-before the flag:
+// bar.sync -> thread 0: fence.sys -> atomic -> (last CTA) fence.sys -> st.release.sys.
+__device__ __forceinline__ void cross_rank_barrier(const ShardCtx& C, unsigned e, unsigned local_target,
+                                                   unsigned long long timeout_ns) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned* mine = C.sync[C.rank];
+        __threadfence_system();
+        const unsigned old = atomicAdd(mine, 1u);
+        if (old + 1u == local_target) {
+            __threadfence_system();
+            for (int q = 0; q < C.world; ++q) st_release_sys(flag_of(C.sync[q], C.rank), e);
+        }
+        volatile int* status = C.status;
+        const unsigned long long t0 = shard_now_ns();
+        for (int q = 0; q < C.world; ++q) {
+            const unsigned* f = flag_of(mine, q);
+            unsigned spins = 0;
+            while ((int)(ld_acquire_sys(f) - e) < 0) {
+                if ((++spins & 1023u) == 0) {
+                    if (*status != 0) break;
+                    if (shard_now_ns() - t0 > timeout_ns) {
+                        atomicExch(C.status, 1);
+                        break;
+                    }
+                }
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
+template <int IT>
+__device__ __forceinline__ void sh_update_store(const trs_table& t, size_t roff, int nch, int gl, int G_,
+                                                const OptScalars& o, float scale, Row<4, IT>& p, Row<4, IT>& s0,
+                                                Row<4, IT>& s1, const Row<4, IT>& g) {
+#pragma unroll
+    for (int a = 0; a < IT; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) opt_update(o, scale, g.c[a][b], p.c[a][b], s0.c[a][b], s1.c[a][b]);
+#pragma unroll
+    for (int a = 0; a < IT; ++a) {
+        const int c = gl + a * G_;
+        if (c < nch) {
+            p.c[a].st(t.emb + roff + (size_t)c * 4);
+            if (o.kind != TRS_OPT_SGD) s0.c[a].st(t.emb_s0 + roff + (size_t)c * 4);
+            if (o.kind == TRS_OPT_SPARSE_ADAM) s1.c[a].st(t.emb_s1 + roff + (size_t)c * 4);
+        }
+    }
+}
+
+template <int G, int IT>
+__global__ void __launch_bounds__((shard_threads<IT>()), 1)
+shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __restrict__ ctxs, const int cpr,
+                   const __grid_constant__ trs_epoch ep, const __grid_constant__ OptScalars opt, const int first_step,
+                   const int n_steps, const unsigned sync_epoch, const unsigned long long timeout_ns) {
+    constexpr int NT = shard_threads<IT>();
+    constexpr int GPB = NT / G, GPW = 32 / G;
+    constexpr int RPL = (SH_SB + G - 1) / G;  // sample records a lane fetches per round
+    __shared__ ShardCtx C;
+    __shared__ float s_loss[NT / 32];
+    extern __shared__ __align__(16) unsigned char sh_smem[];
+    float4* rows = reinterpret_cast<float4*>(sh_smem);  // [SH_SB][3][IT][NT], thread-private slots
+
+    const int vr = blockIdx.x / cpr, c = blockIdx.x % cpr;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(ctxs ? ctxs + vr : &ctx0);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&C);
+        for (int i = threadIdx.x; i < (int)(sizeof(ShardCtx) / 4); i += NT) dst[i] = src[i];
+    }
+    __syncthreads();
+    const uint32_t W = (uint32_t)C.world;
+    const int me = C.rank, dim = C.dim, nch = dim / 4;
+    const int gl = threadIdx.x % G, g_in_cta = threadIdx.x / G;
+    const int gfirst = c * GPB + g_in_cta, gstride = cpr * GPB;
+    const int goff = g_in_cta % GPW;  // my group's position inside its warp: loops run on the warp's first group
+    const int kind = opt.kind;
+    auto slot = [&](int i, int r, int a) { return rows + (((i * 3 + r) * IT + a) * NT + threadIdx.x); };
+    auto slot_row = [&](int i, int r) {
+        Row<4, IT> x;
+#pragma unroll
+        for (int a = 0; a < IT; ++a) {
+            x.c[a] = Vec<4>::zero();
+            if (gl + a * G < nch) x.c[a].v = *slot(i, r, a);
+        }
+        return x;
+    };
+    auto ld_row = [&](const float* base) { return load_row_cg<4, G, IT>(base, nch, gl); };
+    unsigned bar_no = 0;  // cross-rank barriers passed in this launch
+
+    for (int si = 0; si < n_steps; ++si) {
+        const int64_t s = first_step + si;
+        const int64_t lo = s * (int64_t)ep.batch;
+        const int Bs = (int)min((int64_t)ep.batch, ep.n_samples - lo);
+        const float invB = 1.0f / (float)Bs;
+        const float scale = opt.step_scale[s];
+
+        // ------------------------------ phase A ------------------------------------------
+        float hsum = 0.f;
+        {
+            const int nS = (int)C.samp_cnt[s];
+            const uint32_t* samp = C.samp + lo;
+            for (int k0 = gfirst - goff; k0 < nS; k0 += gstride * SH_SB) {  // warp-uniform trip count
+                const int kb = k0 + goff;
+                // records of this round's samples: lane gl fetches samples gl, gl + G, ... of the round
+                uint32_t rb[RPL], ru[RPL], rp[RPL], rn[RPL];
+#pragma unroll
+                for (int z = 0; z < RPL; ++z) {
+                    const int i = gl + z * G;
+                    const int k = kb + i * gstride;
+                    rb[z] = 0xFFFFFFFFu;
+                    ru[z] = rp[z] = rn[z] = 0u;
+                    if (i < SH_SB && k < nS) {
+                        const uint32_t b = __ldg(samp + k);
+                        rb[z] = b;
+                        ru[z] = (uint32_t)ep.user[lo + b];
+                        rp[z] = (uint32_t)ep.pos[lo + b];
+                        rn[z] = (uint32_t)ep.neg[lo + b];
+                    }
+                }
+                float bias_r[SH_SB];  // lane t < 3 holds the width-1 companion of lookup t (user, positive, negative)
+#pragma unroll
+                for (int i = 0; i < SH_SB; ++i) {
+                    const uint32_t b = __shfl_sync(0xffffffffu, rb[i / G], i % G, G);
+                    const uint32_t u = __shfl_sync(0xffffffffu, ru[i / G], i % G, G);
+                    const uint32_t ip = __shfl_sync(0xffffffffu, rp[i / G], i % G, G);
+                    const uint32_t in = __shfl_sync(0xffffffffu, rn[i / G], i % G, G);
+                    bias_r[i] = 0.f;
+                    if (b != 0xFFFFFFFFu) {
+                        const uint32_t qu = u % W, qp = ip % W, qn = in % W;
+                        const size_t ou = (size_t)(u / W) * dim, op = (size_t)(ip / W) * dim, on = (size_t)(in / W) * dim;
+                        const float* pu = C.user[qu].emb + ou;
+                        const float* pp = C.item[qp].emb + op;
+                        const float* pn = C.item[qn].emb + on;
+#pragma unroll
+                        for (int a = 0; a < IT; ++a) {
+                            const int ch = gl + a * G;
+                            if (ch < nch) {
+                                sh_cp_async16(slot(i, 0, a), pu + (size_t)ch * 4);
+                                sh_cp_async16(slot(i, 1, a), pp + (size_t)ch * 4);
+                                sh_cp_async16(slot(i, 2, a), pn + (size_t)ch * 4);
+                            }
+                        }
+                        if (gl < 3) {
+                            const float* lin = gl == 0 ? C.user[qu].lin : (gl == 1 ? C.item[qp].lin : C.item[qn].lin);
+                            const uint32_t lrow = gl == 0 ? u / W : (gl == 1 ? ip / W : in / W);
+                            if (lin) bias_r[i] = __ldcg(lin + lrow);
+                        }
+                    }
+                    sh_cp_async_commit();
+                }
+#pragma unroll
+                for (int i = 0; i < SH_SB; ++i) {
+                    sh_cp_async_wait(SH_SB - 1 - i);
+                    const uint32_t b = __shfl_sync(0xffffffffu, rb[i / G], i % G, G);
+                    const uint32_t ip = __shfl_sync(0xffffffffu, rp[i / G], i % G, G);
+                    const uint32_t in = __shfl_sync(0xffffffffu, rn[i / G], i % G, G);
+                    const uint32_t u = __shfl_sync(0xffffffffu, ru[i / G], i % G, G);
+                    const bool valid = b != 0xFFFFFFFFu;
+                    Row<4, IT> xu, xp, xn;
+                    if (valid) {
+                        xu = slot_row(i, 0);
+                        xp = slot_row(i, 1);
+                        xn = slot_row(i, 2);
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < IT; ++a) xu.c[a] = xp.c[a] = xn.c[a] = Vec<4>::zero();
+                    }
+                    const float bu = __shfl_sync(0xffffffffu, bias_r[i], 0, G);
+                    const float bip = __shfl_sync(0xffffffffu, bias_r[i], 1, G);
+                    const float bin = __shfl_sync(0xffffffffu, bias_r[i], 2, G);
+                    // linear.py:78: s = <u, v> + b_u + b_i; loss.py:7-9: h = s- - s+ + 1, d/ds = [h >= 0] / B
+                    const float sp = (group_sum<G>(row_dot_partial(xu, xp)) + bu) + bip;
+                    const float sn = (group_sum<G>(row_dot_partial(xu, xn)) + bu) + bin;
+                    const float h = __fadd_rn(__fsub_rn(sn, sp), 1.0f);
+                    const float g = (h >= 0.f) ? invB : 0.f;
+                    if (valid) {
+                        if (gl == 0) hsum += fmaxf(h, 0.f);
+                        const uint32_t qu = u % W, qp = ip % W, qn = in % W;
+                        float* du = C.stage_u[qu] + (size_t)b * dim;
+                        float* dp = C.stage_i[qp] + (size_t)b * dim;
+                        float* dn = C.stage_i[qn] + (size_t)(Bs + b) * dim;
+#pragma unroll
+                        for (int a = 0; a < IT; ++a) {
+                            const int ch = gl + a * G;
+                            if (ch < nch) {
+                                Vec<4> gu, gp, gn;
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    gu[e] = g * (xn.c[a][e] - xp.c[a][e]);
+                                    gp[e] = -g * xu.c[a][e];
+                                    gn[e] = g * xu.c[a][e];
+                                }
+                                gu.st(du + (size_t)ch * 4);
+                                gp.st(dp + (size_t)ch * 4);
+                                gn.st(dn + (size_t)ch * 4);
+                            }
+                        }
+                        if (gl == 0) {
+                            C.stage_b[qp][b] = -g;
+                            C.stage_b[qn][Bs + b] = g;
+                        }
+                    }
+                }
+            }
+        }
+        hsum = warp_sum(hsum);
+        if ((threadIdx.x & 31) == 0) s_loss[threadIdx.x >> 5] = hsum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float H = 0.f;
+#pragma unroll
+            for (int w = 0; w < NT / 32; ++w) H += s_loss[w];
+            C.loss_part[(size_t)si * cpr + c] = H;
+        }
+        ++bar_no;
+        cross_rank_barrier(C, sync_epoch + bar_no, bar_no * (unsigned)cpr, timeout_ns);
+
+        // ------------------------------ phase B ------------------------------------------
+        // owned rows: a row group takes sorted position k; only the first position of a run of equal rows works
+#pragma unroll 1
+        for (int space = 0; space < 2; ++space) {
+            const trs_table& t = space ? C.item[me] : C.user[me];
+            const int mult = space ? 2 : 1;
+            const uint32_t* K = (space ? C.ikey : C.ukey) + (size_t)mult * lo;
+            const uint32_t* P = (space ? C.ival : C.uval) + (size_t)mult * lo;
+            const int n = (int)C.own_cnt[2 * s + space];
+            const float* stage = space ? C.stage_i[me] : C.stage_u[me];
+            const float* stage_b = (space && t.lin) ? C.stage_b[me] : nullptr;
+            struct Seg {
+                bool head;
+                int k;
+                uint32_t key;
+                Row<4, IT> g, p, s0, s1;
+                float gb, pl, l0, l1;
+            };
+            auto seg_load = [&](Seg& S, int k) {
+                S.head = false;
+                S.k = k;
+                if (k >= n) return;
+                const uint32_t key = K[k];
+                if (k > 0 && K[k - 1] == key) return;
+                S.head = true;
+                S.key = key;
+                const uint32_t j = P[k];
+                const size_t roff = (size_t)key * dim;
+                S.g = ld_row(stage + (size_t)j * dim);
+                S.p = ld_row(t.emb + roff);
+#pragma unroll
+                for (int a = 0; a < IT; ++a) S.s0.c[a] = S.s1.c[a] = Vec<4>::zero();
+                if (kind != TRS_OPT_SGD) S.s0 = ld_row(t.emb_s0 + roff);
+                if (kind == TRS_OPT_SPARSE_ADAM) S.s1 = ld_row(t.emb_s1 + roff);
+                S.gb = S.pl = S.l0 = S.l1 = 0.f;
+                if (stage_b && gl == 0) {
+                    S.gb = __ldcg(stage_b + j);
+                    S.pl = __ldcg(t.lin + key);
+                    if (kind != TRS_OPT_SGD) S.l0 = __ldcg(t.lin_s0 + key);
+                    if (kind == TRS_OPT_SPARSE_ADAM) S.l1 = __ldcg(t.lin_s1 + key);
+                }
+            };
+            auto seg_finish = [&](Seg& S) {
+                if (!S.head) return;
+                for (int q = S.k + 1; q < n && K[q] == S.key; ++q) {  // duplicates, in slot order
+                    const uint32_t j = P[q];
+                    const Row<4, IT> r = ld_row(stage + (size_t)j * dim);
+#pragma unroll
+                    for (int a = 0; a < IT; ++a)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) S.g.c[a][e] = __fadd_rn(S.g.c[a][e], r.c[a][e]);
+                    if (stage_b && gl == 0) S.gb = __fadd_rn(S.gb, __ldcg(stage_b + j));
+                }
+                sh_update_store<IT>(t, (size_t)S.key * dim, nch, gl, G, opt, scale, S.p, S.s0, S.s1, S.g);
+                if (stage_b && gl == 0) {
+                    opt_update(opt, scale, S.gb, S.pl, S.l0, S.l1);
+                    t.lin[S.key] = S.pl;
+                    if (kind != TRS_OPT_SGD) t.lin_s0[S.key] = S.l0;
+                    if (kind == TRS_OPT_SPARSE_ADAM) t.lin_s1[S.key] = S.l1;
+                }
+            };
+            for (int k = gfirst; k < n; k += 2 * gstride) {  // two rows in flight per group
+                Seg A, B_;
+                seg_load(A, k);
+                seg_load(B_, k + gstride);
+                seg_finish(A);
+                seg_finish(B_);
+            }
+        }
+        ++bar_no;
+        cross_rank_barrier(C, sync_epoch + bar_no, bar_no * (unsigned)cpr, timeout_ns);
+    }
+
+    // per-step hinge sums of this rank, CTAs added in a fixed order
+    if (c == 0) {
+        for (int si = threadIdx.x; si < n_steps; si += NT) {
+            float H = 0.f;
+            for (int q = 0; q < cpr; ++q) H += __ldcg(C.loss_part + (size_t)si * cpr + q);
+            C.loss_out[si] = H;
+        }
+    }
+}
+
+struct ShardStage {
+    size_t gU, gI, gb, total;
+};
+static ShardStage shard_stage_layout(int dim, int64_t B) {
+    ShardStage L;
+    size_t off = 0;
+    auto take = [&](size_t n_floats) {
+        size_t o = off;
+        off += (n_floats * sizeof(float) + 255) / 256 * 256;
+        return o;
+    };
+    L.gU = take((size_t)B * dim);
+    L.gI = take((size_t)2 * B * dim);
+    L.gb = take((size_t)2 * B);
+    L.total = off;
+    return L;
+}
+
+template <int G, int IT>
+static cudaError_t launch_shard(const ShardCtx* ctx0, const ShardCtx* ctxs, int cpr, int n_local, const trs_epoch* ep,
+                                const OptScalars* os, int first_step, int n_steps, unsigned sync_epoch,
+                                unsigned long long timeout_ns, cudaStream_t stream) {
+    const void* fn = (const void*)shard_train_kernel<G, IT>;
+    const size_t smem = shard_smem_bytes<IT>();
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    void* args[] = {(void*)ctx0, (void*)&ctxs, (void*)&cpr, (void*)ep, (void*)os, (void*)&first_step,
+                    (void*)&n_steps, (void*)&sync_epoch, (void*)&timeout_ns};
+    return cudaLaunchCooperativeKernel(fn, dim3(cpr * n_local), dim3(shard_threads<IT>()), args, smem, stream);
+}
+
+static int check_shard(const trs_shard* sh, RowShape* shape) {
+    TRS_REQUIRE(sh != nullptr, "shard is NULL");
+    TRS_REQUIRE(sh->world >= 1 && sh->world <= TRS_MAX_RANKS, "world %d outside 1..%d", sh->world, TRS_MAX_RANKS);
+    TRS_REQUIRE(sh->rank >= 0 && sh->rank < sh->world, "rank %d outside the group of %d", sh->rank, sh->world);
+    TRS_REQUIRE(sh->dim > 0 && sh->dim % 4 == 0 && pick_row_shape(sh->dim, shape),
+                "row-sharded training needs n_factors to be a multiple of 4 up to 512 (got %d)", sh->dim);
+    TRS_REQUIRE(sh->n_users > 0 && sh->n_users <= 0xFFFFFFFFll && sh->n_items > 0 && sh->n_items <= 0xFFFFFFFFll,
+                "n_users / n_items out of range");
+    return TRS_OK;
+}
+
+}  // namespace trs
+
+using namespace trs;
+
+extern "C" size_t trs_shard_stage_bytes(int dim, int global_batch) {
+    if (dim <= 0 || global_batch <= 0) return 0;
+    return shard_stage_layout(dim, global_batch).total;
+}
+
+extern "C" size_t trs_shard_plan_bytes(const trs_epoch* ep) {
+    if (!ep || ep->batch <= 0) return 0;
+    return shard_plan_layout(ep->n_samples, ep->batch).total;
+}
+
+static size_t shard_tmp_pairs_bytes(const trs_epoch* ep) {
+    return ((size_t)4 * ep->n_samples * sizeof(uint32_t) + 511) / 256 * 256;
+}
+static int route_tiles(const trs_epoch* ep) { return (int)((2ll * ep->batch + RT_TILE - 1) / RT_TILE); }
+
+extern "C" size_t trs_shard_plan_tmp_bytes(const trs_epoch* ep) {
+    if (!ep || ep->batch <= 0) return 0;
+    const size_t tile_cnt = ((size_t)n_steps_of(ep) * route_tiles(ep) * sizeof(uint32_t) + 255) / 256 * 256;
+    return shard_tmp_pairs_bytes(ep) + tile_cnt + hist_bytes(ep);
+}
+
+extern "C" int trs_shard_plan_build(const trs_shard* sh, const trs_epoch* ep, void* plan, size_t plan_bytes,
+                                    void* tmp, size_t tmp_bytes, trs_stream_t stream) {
+    RowShape shape;
+    int rc = check_shard(sh, &shape);
+    if (rc) return rc;
+    TRS_REQUIRE(ep && ep->user && ep->pos && ep->neg, "epoch ids are NULL");
+    TRS_REQUIRE(ep->batch > 0 && ep->batch <= (1 << 29), "global batch out of range");
+    TRS_REQUIRE(ep->pos_meta == nullptr && ep->neg_meta == nullptr, "row-sharded training does not take metadata");
+    TRS_REQUIRE(plan && tmp, "plan / tmp is NULL");
+    if (ep->n_samples == 0) return TRS_OK;
+    TRS_REQUIRE(n_steps_of(ep) <= 65535, "shard_plan_build: %lld steps in one call (limit 65535)", (long long)n_steps_of(ep));
+    const ShardPlanLayout L = shard_plan_layout(ep->n_samples, ep->batch);
+    if (plan_bytes < L.total || tmp_bytes < trs_shard_plan_tmp_bytes(ep)) {
+        set_error("shard plan workspace too small: plan %zu < %zu or tmp %zu < %zu", plan_bytes, L.total, tmp_bytes,
+                  trs_shard_plan_tmp_bytes(ep));
+        return TRS_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char* P = (char*)plan;
+    const int64_t n = ep->n_samples, steps = n_steps_of(ep);
+    uint32_t* tkey = (uint32_t*)tmp;
+    uint32_t* tval = tkey + 2 * n;
+    uint32_t* tile_cnt = (uint32_t*)((char*)tmp + shard_tmp_pairs_bytes(ep));
+    uint32_t* hist = (uint32_t*)((char*)tile_cnt + ((size_t)steps * route_tiles(ep) * sizeof(uint32_t) + 255) / 256 * 256);
+    uint32_t* samp_cnt = (uint32_t*)(P + L.samp_cnt);
+    uint32_t* own_cnt = (uint32_t*)(P + L.own_cnt);
+    uint32_t* samp = (uint32_t*)(P + L.samp);
+    const uint32_t W = (uint32_t)sh->world, r = (uint32_t)sh->rank;
+    auto rows_of = [&](int64_t n_rows) { return (n_rows + W - 1) / W; };
+
+    auto space = [&](const int64_t* a, const int64_t* b, int mult, int64_t n_rows, uint32_t* key, uint32_t* val,
+                     int sp) -> int {
+        const int tiles = (int)(((int64_t)mult * ep->batch + RT_TILE - 1) / RT_TILE);
+        dim3 grid((unsigned)tiles, (unsigned)steps);
+        route_count_kernel<<<grid, RT_THREADS, 0, st>>>(a, b, mult, n, ep->batch, W, r, tile_cnt, tiles);
+        // an odd number of radix passes ends in the other buffer: start there so the result lands in the plan
+        const int npass = sort_passes(rows_of(n_rows));
+        uint32_t* k0 = (npass & 1) ? tkey : key;
+        uint32_t* v0 = (npass & 1) ? tval : val;
+        uint32_t* k1 = (npass & 1) ? key : tkey;
+        uint32_t* v1 = (npass & 1) ? val : tval;
+        route_scatter_kernel<<<grid, RT_THREADS, 0, st>>>(a, b, mult, n, ep->batch, W, r, tile_cnt, tiles, k0, v0,
+                                                         sp == 0 ? samp : nullptr, own_cnt + sp,
+                                                         sp == 0 ? samp_cnt : nullptr);
+        sort_pairs(k0, v0, k1, v1, mult, rows_of(n_rows), ep, own_cnt + sp, 2, hist, st);
+        return TRS_OK;
+    };
+    space(ep->user, ep->user, 1, sh->n_users, (uint32_t*)(P + L.ukey), (uint32_t*)(P + L.uval), 0);
+    space(ep->pos, ep->neg, 2, sh->n_items, (uint32_t*)(P + L.ikey), (uint32_t*)(P + L.ival), 1);
+    TRS_CUDA(cudaGetLastError());
+    return TRS_OK;
+}
+
+static int shard_cpr(int n_local) { return device_props().sm_count / (n_local > 0 ? n_local : 1); }
+
+extern "C" size_t trs_shard_workspace_bytes(const trs_epoch* ep, int n_local) {
+    if (!ep || ep->batch <= 0 || n_local < 1 || n_local > TRS_MAX_RANKS) return 0;
+    const size_t ctx = ((size_t)n_local * sizeof(ShardCtx) + 255) / 256 * 256;
+    const size_t part = ((size_t)n_local * n_steps_of(ep) * shard_cpr(n_local) * sizeof(float) + 255) / 256 * 256;
+    return ctx + part;
+}
+
+extern "C" int trs_shard_train_steps(const trs_shard* shards, int n_local, const trs_epoch* ep, const trs_optim* optim,
+                                     const void* const* plans_host, void* workspace, size_t workspace_bytes,
+                                     int first_step, int n_steps, uint64_t sync_epoch, float* const* loss_sum_host,
+                                     int32_t* status, int timeout_ms, trs_stream_t stream) {
+    TRS_REQUIRE(shards && n_local >= 1 && n_local <= TRS_MAX_RANKS, "shard_train_steps: n_local out of range");
+    TRS_REQUIRE(n_local == 1 || n_local == shards[0].world,
+                "shard_train_steps: one launch hosts either one rank or the whole group");
+    TRS_REQUIRE(ep && ep->user && ep->pos && ep->neg && ep->batch > 0, "epoch ids are NULL");
+    TRS_REQUIRE(optim && optim->step_scale, "optimizer / step_scale is NULL");
+    TRS_REQUIRE(optim->kind >= TRS_OPT_SGD && optim->kind <= TRS_OPT_SPARSE_ADAM, "unknown optimizer kind %d", optim->kind);
+    TRS_REQUIRE(plans_host && workspace && loss_sum_host && status, "plans / workspace / loss / status is NULL");
+    const int64_t steps = n_steps_of(ep);
+    TRS_REQUIRE(first_step >= 0 && n_steps >= 0 && first_step + (int64_t)n_steps <= steps,
+                "steps [%d, %d) outside the epoch's %lld steps", first_step, first_step + n_steps, (long long)steps);
+    if (n_steps == 0) return TRS_OK;
+    if (workspace_bytes < trs_shard_workspace_bytes(ep, n_local)) {
+        set_error("shard workspace too small: %zu < %zu", workspace_bytes, trs_shard_workspace_bytes(ep, n_local));
+        return TRS_ERR_WORKSPACE;
+    }
+    RowShape shape;
+    const int cpr = shard_cpr(n_local);
+    TRS_REQUIRE(cpr >= 1, "more local ranks than SMs");
+    const ShardPlanLayout PL = shard_plan_layout(ep->n_samples, ep->batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    ShardCtx ctx[TRS_MAX_RANKS];
+    const size_t ctx_bytes = ((size_t)n_local * sizeof(ShardCtx) + 255) / 256 * 256;
+    float* loss_part = (float*)((char*)workspace + ctx_bytes);
+    for (int i = 0; i < n_local; ++i) {
+        const trs_shard& sh = shards[i];
+        int rc = check_shard(&sh, &shape);
+        if (rc) return rc;
+        TRS_REQUIRE(sh.world == shards[0].world && sh.dim == shards[0].dim, "local ranks disagree on world / dim");
+        const ShardStage SL = shard_stage_layout(sh.dim, ep->batch);
+        ShardCtx& c = ctx[i];
+        memset(&c, 0, sizeof(c));
+        c.rank = sh.rank;
+        c.world = sh.world;
+        c.dim = sh.dim;
+        for (int q = 0; q < sh.world; ++q) {
+            TRS_REQUIRE(sh.user[q].emb && sh.item[q].emb && sh.stage[q] && sh.sync[q], "rank %d: peer %d is not mapped",
+                        sh.rank, q);
+            c.user[q] = sh.user[q];
+            c.item[q] = sh.item[q];
+            c.stage_u[q] = (float*)((char*)sh.stage[q] + SL.gU);
+            c.stage_i[q] = (float*)((char*)sh.stage[q] + SL.gI);
+            c.stage_b[q] = (float*)((char*)sh.stage[q] + SL.gb);
+            c.sync[q] = (unsigned*)sh.sync[q];
+        }
+        const trs_table& mu = sh.user[sh.rank];
+        const trs_table& mi = sh.item[sh.rank];
+        if (optim->kind != TRS_OPT_SGD)
+            TRS_REQUIRE(mu.emb_s0 && mi.emb_s0 && (!mi.lin || mi.lin_s0), "rank %d: optimizer state s0 is NULL", sh.rank);
+        if (optim->kind == TRS_OPT_SPARSE_ADAM)
+            TRS_REQUIRE(mu.emb_s1 && mi.emb_s1 && (!mi.lin || mi.lin_s1), "rank %d: optimizer state s1 is NULL", sh.rank);
+        TRS_REQUIRE(plans_host[i] && loss_sum_host[i], "rank %d: plan / loss is NULL", sh.rank);
+        const char* P = (const char*)plans_host[i];
+        c.samp_cnt = (const uint32_t*)(P + PL.samp_cnt);
+        c.own_cnt = (const uint32_t*)(P + PL.own_cnt);
+        c.samp = (const uint32_t*)(P + PL.samp);
+        c.ukey = (const uint32_t*)(P + PL.ukey);
+        c.uval = (const uint32_t*)(P + PL.uval);
+        c.ikey = (const uint32_t*)(P + PL.ikey);
+        c.ival = (const uint32_t*)(P + PL.ival);
+        c.loss_part = loss_part + (size_t)i * steps * cpr;
+        c.loss_out = loss_sum_host[i];
+        c.status = status;
+        // the rank's own grid-barrier counter restarts with every launch (peers never touch it)
+        TRS_CUDA(cudaMemsetAsync(sh.sync[sh.rank], 0, sizeof(unsigned), st));
+    }
+    const ShardCtx* ctxs_dev = nullptr;
+    if (n_local > 1) {  // emulation of a whole group on one GPU (tests): contexts travel through the workspace
+        TRS_CUDA(cudaMemcpyAsync(workspace, ctx, (size_t)n_local * sizeof(ShardCtx), cudaMemcpyHostToDevice, st));
+        ctxs_dev = (const ShardCtx*)workspace;
+    }
+    const OptScalars os = make_opt_scalars(optim);
+    const unsigned long long timeout_ns = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 20000) * 1000000ull;
+    cudaError_t err = cudaErrorInvalidValue;
+    const int key = shape.G * 100 + shape.IT;
+    switch (key) {
+        case 401: err = launch_shard<4, 1>(&ctx[0], ctxs_dev, cpr, n_local, ep, &os, first_step, n_steps, (unsigned)sync_epoch, timeout_ns, st); break;
+        case 801: err = launch_shard<8, 1>(&ctx[0], ctxs_dev, cpr, n_local, ep, &os, first_step, n_steps, (unsigned)sync_epoch, timeout_ns, st); break;
+        case 1601: err = launch_shard<16, 1>(&ctx[0], ctxs_dev, cpr, n_local, ep, &os, first_step, n_steps, (unsigned)sync_epoch, timeout_ns, st); break;
+        case 3201: err = launch_shard<32, 1>(&ctx[0], ctxs_dev, cpr, n_local, ep, &os, first_step, n_steps, (unsigned)sync_epoch, timeout_ns, st); break;
+        case 3202: err = launch_shard<32, 2>(&ctx[0], ctxs_dev, cpr, n_local, ep, &os, first_step, n_steps, (unsigned)sync_epoch, timeout_ns, st); break;
+        case 3204: err = launch_shard<32, 4>(&ctx[0], ctxs_dev, cpr, n_local, ep, &os, first_step, n_steps, (unsigned)sync_epoch, timeout_ns, st); break;
+        default: break;
+    }
+    TRS_CUDA(err);
+    return TRS_OK;
+}
+
+// ---- CUDA IPC plumbing ---------------------------------------------------------------------------------------
+extern "C" int trs_ipc_export(const void* ptr, void* handle64_host, uint64_t* offset_host) {
+    TRS_REQUIRE(ptr && handle64_host && offset_host, "ipc_export: NULL pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    typedef CUresult (*range_fn)(CUdeviceptr*, size_t*, CUdeviceptr);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    TRS_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
+    TRS_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "ipc_export: cuMemGetAddressRange is not available");
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    const CUresult cr = ((range_fn)fn)(&base, &size, (CUdeviceptr)ptr);
+    TRS_REQUIRE(cr == CUDA_SUCCESS, "ipc_export: cuMemGetAddressRange failed (%d)", (int)cr);
+    cudaIpcMemHandle_t h;
+    TRS_CUDA(cudaIpcGetMemHandle(&h, (void*)base));
+    memcpy(handle64_host, &h, sizeof(h));
+    *offset_host = (uint64_t)((CUdeviceptr)ptr - base);
+    return TRS_OK;
+}
+
+extern "C" int trs_ipc_open(const void* handle64_host, void** base_host) {
+    TRS_REQUIRE(handle64_host && base_host, "ipc_open: NULL pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64_host, sizeof(h));
+    TRS_CUDA(cudaIpcOpenMemHandle(base_host, h, cudaIpcMemLazyEnablePeerAccess));
+    return TRS_OK;
+}
+
+extern "C" int trs_ipc_close(void* base) {
+    TRS_REQUIRE(base, "ipc_close: NULL pointer");
+    TRS_CUDA(cudaIpcCloseMemHandle(base));
+    return TRS_OK;
+}

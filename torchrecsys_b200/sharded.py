@@ -1,201 +1,315 @@
 """Multi-GPU paths for tables that do not fit (or should not be replicated on) one GPU -- SURVEY.md §8e.
-The reference is single-device (model.py:74, README.md:3); this is new design, one process per GPU,
-``torch.distributed`` (NCCL over NVLink 5 / NVSwitch; gloo in the CPU tests) for the exchange steps.
+The reference is single-device (model.py:74, README.md:3); this is new design: one process per GPU,
+``torch.distributed`` (NCCL; gloo in the CPU tests) for rendezvous, the per-epoch id all-gather and the loss
+all-reduce -- and NO collective on the step path:
 
-Row-sharded training (BASELINE configs[3], Linear 50M x 5M, dim 128)
+Row-sharded training (BASELINE configs[3], Linear 50M x 5M, dim 128)  -- ``ShardedLinearTrainer``
     owner(row) = row % G, local row = row // G  (uniform load under any id skew).
-    Every rank draws its own B samples.  Per step:
-      1. route   the rank's 3B lookups are ordered by (owner, id space); counts go round in one small
-                 all_to_all, the local-row ids in a second
-      2. gather  each OWNER gathers the requested rows + biases of ITS shard (trs_embed_gather_sum) and the
-                 rows travel back in a third all_to_all ([n, dim+1] fp32: row | bias)
-      3. compute trs_linear_rows_step on the rank's samples: forward x2, hinge over the GLOBAL batch
-                 (inv_batch = 1/(G*B)), closed-form gradient row per lookup
-      4. return  gradient rows go to the owners in a fourth all_to_all
-      5. update  each owner runs trs_sparse_row_update on what it received: stable sort by row, duplicates
-                 summed in (rank, lookup) order, SparseAdam / Adagrad / SGD -- so a row looked up from several
-                 ranks is reduced BEFORE the non-linear update, as grad.coalesce() does on one device.
-    No all-reduce of parameters: every row has exactly one owner.
+    Every rank holds its shards, their optimizer state, a gradient staging buffer and a page of barrier words in
+    ONE device allocation (the *arena*) and maps every peer's arena into its own address space by CUDA IPC.
+    ``train_epoch`` takes the GLOBAL epoch (every rank's samples in loader order, identical on all ranks) and runs
+    it as one persistent kernel per rank (csrc/shard.cu): a rank runs the samples whose user row it owns, reads
+    item rows straight from their owner's HBM over NVLink, stores each lookup's gradient row straight into its
+    owner's staging buffer, and every owner coalesces + updates its own rows -- two flag barriers per step.
+    ``state_dict()`` / ``load_state_dict()`` gather / scatter the shards (parameters AND optimizer state) in the
+    reference's single-process layout and key names, so checkpoints interchange with ``TorchRecSys``.
+    One GPU can host the whole group (``emulate_world=G``): the parity tests run that way on a 1-GPU box.
 
 Item-sharded predict (BASELINE configs[4])
     contiguous item blocks per rank (global id = offset + local id, so the single-GPU tie-break "lower item id
     first" carries over), user rows replicated; each rank runs trs_predict_topk on its block, the
     (score, id)[Q, k] lists are all-gathered and merged by trs_topk_merge.
 
-The routing code is plain torch + torch.distributed and device-agnostic; the three compute hooks
-(``gather``, ``compute``, ``update``) are the CUDA kernels in production and torch stand-ins in the gloo tests."""
+The host-driven all_to_all baseline of round 1 lives in ``routed.py``."""
 from __future__ import annotations
 
-from dataclasses import dataclass
-from typing import Callable, List, Optional, Tuple
+from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
+from .engine import OptBinding, step_scales
 
-# ------------------------------------------------------------------------------------------------------
-# routing
-# ------------------------------------------------------------------------------------------------------
-@dataclass
-class Route:
-    order: torch.Tensor        # [n] permutation: lookups sorted by (owner, space)
-    send_splits: List[int]     # lookups this rank sends to each owner (host ints)
-    recv_splits: List[int]     # lookups each rank sends to THIS owner
-    recv_rows: torch.Tensor    # [n_recv] local row ids requested from this owner (rank-major, then space, then lookup order)
-    by_space: torch.Tensor     # [n_recv] permutation grouping the received requests by id space (stable)
-    space_sizes: List[int]     # requests per id space on this owner (host ints)
+_KINDS = {"sgd": 0, "adagrad": 1, "sparse_adam": 2}
+_STATE_KEYS = {"sgd": (), "adagrad": ("sum",), "sparse_adam": ("exp_avg", "exp_avg_sq")}
 
 
-def _a2a(out: torch.Tensor, inp: torch.Tensor, out_splits: List[int], in_splits: List[int], group) -> None:
-    dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
+def shard_rows(n: int, rank: int, world: int) -> int:
+    """Rows r of a table of n with r % world == rank."""
+    return (n - rank + world - 1) // world if n > rank else 0
 
 
-def make_route(ids: torch.Tensor, space: torch.Tensor, n_spaces: int, world: int, group=None) -> Route:
-    """ids: global row ids of this rank's lookups, space: their id space (0 user, 1 item, ...)."""
-    owner = ids % world
-    key = owner * n_spaces + space
-    order = torch.sort(key, stable=True)[1]
-    send_counts = torch.bincount(key, minlength=world * n_spaces).view(world, n_spaces)
-    recv_counts = torch.empty_like(send_counts)
-    dist.all_to_all_single(recv_counts, send_counts, group=group)
-    # the one host synchronisation of a step: all_to_all needs its split sizes on the host
-    counts = torch.stack([send_counts, recv_counts]).cpu()
-    in_splits = counts[0].sum(1).tolist()
-    out_splits = counts[1].sum(1).tolist()
-    recv_rows = torch.empty(sum(out_splits), dtype=ids.dtype, device=ids.device)
-    _a2a(recv_rows, (ids[order] // world).contiguous(), out_splits, in_splits, group)
-    # the space of each received request follows from the counts: per source rank, space 0 block then space 1 ...
-    recv_space = torch.repeat_interleave(torch.arange(n_spaces).repeat(world), counts[1].reshape(-1))
-    by_space = torch.sort(recv_space, stable=True)[1].to(ids.device, non_blocking=True)
-    return Route(order, in_splits, out_splits, recv_rows, by_space, counts[1].sum(0).tolist())
+class _ArenaLayout:
+    """Byte offsets inside a rank's arena -- the same on every rank (shards are sized for ceil(n / world) rows)."""
+
+    def __init__(self, n_users: int, n_items: int, dim: int, n_state: int, world: int, stage_bytes: int, sync_bytes: int):
+        off = 0
+
+        def take(nbytes: int) -> int:
+            nonlocal off
+            o = off
+            off += (nbytes + 255) // 256 * 256
+            return o
+
+        self.rows = {"user": -(-n_users // world), "item": -(-n_items // world)}
+        self.emb, self.emb_state, self.lin, self.lin_state = {}, {}, {}, {}
+        for name in ("user", "item"):
+            r = max(self.rows[name], 1)
+            self.emb[name] = take(r * dim * 4)
+            self.emb_state[name] = [take(r * dim * 4) for _ in range(n_state)]
+            self.lin[name] = take(r * 4)
+            self.lin_state[name] = [take(r * 4) for _ in range(n_state)]
+        self.stage = take(stage_bytes)
+        self.sync = take(sync_bytes)
+        self.total = off
 
 
-def exchange_back(route: Route, payload: torch.Tensor, group=None) -> torch.Tensor:
-    """Owner -> requester: payload[n_recv, W] (one row per received request) -> [n, W] in LOOKUP order."""
-    got = torch.empty((sum(route.send_splits), payload.shape[1]), dtype=payload.dtype, device=payload.device)
-    _a2a(got, payload.contiguous(), route.send_splits, route.recv_splits, group)
-    out = torch.empty_like(got)
-    out[route.order] = got
-    return out
-
-
-def exchange_forward(route: Route, payload: torch.Tensor, group=None) -> torch.Tensor:
-    """Requester -> owner: payload[n, W] in lookup order -> [n_recv, W] aligned with route.recv_rows."""
-    got = torch.empty((sum(route.recv_splits), payload.shape[1]), dtype=payload.dtype, device=payload.device)
-    _a2a(got, payload[route.order].contiguous(), route.recv_splits, route.send_splits, group)
-    return got
-
-
-# ------------------------------------------------------------------------------------------------------
-# row-sharded Linear training
-# ------------------------------------------------------------------------------------------------------
 class ShardedLinearTrainer:
-    """Linear scorer (collaborative/linear.py) with user / item tables row-sharded over the ranks of ``group``.
+    """Linear scorer (collaborative/linear.py:8-80) with user / item tables row-sharded over the ranks of ``group``.
 
-    ``tables`` = {"user": (emb, bias), "item": (emb, bias)}: this rank's shards, fp32 [ceil(n/G), dim] / [.., 1]
-    (rows r*G + rank of the global table).  ``gather / compute / update`` default to the CUDA kernels."""
+    ``global_batch`` is the largest step (samples over ALL ranks) ``train_epoch`` will be asked to run: it sizes
+    the staging buffers, which are part of the peer-mapped arena.  ``emulate_world=G`` builds all G ranks inside
+    this process on the current GPU (no torch.distributed needed)."""
 
-    def __init__(self, n_users: int, n_items: int, dim: int, optimizer: str = "sparse_adam", lr: float = 1e-3,
-                 device=None, group=None, seed: int = 1234, betas=(0.9, 0.999), eps: Optional[float] = None,
-                 hooks: Optional[dict] = None):
-        self.group = group
-        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.dim, self.n_users, self.n_items = dim, n_users, n_items
-        self.device = device or torch.device("cuda", torch.cuda.current_device())
-        self.kind, self.lr, self.betas = optimizer, lr, betas
-        self.eps = eps if eps is not None else (1e-8 if optimizer == "sparse_adam" else 1e-10)
-        self.step = 0
-        g = torch.Generator(device="cpu").manual_seed(seed)
-        self.tables, self.state = {}, {}
-        for name, n in (("user", n_users), ("item", n_items)):
-            rows = (n - self.rank + self.world - 1) // self.world
-            # init = the rows this rank owns of the table a single process would draw: N(0, 1/dim), zero biases
-            emb = torch.empty((max(rows, 1), dim), dtype=torch.float32, device=self.device)
-            emb.normal_(0.0, 1.0 / dim) if self.device.type == "cuda" else emb.copy_(
-                torch.randn((max(rows, 1), dim), generator=g) / dim)
-            bias = torch.zeros((max(rows, 1), 1), dtype=torch.float32, device=self.device)
-            self.tables[name] = (emb, bias)
-            n_state = {"sgd": 0, "adagrad": 1, "sparse_adam": 2}[optimizer]
-            self.state[name] = [(torch.zeros_like(emb), torch.zeros_like(bias)) for _ in range(n_state)]
-        hooks = hooks or {}
-        self._gather = hooks.get("gather", self._gather_cuda)
-        self._compute = hooks.get("compute", self._compute_cuda)
-        self._update = hooks.get("update", self._update_cuda)
-
-    # ---- CUDA hooks ------------------------------------------------------------------------------
-    def _gather_cuda(self, name: str, rows: torch.Tensor) -> torch.Tensor:
+    def __init__(self, n_users: int, n_items: int, dim: int, global_batch: int, optimizer: str = "sparse_adam",
+                 lr: float = 1e-3, device=None, group=None, betas=(0.9, 0.999), eps: Optional[float] = None,
+                 lr_decay: float = 0.0, emulate_world: Optional[int] = None, timeout_ms: int = 20000):
         from . import _lib
-        emb, bias = self.tables[name]
-        out = torch.empty((rows.shape[0], self.dim + 1), dtype=torch.float32, device=rows.device)
-        if rows.numel():
-            out[:, :self.dim] = _lib.embed_gather_sum(emb, rows)
-            out[:, self.dim:] = _lib.embed_gather_sum(bias, rows)
+        self._lib = _lib
+        self.group = group
+        if emulate_world:
+            self.world, self.local_ranks = int(emulate_world), list(range(int(emulate_world)))
+            self.rank = 0
+        else:
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+            self.local_ranks = [self.rank]
+        if not 1 <= self.world <= _lib.MAX_RANKS:
+            raise ValueError(f"world size {self.world} outside 1..{_lib.MAX_RANKS}")
+        if dim % 4 or dim <= 0 or dim > 512:
+            raise ValueError("row-sharded training needs n_factors to be a multiple of 4 (<= 512)")
+        if optimizer not in _KINDS:
+            raise ValueError(f"optimizer must be one of {sorted(_KINDS)}")
+        self.dim, self.n_users, self.n_items = dim, n_users, n_items
+        self.global_batch = int(global_batch)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.kind = optimizer
+        eps = eps if eps is not None else (1e-8 if optimizer == "sparse_adam" else 1e-10)
+        self.binding = OptBinding(_KINDS[optimizer], _STATE_KEYS[optimizer], float(lr), float(betas[0]),
+                                  float(betas[1]), float(eps), float(lr_decay), 0)
+        self.timeout_ms = timeout_ms
+        self.sync_epoch = 0   # cross-rank barriers the group has passed (2 per step), identical on every rank
+        n_state = len(_STATE_KEYS[optimizer])
+        self.layout = _ArenaLayout(n_users, n_items, dim, n_state, self.world,
+                                   _lib.shard_stage_bytes(dim, self.global_batch), _lib.SHARD_SYNC_BYTES)
+        # one allocation per local rank; barrier words zeroed once, tables initialised like the reference's
+        # ScaledEmbedding / ZeroEmbedding (embeddings/init_embeddings.py:43-50, 90-97): N(0, 1/dim), zero biases
+        self.arenas: Dict[int, torch.Tensor] = {}
+        self.tables: Dict[int, Dict[str, Tuple[torch.Tensor, torch.Tensor]]] = {}
+        self.state: Dict[int, Dict[str, List[Tuple[torch.Tensor, torch.Tensor]]]] = {}
+        L = self.layout
+        for r in self.local_ranks:
+            arena = torch.empty(L.total, dtype=torch.uint8, device=self.device)
+            arena[L.sync:L.sync + _lib.SHARD_SYNC_BYTES].zero_()
+            self.arenas[r] = arena
+            self.tables[r], self.state[r] = {}, {}
+            for name, n in (("user", n_users), ("item", n_items)):
+                rows = shard_rows(n, r, self.world)
+                view = lambda off, cols: arena[off:off + rows * cols * 4].view(torch.float32).view(rows, cols)
+                emb, lin = view(L.emb[name], dim), view(L.lin[name], 1)
+                emb.normal_(0.0, 1.0 / dim)
+                lin.zero_()
+                self.tables[r][name] = (emb, lin)
+                self.state[r][name] = []
+                for i in range(n_state):
+                    s_e, s_l = view(L.emb_state[name][i], dim), view(L.lin_state[name][i], 1)
+                    s_e.zero_()
+                    s_l.zero_()
+                    self.state[r][name].append((s_e, s_l))
+        self._map_peers()
+        self._plans: Dict[int, torch.Tensor] = {}
+        self._plan_tmp = None
+        self._ws = None
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.launches = 0
+
+    # ---- peer mapping -----------------------------------------------------------------------------
+    def _map_peers(self) -> None:
+        """bases[q] = address of rank q's arena in THIS process."""
+        _lib = self._lib
+        self._opened: List[int] = []
+        if self.device.type != "cuda":  # host-logic tests: checkpoints work on CPU arenas, training does not
+            self.bases = None
+            return
+        if len(self.local_ranks) == self.world:
+            self.bases = [self.arenas[q].data_ptr() for q in range(self.world)]
+            return
+        handle, off = _lib.ipc_export(self.arenas[self.rank])
+        everyone: List = [None] * self.world
+        dist.all_gather_object(everyone, (handle, off), group=self.group)
+        self.bases = []
+        for q, (h, o) in enumerate(everyone):
+            if q == self.rank:
+                self.bases.append(self.arenas[q].data_ptr())
+            else:
+                base = _lib.ipc_open(h)
+                self._opened.append(base)
+                self.bases.append(base + o)
+        dist.barrier(group=self.group)  # every arena is initialised and mapped before anyone trains
+
+    def close(self) -> None:
+        for base in getattr(self, "_opened", []):
+            self._lib.ipc_close(base)
+        self._opened = []
+
+    def _shard_struct(self, r: int):
+        """trs_shard of local rank r: every rank's tables / staging / barrier words at their mapped addresses."""
+        _lib, L = self._lib, self.layout
+        sh = _lib.Shard()
+        sh.rank, sh.world, sh.dim = r, self.world, self.dim
+        sh.n_users, sh.n_items = self.n_users, self.n_items
+        pick = lambda offs, i: offs[i] if i < len(offs) else None
+        for q in range(self.world):
+            for name, arr, n in (("user", sh.user, self.n_users), ("item", sh.item, self.n_items)):
+                es, ls = L.emb_state[name], L.lin_state[name]
+                arr[q] = _lib.table_at(self.bases[q], L.emb[name], pick(es, 0), pick(es, 1), L.lin[name], pick(ls, 0),
+                                       pick(ls, 1), shard_rows(n, q, self.world))
+            sh.stage[q] = self.bases[q] + L.stage
+            sh.sync[q] = self.bases[q] + L.sync
+        return sh
+
+    # ---- training -----------------------------------------------------------------------------------
+    def train_epoch(self, user: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, global_batch: Optional[int] = None,
+                    check: bool = True, timing: bool = False) -> torch.Tensor:
+        """user / pos / neg: the GLOBAL epoch (int64 device tensors, identical on every rank), step s = samples
+        [s*B, (s+1)*B) with B = ``global_batch``.  Returns the per-step batch-mean hinge losses (device, [n_steps]) --
+        what ``loss.item()`` returns at model.py:200.  ``check=False`` skips the status read-back (no host sync);
+        call ``check_status()`` later.  ``timing=True`` brackets the plan build and the persistent kernel with CUDA
+        events (``self.events = (plan0, plan1, kernel0, kernel1)``, bench.py's roofline)."""
+        _lib = self._lib
+        if self.bases is None:
+            raise RuntimeError("torchrecsys_b200 has no CPU fallback: row-sharded training needs CUDA devices")
+        B = int(global_batch or self.global_batch)
+        if B > self.global_batch:
+            raise ValueError(f"global batch {B} exceeds the {self.global_batch} the staging buffers were sized for")
+        n = user.shape[0]
+        n_steps = -(-n // B)
+        if n_steps == 0:
+            return torch.empty(0, device=self.device)
+        epoch = _lib.make_epoch(user, pos, neg, None, None, B)
+        shards = [self._shard_struct(r) for r in self.local_ranks]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timing else None
+        if ev:
+            ev[0].record()
+        for r, sh in zip(self.local_ranks, shards):
+            self._plans[r] = _lib.shard_plan_build(sh, epoch, self.device, self._plans.get(r), self._plan_tmp)
+        scales = torch.tensor(step_scales(self.binding, n_steps), dtype=torch.float64).to(torch.float32)
+        scales = scales.to(self.device, non_blocking=True)
+        b = self.binding
+        optim = _lib.Optim(b.kind, 0, b.beta1, b.beta2, b.eps, scales.data_ptr())
+        sums = torch.zeros((len(self.local_ranks), n_steps), dtype=torch.float32, device=self.device)
+        if ev:
+            ev[1].record()
+            ev[2].record()
+        self._ws = _lib.shard_train_steps(shards, epoch, optim, [self._plans[r] for r in self.local_ranks], 0, n_steps,
+                                          self.sync_epoch, [sums[i] for i in range(len(shards))], self.status,
+                                          self._ws, self.timeout_ms)
+        if ev:
+            ev[3].record()
+            self.events = tuple(ev)
+        self.sync_epoch += 2 * n_steps
+        self.launches += 1 + len(self.local_ranks) * self.plan_launches()
+        b.step0 += n_steps
+        total = sums.sum(0)
+        if len(self.local_ranks) < self.world:
+            dist.all_reduce(total, group=self.group)
+        counts = torch.full((n_steps,), float(B), device=self.device)
+        counts[-1] = float(n - (n_steps - 1) * B)
+        if check:
+            self.check_status()
+        return total / counts
+
+    def plan_launches(self) -> int:
+        """CUDA kernels one trs_shard_plan_build launches for one rank (bench.py's gpu_launches)."""
+        passes = lambda rows: max(1, -(-max(1, (max(rows, 2) - 1).bit_length()) // 8))
+        return 2 * (2 + passes(-(-self.n_users // self.world)) + passes(-(-self.n_items // self.world)))
+
+    def check_status(self) -> None:
+        if int(self.status.item()) != 0:
+            raise RuntimeError("row-sharded training: a peer rank did not reach a step barrier within "
+                               f"{self.timeout_ms} ms; the tables are in an undefined state")
+
+    def train_step(self, user: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
+        """Convenience: THIS rank's samples of one step; the global batch is the all-gather over ranks (rank-major).
+        Returns the global batch-mean hinge (device scalar)."""
+        if len(self.local_ranks) < self.world:
+            parts = []
+            for t in (user, pos, neg):
+                out = torch.empty(self.world * t.shape[0], dtype=t.dtype, device=t.device)
+                dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+                parts.append(out)
+            user, pos, neg = parts
+        return self.train_epoch(user, pos, neg, user.shape[0])[0]
+
+    # ---- checkpoints: the reference's single-process layout (state_dict keys of collaborative/linear.py) --------
+    _KEYS = (("user", "user.weight", "user_bias.weight"), ("item", "item.weight", "item_bias.weight"))
+
+    def _gather(self, pieces: Dict[int, torch.Tensor], n: int) -> torch.Tensor:
+        """Interleave per-rank shards [rows_q, C] into the full [n, C] table (row r = shard r % G, row r // G)."""
+        G = self.world
+        cols = next(iter(pieces.values())).shape[1]
+        rows = -(-n // G)
+        pad = lambda t: torch.cat([t, t.new_zeros((rows - t.shape[0], cols))]) if t.shape[0] < rows else t
+        if len(self.local_ranks) == G:
+            stack = [pad(pieces[q]) for q in range(G)]
+        else:
+            mine = pad(pieces[self.rank]).contiguous()
+            stack = [torch.empty_like(mine) for _ in range(G)]
+            dist.all_gather(stack, mine, group=self.group)
+        return torch.stack(stack, 1).reshape(rows * G, cols)[:n].contiguous()
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        out = {}
+        for name, wkey, bkey in self._KEYS:
+            n = self.n_users if name == "user" else self.n_items
+            out[wkey] = self._gather({r: self.tables[r][name][0] for r in self.local_ranks}, n)
+            out[bkey] = self._gather({r: self.tables[r][name][1] for r in self.local_ranks}, n)
         return out
 
-    def _compute_cuda(self, u, vp, vn, inv_batch):
-        from . import _lib
-        D = self.dim
-        g_u, g_vp, g_vn, g_bp, g_bn, hsum = _lib.linear_rows_step(
-            u[:, :D].contiguous(), vp[:, :D].contiguous(), vn[:, :D].contiguous(), u[:, D].contiguous(),
-            vp[:, D].contiguous(), vn[:, D].contiguous(), inv_batch)
-        zero = torch.zeros_like(g_bp)
-        pack = lambda g, b: torch.cat([g, b[:, None]], 1)
-        return pack(g_u, zero), pack(g_vp, g_bp), pack(g_vn, g_bn), hsum
+    def optimizer_state_dict(self) -> Dict[str, Dict[str, torch.Tensor]]:
+        """{parameter key: {torch's state name: full tensor, "step": t}} -- torch.optim's per-parameter state."""
+        out: Dict[str, Dict[str, torch.Tensor]] = {}
+        for name, wkey, bkey in self._KEYS:
+            n = self.n_users if name == "user" else self.n_items
+            out[wkey], out[bkey] = {"step": self.binding.step0}, {"step": self.binding.step0}
+            for i, sname in enumerate(_STATE_KEYS[self.kind]):
+                out[wkey][sname] = self._gather({r: self.state[r][name][i][0] for r in self.local_ranks}, n)
+                out[bkey][sname] = self._gather({r: self.state[r][name][i][1] for r in self.local_ranks}, n)
+        return out
 
-    def _scale(self) -> float:
-        import math
-        t = self.step + 1
-        if self.kind == "sparse_adam":
-            return self.lr * math.sqrt(1 - self.betas[1] ** t) / (1 - self.betas[0] ** t)
-        return self.lr
+    def load_state_dict(self, params: Dict[str, torch.Tensor],
+                        optimizer_state: Optional[Dict[str, Dict[str, torch.Tensor]]] = None) -> None:
+        """Scatter full tables (a ``Linear``/``TorchRecSys.net`` state_dict, or ``state_dict()`` of another group
+        size) onto the shards: every rank keeps rows rank::world."""
+        G = self.world
+        for name, wkey, bkey in self._KEYS:
+            for r in self.local_ranks:
+                emb, lin = self.tables[r][name]
+                emb.copy_(params[wkey][r::G].to(self.device))
+                lin.copy_(params[bkey][r::G].to(self.device).view(-1, 1))
+                if optimizer_state is not None:
+                    for i, sname in enumerate(_STATE_KEYS[self.kind]):
+                        self.state[r][name][i][0].copy_(optimizer_state[wkey][sname][r::G].to(self.device))
+                        self.state[r][name][i][1].copy_(optimizer_state[bkey][sname][r::G].to(self.device).view(-1, 1))
+        if optimizer_state is not None:
+            self.binding.step0 = int(optimizer_state["user.weight"].get("step", 0))
+        if len(self.local_ranks) < G:
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)  # peers read these rows: nobody trains before everyone has loaded
 
-    def _update_cuda(self, name: str, rows: torch.Tensor, grads: torch.Tensor) -> None:
-        from . import _lib
-        emb, bias = self.tables[name]
-        st = self.state[name]
-        s0 = st[0] if len(st) > 0 else (None, None)
-        s1 = st[1] if len(st) > 1 else (None, None)
-        table = _lib.make_table(emb, s0[0], s1[0], bias, s0[1], s1[1])
-        kind = {"sgd": _lib.OPT_SGD, "adagrad": _lib.OPT_ADAGRAD, "sparse_adam": _lib.OPT_SPARSE_ADAM}[self.kind]
-        scale = torch.tensor([self._scale()], dtype=torch.float64).float().to(rows.device)
-        optim = _lib.Optim(kind, 0, self.betas[0], self.betas[1], self.eps, scale.data_ptr())
-        g_lin = None if name == "user" else grads[:, self.dim].contiguous()  # d user_bias == 0
-        _lib.sparse_row_update(table, self.dim, rows, grads[:, :self.dim].contiguous(), g_lin, optim, 0)
-
-    # ---- one step --------------------------------------------------------------------------------
-    def train_step(self, user: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
-        """user / pos / neg: this rank's B samples (global ids).  Returns the rank's hinge sum (device scalar);
-        the global batch-mean loss is ``all_reduce(sum) / (G*B)``."""
-        B = user.shape[0]
-        ids = torch.cat([user, pos, neg])
-        space = torch.cat([torch.zeros_like(user), torch.ones_like(pos), torch.ones_like(neg)])
-        route = make_route(ids, space, 2, self.world, self.group)
-        nu = route.space_sizes[0]
-        req = route.recv_rows[route.by_space]                       # user requests first, then item requests
-        payload = torch.empty((req.shape[0], self.dim + 1), dtype=torch.float32, device=ids.device)
-        payload[route.by_space] = torch.cat([self._gather("user", req[:nu]), self._gather("item", req[nu:])])
-        rows = exchange_back(route, payload, self.group)            # [3B, dim+1] in lookup order
-        g_u, g_vp, g_vn, hsum = self._compute(rows[:B], rows[B:2 * B], rows[2 * B:], 1.0 / (B * self.world))
-        grads = exchange_forward(route, torch.cat([g_u, g_vp, g_vn]), self.group)[route.by_space]
-        self._update("user", req[:nu], grads[:nu])
-        self._update("item", req[nu:], grads[nu:])
-        self.step += 1
-        return hsum
-
-    # ---- helpers for tests / checkpoints -----------------------------------------------------------
     def gather_full(self, name: str) -> Tuple[torch.Tensor, torch.Tensor]:
-        """All-gather a sharded table back into the single-process [n, dim] layout (state_dict interchange)."""
-        emb, bias = self.tables[name]
-        n = self.n_users if name == "user" else self.n_items
-        rows = (n + self.world - 1) // self.world
-        pad = lambda t: torch.cat([t, t.new_zeros((rows - t.shape[0],) + t.shape[1:])]) if t.shape[0] < rows else t[:rows]
-        embs = [torch.empty((rows, self.dim), dtype=emb.dtype, device=emb.device) for _ in range(self.world)]
-        bs = [torch.empty((rows, 1), dtype=bias.dtype, device=bias.device) for _ in range(self.world)]
-        dist.all_gather(embs, pad(emb).contiguous(), group=self.group)
-        dist.all_gather(bs, pad(bias).contiguous(), group=self.group)
-        full_e = torch.stack(embs, 1).reshape(rows * self.world, self.dim)[:n]
-        full_b = torch.stack(bs, 1).reshape(rows * self.world, 1)[:n]
-        return full_e, full_b
+        sd = self.state_dict()
+        return sd[f"{name}.weight"], sd[f"{name}_bias.weight"]
 
 
 # ------------------------------------------------------------------------------------------------------
