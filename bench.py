@@ -87,6 +87,7 @@ def parse_args():
     ap.add_argument("--min-ms", type=float, default=100.0, help="the K-step block is repeated until the timed region lasts this long")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the other_workloads sub-results")
+    ap.add_argument("--shard-it", type=int, default=0, help="tuning: 16-byte chunks per lane of the sharded kernel (1 or 2)")
     ap.add_argument("--emulate-world", type=int, default=0,
                     help="c4_linear on ONE GPU: host a group of this many ranks in one launch (structure check, no NVLink)")
     return ap.parse_args()
@@ -352,8 +353,9 @@ def gpu_bench(args, wl, name):
     # W warm-up steps, then the memory pool: an epoch of K steps needs other buffer sizes than the W warm-up steps
     # did.  Reserve them now, so that the timed region measures the steps and not torch's first cudaMalloc of each
     # size (in a real fit() every epoch has the same shape and reuses the blocks of the one before)
-    step_block(user[:W * B], pos[:W * B], 0)
+    loss_w = step_block(user[:W * B], pos[:W * B], 0)
     sync_all()
+    first_loss = float(loss_w[0].item())
     if hasattr(runner, "reserve"):
         runner.reserve(K * B, B)
     uK, pK = user[W * B:], pos[W * B:]
@@ -477,7 +479,9 @@ def gpu_bench(args, wl, name):
                                    "not a scaling result)") if world > 1 else "single GPU",
                    "clock_ramp": "0.3 s of device copies before the warm-up steps",
                    "memory_pool": "buffer sizes of a K-step epoch reserved before the timed region (no cudaMalloc inside)",
-                   "mean_loss": mean_loss},
+                   "first_step_loss": first_loss, "mean_loss_last_block": mean_loss,
+                   "loss_note": "the K-step block is replayed `repeats` times (fresh negatives each time): the model "
+                                "memorises its few samples, the hinge goes to 0; the work per step does not change"},
         "e2e": {"value": world * R * K * B / (e2e_ms * 1e-3), "unit": "samples/s",
                 "h2d_bytes_per_step": 16 * B, "d2h_bytes_per_step": 4,
                 "note": "user+positive ids from pinned host memory; metadata ids and negatives are derived on the device"},
@@ -665,6 +669,8 @@ def sharded_bench(args, wl, name):
     emu = args.emulate_world if world == 1 else 0
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
+    if args.shard_it:
+        _lib.lib().trs_debug_shard_chunks_per_lane(args.shard_it)
     G = emu or world                       # ranks of the group
     K, W, B = args.steps, max(args.warmup, 3), wl["batch"]
     Bg = B * G
@@ -705,9 +711,10 @@ def sharded_bench(args, wl, name):
     sync_all = (lambda: (torch.cuda.synchronize(), dist.barrier(), torch.cuda.synchronize())) if world > 1 \
         else torch.cuda.synchronize
     clock_ramp(dev)
-    block(ids_d, 0, W)
+    loss_w = block(ids_d, 0, W)[0]
     sync_all()
     tr.check_status()
+    first_loss = float(loss_w[0].item())
     loss_host = torch.empty(K, dtype=torch.float32).pin_memory()
 
     def resident_block():
@@ -778,7 +785,9 @@ def sharded_bench(args, wl, name):
                    "timed_region": "id all-gather (NCCL) + Philox negatives + routing / sort plan + persistent sharded "
                                    "kernel (K steps in one launch) + loss all-reduce, x repeats",
                    "clock_ramp": "0.3 s of device copies before the warm-up steps",
-                   "mean_loss": mean_loss},
+                   "first_step_loss": first_loss, "mean_loss_last_block": mean_loss,
+                   "loss_note": "the K-step block is replayed `repeats` times (fresh negatives each time): the model "
+                                "memorises its few samples, the hinge goes to 0; the work per step does not change"},
         "e2e": {"value": R * K * Bg / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": 16 * B,
                 "d2h_bytes_per_step": 4,
                 "note": "each rank's user+positive ids from pinned host memory; negatives are drawn on the device"},

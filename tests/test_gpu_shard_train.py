@@ -82,8 +82,8 @@ def test_sharded_steps_match_the_oracle_on_the_global_batch(dev, world, dim, opt
                 continue  # its gradient is exactly 0: state stays 0 here; the oracle decays nothing either
             np.testing.assert_allclose(gst[k][sname].cpu().numpy(), want_s, err_msg=f"{k}.{sname}", **tol)
     # rows nobody looked up are bit-identical to the initial tables
-    untouched = np.setdiff1d(np.arange(I), np.concatenate([pos, neg]))
-    assert untouched.size and np.array_equal(got["item.weight"][untouched], params["item.weight"][untouched])
+    untouched = np.setdiff1d(np.arange(U), user)
+    assert untouched.size and np.array_equal(got["user.weight"][untouched], params["user.weight"][untouched])
 
 
 def test_group_sizes_agree_bit_for_bit_and_split_launches_equal_one(dev):

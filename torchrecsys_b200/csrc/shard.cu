@@ -176,7 +176,10 @@ route_scatter_kernel(const int64_t* __restrict__ a, const int64_t* __restrict__ 
 // ------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------
-constexpr int SH_SB = 8;  // samples whose rows are in flight per row group in phase A
+// Thread-private 16-byte shared-memory slots per chunk a lane owns: phase A keeps SB samples x {user, positive,
+// negative} row in flight per row group, phase B PB owned rows x {gradient, parameter, state 0, state 1}.
+template <int IT>
+constexpr int shard_slots() { return IT == 1 ? 24 : 12; }
 
 struct ShardCtx {  // everything one (virtual) rank needs; copied to shared memory by each of its CTAs
     int rank, world, dim, pad;
@@ -196,12 +199,20 @@ struct ShardCtx {  // everything one (virtual) rank needs; copied to shared memo
 // word 64 + 32 * q = the number of the last cross-rank barrier rank q has reached (monotonic over launches)
 __device__ __forceinline__ unsigned* flag_of(unsigned* sync, int q) { return sync + 64 + 32 * q; }
 
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+__device__ __forceinline__ void st_relaxed_gpu(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
     unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned long long shard_now_ns() {
@@ -229,31 +240,42 @@ __device__ __forceinline__ void sh_cp_async_wait(int n) {
 }
 
 template <int IT>
-constexpr int shard_threads() { return IT == 1 ? 512 : (IT == 2 ? 256 : 128); }
+constexpr int shard_threads() { return IT <= 2 ? 512 : 256; }
 template <int IT>
-constexpr size_t shard_smem_bytes() { return (size_t)shard_threads<IT>() * SH_SB * 3 * IT * 16; }
+constexpr size_t shard_smem_bytes() { return (size_t)shard_threads<IT>() * shard_slots<IT>() * IT * 16; }
 
 // Cross-rank barrier number e (1-based over the life of the group).  Every CTA of the rank arrives on the rank's
 // own counter; the last one posts e into every rank's flag words; everybody waits until all W flags of ITS OWN
-// sync words have reached e.  Writes of all threads (including stores into peer memory) happen-before the flag:
-// bar.sync -> thread 0: fence.sys -> atomic -> (last CTA) fence.sys -> st.release.sys.
+// sync words have reached e.  Writes of all threads happen-before the flag: bar.sync -> thread 0: fence -> atomic
+// -> (last CTA) fence.sys -> flag stores -> (peer) relaxed polls + fence.sys.  `remote_writes`: the phase before
+// the barrier stored into PEER memory (gradient rows): each CTA's fence is then system-scope, so that its own
+// stores are acknowledged by the peer before it arrives; after a phase that only wrote local memory (the owner's
+// update: peers read those rows through THIS GPU's L2) a gpu-scope fence per CTA is enough.  A group of one rank
+// never leaves gpu scope.  Fences are the expensive part of the barrier (a system-scope fence waits for every
+// outstanding store of the SM): there is exactly one per CTA on the way in and one on the way out.
 __device__ __forceinline__ void cross_rank_barrier(const ShardCtx& C, unsigned e, unsigned local_target,
-                                                   unsigned long long timeout_ns) {
+                                                   unsigned long long timeout_ns, bool remote_writes) {
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned* mine = C.sync[C.rank];
-        __threadfence_system();
+        const bool multi = C.world > 1;
+        if (multi && remote_writes) __threadfence_system(); else __threadfence();
         const unsigned old = atomicAdd(mine, 1u);
         if (old + 1u == local_target) {
-            __threadfence_system();
-            for (int q = 0; q < C.world; ++q) st_release_sys(flag_of(C.sync[q], C.rank), e);
+            if (multi) {
+                __threadfence_system();
+                for (int q = 0; q < C.world; ++q) st_relaxed_sys(flag_of(C.sync[q], C.rank), e);
+            } else {
+                __threadfence();
+                st_relaxed_gpu(flag_of(mine, 0), e);
+            }
         }
         volatile int* status = C.status;
         const unsigned long long t0 = shard_now_ns();
         for (int q = 0; q < C.world; ++q) {
             const unsigned* f = flag_of(mine, q);
             unsigned spins = 0;
-            while ((int)(ld_acquire_sys(f) - e) < 0) {
+            while ((int)((multi ? ld_relaxed_sys(f) : ld_relaxed_gpu(f)) - e) < 0) {
                 if ((++spins & 1023u) == 0) {
                     if (*status != 0) break;
                     if (shard_now_ns() - t0 > timeout_ns) {
@@ -263,42 +285,47 @@ __device__ __forceinline__ void cross_rank_barrier(const ShardCtx& C, unsigned e
                 }
             }
         }
-        __threadfence_system();
+        if (multi) __threadfence_system(); else __threadfence();
     }
     __syncthreads();
 }
 
-template <int IT>
+template <int KIND, int IT>
 __device__ __forceinline__ void sh_update_store(const trs_table& t, size_t roff, int nch, int gl, int G_,
                                                 const OptScalars& o, float scale, Row<4, IT>& p, Row<4, IT>& s0,
                                                 Row<4, IT>& s1, const Row<4, IT>& g) {
+    OptScalars ok = o;
+    ok.kind = KIND;  // compile-time optimizer: opt_update's branches fold
 #pragma unroll
     for (int a = 0; a < IT; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) opt_update(o, scale, g.c[a][b], p.c[a][b], s0.c[a][b], s1.c[a][b]);
+        for (int b = 0; b < 4; ++b) opt_update(ok, scale, g.c[a][b], p.c[a][b], s0.c[a][b], s1.c[a][b]);
 #pragma unroll
     for (int a = 0; a < IT; ++a) {
         const int c = gl + a * G_;
         if (c < nch) {
             p.c[a].st(t.emb + roff + (size_t)c * 4);
-            if (o.kind != TRS_OPT_SGD) s0.c[a].st(t.emb_s0 + roff + (size_t)c * 4);
-            if (o.kind == TRS_OPT_SPARSE_ADAM) s1.c[a].st(t.emb_s1 + roff + (size_t)c * 4);
+            if (KIND != TRS_OPT_SGD) s0.c[a].st(t.emb_s0 + roff + (size_t)c * 4);
+            if (KIND == TRS_OPT_SPARSE_ADAM) s1.c[a].st(t.emb_s1 + roff + (size_t)c * 4);
         }
     }
 }
 
-template <int G, int IT>
+template <int KIND, int G, int IT>
 __global__ void __launch_bounds__((shard_threads<IT>()), 1)
 shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __restrict__ ctxs, const int cpr,
                    const __grid_constant__ trs_epoch ep, const __grid_constant__ OptScalars opt, const int first_step,
                    const int n_steps, const unsigned sync_epoch, const unsigned long long timeout_ns) {
     constexpr int NT = shard_threads<IT>();
     constexpr int GPB = NT / G, GPW = 32 / G;
-    constexpr int RPL = (SH_SB + G - 1) / G;  // sample records a lane fetches per round
+    constexpr int SB = shard_slots<IT>() / 3;  // samples in flight per row group (phase A)
+    constexpr int PB = shard_slots<IT>() / 4;  // owned rows in flight per row group (phase B)
+    constexpr int RPL = (SB + G - 1) / G;      // sample records a lane fetches per phase-A round
+    constexpr int DPL = (PB + G - 1) / G;      // row descriptors a lane fetches per phase-B round
     __shared__ ShardCtx C;
     __shared__ float s_loss[NT / 32];
     extern __shared__ __align__(16) unsigned char sh_smem[];
-    float4* rows = reinterpret_cast<float4*>(sh_smem);  // [SH_SB][3][IT][NT], thread-private slots
+    float4* rows = reinterpret_cast<float4*>(sh_smem);  // [slot][IT][NT]
 
     const int vr = blockIdx.x / cpr, c = blockIdx.x % cpr;
     {
@@ -308,23 +335,97 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
     }
     __syncthreads();
     const uint32_t W = (uint32_t)C.world;
+    const bool wpow2 = (W & (W - 1u)) == 0u;
+    const int wshift = __ffs((int)W) - 1;
     const int me = C.rank, dim = C.dim, nch = dim / 4;
     const int gl = threadIdx.x % G, g_in_cta = threadIdx.x / G;
     const int gfirst = c * GPB + g_in_cta, gstride = cpr * GPB;
     const int goff = g_in_cta % GPW;  // my group's position inside its warp: loops run on the warp's first group
-    const int kind = opt.kind;
-    auto slot = [&](int i, int r, int a) { return rows + (((i * 3 + r) * IT + a) * NT + threadIdx.x); };
-    auto slot_row = [&](int i, int r) {
+    auto slot = [&](int j, int a) { return rows + ((j * IT + a) * NT + threadIdx.x); };
+    auto slot_row = [&](int j) {
         Row<4, IT> x;
 #pragma unroll
         for (int a = 0; a < IT; ++a) {
             x.c[a] = Vec<4>::zero();
-            if (gl + a * G < nch) x.c[a].v = *slot(i, r, a);
+            if (gl + a * G < nch) x.c[a].v = *slot(j, a);
         }
         return x;
     };
+    auto copy_row = [&](int j, const float* base) {
+#pragma unroll
+        for (int a = 0; a < IT; ++a) {
+            const int ch = gl + a * G;
+            if (ch < nch) sh_cp_async16(slot(j, a), base + (size_t)ch * 4);
+        }
+    };
     auto ld_row = [&](const float* base) { return load_row_cg<4, G, IT>(base, nch, gl); };
+    const trs_table& tU = C.user[me];
+    const trs_table& tI = C.item[me];
+    const bool item_lin = tI.lin != nullptr;
+    float* const my_stage_u = C.stage_u[me];
+    float* const my_stage_i = C.stage_i[me];
+    const float* const my_stage_b = C.stage_b[me];
     unsigned bar_no = 0;  // cross-rank barriers passed in this launch
+
+    // ---- records of a phase-A round: lane gl fetches samples gl, gl + G, ... of the round and splits their ids
+    //      into (owner, local row) ONCE (plan + epoch data: immutable, so the NEXT step's first round is fetched a
+    //      whole step ahead).  q packs the three owners, 4 bits each ----
+    struct Rec { uint32_t b[RPL], q[RPL], lu[RPL], lp[RPL], ln[RPL]; };
+    auto split = [&](uint32_t id, uint32_t& owner, uint32_t& local) {
+        if (wpow2) { owner = id & (W - 1u); local = id >> wshift; }
+        else { owner = id % W; local = id / W; }
+    };
+    auto fetch_records = [&](Rec& R, int64_t lo_, int nS_, int kb) {
+        const uint32_t* samp = C.samp + lo_;
+#pragma unroll
+        for (int z = 0; z < RPL; ++z) {
+            const int i = gl + z * G;
+            const int k = kb + i * gstride;
+            R.b[z] = 0xFFFFFFFFu;
+            R.q[z] = R.lu[z] = R.lp[z] = R.ln[z] = 0u;
+            if (i < SB && k < nS_) {
+                const uint32_t b = __ldg(samp + k);
+                R.b[z] = b;
+                uint32_t qu, qp, qn;
+                split((uint32_t)__ldg(ep.user + lo_ + b), qu, R.lu[z]);
+                split((uint32_t)__ldg(ep.pos + lo_ + b), qp, R.lp[z]);
+                split((uint32_t)__ldg(ep.neg + lo_ + b), qn, R.ln[z]);
+                R.q[z] = qu | (qp << 4) | (qn << 8);
+            }
+        }
+    };
+    // ---- descriptors of a phase-B round: the owned lookups of a step are one list of positions, user space
+    //      [0, nU) then item space [nU, nU + nI); lane gl fetches positions gl, gl + G, ... of the round ----
+    // sf = slot | flags << 29; flag bits: 1 head (first position of a run of equal rows), 2 the run continues,
+    // 4 item space
+    struct Desc { uint32_t key[DPL], sf[DPL]; };
+    auto fetch_descs = [&](Desc& Dd, int64_t lo_, int nU_, int nI_, int pb) {
+#pragma unroll
+        for (int z = 0; z < DPL; ++z) {
+            const int i = gl + z * G;
+            const int p = pb + i * gstride;
+            Dd.key[z] = Dd.sf[z] = 0u;
+            if (i < PB && p < nU_ + nI_) {
+                const bool it = p >= nU_;
+                const int k = it ? p - nU_ : p, n = it ? nI_ : nU_;
+                const uint32_t* K = it ? C.ikey + 2 * lo_ : C.ukey + lo_;
+                const uint32_t* P = it ? C.ival + 2 * lo_ : C.uval + lo_;
+                const uint32_t key = __ldg(K + k);
+                const uint32_t prev = k > 0 ? __ldg(K + k - 1) : ~key;
+                const uint32_t next = k + 1 < n ? __ldg(K + k + 1) : ~key;
+                Dd.key[z] = key;
+                Dd.sf[z] = __ldg(P + k) | ((prev != key ? 1u : 0u) | (next == key ? 2u : 0u) | (it ? 4u : 0u)) << 29;
+            }
+        }
+    };
+
+    Rec recA;
+    int nS_cur = 0;
+    {
+        const int64_t lo0 = (int64_t)first_step * ep.batch;
+        nS_cur = (int)C.samp_cnt[first_step];
+        fetch_records(recA, lo0, nS_cur, gfirst);
+    }
 
     for (int si = 0; si < n_steps; ++si) {
         const int64_t s = first_step + si;
@@ -332,116 +433,101 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
         const int Bs = (int)min((int64_t)ep.batch, ep.n_samples - lo);
         const float invB = 1.0f / (float)Bs;
         const float scale = opt.step_scale[s];
+        const int nS = nS_cur;
+        const int nU = (int)C.own_cnt[2 * s], nI = (int)C.own_cnt[2 * s + 1];
+        const bool more = si + 1 < n_steps;
+        const int nS_next = more ? (int)C.samp_cnt[s + 1] : 0;
 
         // ------------------------------ phase A ------------------------------------------
         float hsum = 0.f;
-        {
-            const int nS = (int)C.samp_cnt[s];
-            const uint32_t* samp = C.samp + lo;
-            for (int k0 = gfirst - goff; k0 < nS; k0 += gstride * SH_SB) {  // warp-uniform trip count
-                const int kb = k0 + goff;
-                // records of this round's samples: lane gl fetches samples gl, gl + G, ... of the round
-                uint32_t rb[RPL], ru[RPL], rp[RPL], rn[RPL];
+        for (int k0 = gfirst - goff; k0 < nS; k0 += gstride * SB) {  // warp-uniform trip count
+            const int kb = k0 + goff;
+            float bias_r[SB];  // lane t < 3 holds the width-1 companion of lookup t (user, positive, negative)
 #pragma unroll
-                for (int z = 0; z < RPL; ++z) {
-                    const int i = gl + z * G;
-                    const int k = kb + i * gstride;
-                    rb[z] = 0xFFFFFFFFu;
-                    ru[z] = rp[z] = rn[z] = 0u;
-                    if (i < SH_SB && k < nS) {
-                        const uint32_t b = __ldg(samp + k);
-                        rb[z] = b;
-                        ru[z] = (uint32_t)ep.user[lo + b];
-                        rp[z] = (uint32_t)ep.pos[lo + b];
-                        rn[z] = (uint32_t)ep.neg[lo + b];
+            for (int i = 0; i < SB; ++i) {
+                const uint32_t b = __shfl_sync(0xffffffffu, recA.b[i / G], i % G, G);
+                const uint32_t q = __shfl_sync(0xffffffffu, recA.q[i / G], i % G, G);
+                const uint32_t lu = __shfl_sync(0xffffffffu, recA.lu[i / G], i % G, G);
+                const uint32_t lp = __shfl_sync(0xffffffffu, recA.lp[i / G], i % G, G);
+                const uint32_t ln = __shfl_sync(0xffffffffu, recA.ln[i / G], i % G, G);
+                bias_r[i] = 0.f;
+                if (b != 0xFFFFFFFFu) {
+                    const trs_table& TU = C.user[q & 15u];
+                    const trs_table& TP = C.item[(q >> 4) & 15u];
+                    const trs_table& TN = C.item[(q >> 8) & 15u];
+                    copy_row(i * 3 + 0, TU.emb + (size_t)lu * dim);
+                    copy_row(i * 3 + 1, TP.emb + (size_t)lp * dim);
+                    copy_row(i * 3 + 2, TN.emb + (size_t)ln * dim);
+                    if (gl < 3) {
+                        const float* lin = gl == 0 ? TU.lin : (gl == 1 ? TP.lin : TN.lin);
+                        const uint32_t lrow = gl == 0 ? lu : (gl == 1 ? lp : ln);
+                        if (lin) bias_r[i] = __ldcg(lin + lrow);
                     }
                 }
-                float bias_r[SH_SB];  // lane t < 3 holds the width-1 companion of lookup t (user, positive, negative)
+                sh_cp_async_commit();
+            }
+            Rec cur = recA;
+            // the next round's records -- or, after the last round, the next step's first round
+            if (k0 + gstride * SB < nS) fetch_records(recA, lo, nS, kb + gstride * SB);
+            else if (more) fetch_records(recA, lo + ep.batch, nS_next, gfirst);
 #pragma unroll
-                for (int i = 0; i < SH_SB; ++i) {
-                    const uint32_t b = __shfl_sync(0xffffffffu, rb[i / G], i % G, G);
-                    const uint32_t u = __shfl_sync(0xffffffffu, ru[i / G], i % G, G);
-                    const uint32_t ip = __shfl_sync(0xffffffffu, rp[i / G], i % G, G);
-                    const uint32_t in = __shfl_sync(0xffffffffu, rn[i / G], i % G, G);
-                    bias_r[i] = 0.f;
-                    if (b != 0xFFFFFFFFu) {
-                        const uint32_t qu = u % W, qp = ip % W, qn = in % W;
-                        const size_t ou = (size_t)(u / W) * dim, op = (size_t)(ip / W) * dim, on = (size_t)(in / W) * dim;
-                        const float* pu = C.user[qu].emb + ou;
-                        const float* pp = C.item[qp].emb + op;
-                        const float* pn = C.item[qn].emb + on;
+            for (int i = 0; i < SB; ++i) {
+                sh_cp_async_wait(SB - 1 - i);
+                const uint32_t b = __shfl_sync(0xffffffffu, cur.b[i / G], i % G, G);
+                const uint32_t q = __shfl_sync(0xffffffffu, cur.q[i / G], i % G, G);
+                const bool valid = b != 0xFFFFFFFFu;
+                Row<4, IT> xu, xp, xn;
+                if (valid) {
+                    xu = slot_row(i * 3 + 0);
+                    xp = slot_row(i * 3 + 1);
+                    xn = slot_row(i * 3 + 2);
+                } else {
 #pragma unroll
-                        for (int a = 0; a < IT; ++a) {
-                            const int ch = gl + a * G;
-                            if (ch < nch) {
-                                sh_cp_async16(slot(i, 0, a), pu + (size_t)ch * 4);
-                                sh_cp_async16(slot(i, 1, a), pp + (size_t)ch * 4);
-                                sh_cp_async16(slot(i, 2, a), pn + (size_t)ch * 4);
-                            }
-                        }
-                        if (gl < 3) {
-                            const float* lin = gl == 0 ? C.user[qu].lin : (gl == 1 ? C.item[qp].lin : C.item[qn].lin);
-                            const uint32_t lrow = gl == 0 ? u / W : (gl == 1 ? ip / W : in / W);
-                            if (lin) bias_r[i] = __ldcg(lin + lrow);
-                        }
-                    }
-                    sh_cp_async_commit();
+                    for (int a = 0; a < IT; ++a) xu.c[a] = xp.c[a] = xn.c[a] = Vec<4>::zero();
                 }
+                const float bu = __shfl_sync(0xffffffffu, bias_r[i], 0, G);
+                const float bip = __shfl_sync(0xffffffffu, bias_r[i], 1, G);
+                const float bin = __shfl_sync(0xffffffffu, bias_r[i], 2, G);
+                // linear.py:78: s = <u, v> + b_u + b_i; loss.py:7-9: h = s- - s+ + 1, d/ds = [h >= 0] / B
+                const float sp = (group_sum<G>(row_dot_partial(xu, xp)) + bu) + bip;
+                const float sn = (group_sum<G>(row_dot_partial(xu, xn)) + bu) + bin;
+                const float h = __fadd_rn(__fsub_rn(sn, sp), 1.0f);
+                const float g = (h >= 0.f) ? invB : 0.f;
+                if (valid) {
+                    if (gl == 0) hsum += fmaxf(h, 0.f);
+                    const uint32_t qu = q & 15u, qp = (q >> 4) & 15u, qn = (q >> 8) & 15u;
+                    float* du = C.stage_u[qu] + (size_t)b * dim;
+                    float* dp = C.stage_i[qp] + (size_t)b * dim;
+                    float* dn = C.stage_i[qn] + (size_t)(Bs + b) * dim;
 #pragma unroll
-                for (int i = 0; i < SH_SB; ++i) {
-                    sh_cp_async_wait(SH_SB - 1 - i);
-                    const uint32_t b = __shfl_sync(0xffffffffu, rb[i / G], i % G, G);
-                    const uint32_t ip = __shfl_sync(0xffffffffu, rp[i / G], i % G, G);
-                    const uint32_t in = __shfl_sync(0xffffffffu, rn[i / G], i % G, G);
-                    const uint32_t u = __shfl_sync(0xffffffffu, ru[i / G], i % G, G);
-                    const bool valid = b != 0xFFFFFFFFu;
-                    Row<4, IT> xu, xp, xn;
-                    if (valid) {
-                        xu = slot_row(i, 0);
-                        xp = slot_row(i, 1);
-                        xn = slot_row(i, 2);
-                    } else {
+                    for (int a = 0; a < IT; ++a) {
+                        const int ch = gl + a * G;
+                        if (ch < nch) {
+                            Vec<4> gu, gp, gn;
 #pragma unroll
-                        for (int a = 0; a < IT; ++a) xu.c[a] = xp.c[a] = xn.c[a] = Vec<4>::zero();
-                    }
-                    const float bu = __shfl_sync(0xffffffffu, bias_r[i], 0, G);
-                    const float bip = __shfl_sync(0xffffffffu, bias_r[i], 1, G);
-                    const float bin = __shfl_sync(0xffffffffu, bias_r[i], 2, G);
-                    // linear.py:78: s = <u, v> + b_u + b_i; loss.py:7-9: h = s- - s+ + 1, d/ds = [h >= 0] / B
-                    const float sp = (group_sum<G>(row_dot_partial(xu, xp)) + bu) + bip;
-                    const float sn = (group_sum<G>(row_dot_partial(xu, xn)) + bu) + bin;
-                    const float h = __fadd_rn(__fsub_rn(sn, sp), 1.0f);
-                    const float g = (h >= 0.f) ? invB : 0.f;
-                    if (valid) {
-                        if (gl == 0) hsum += fmaxf(h, 0.f);
-                        const uint32_t qu = u % W, qp = ip % W, qn = in % W;
-                        float* du = C.stage_u[qu] + (size_t)b * dim;
-                        float* dp = C.stage_i[qp] + (size_t)b * dim;
-                        float* dn = C.stage_i[qn] + (size_t)(Bs + b) * dim;
-#pragma unroll
-                        for (int a = 0; a < IT; ++a) {
-                            const int ch = gl + a * G;
-                            if (ch < nch) {
-                                Vec<4> gu, gp, gn;
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    gu[e] = g * (xn.c[a][e] - xp.c[a][e]);
-                                    gp[e] = -g * xu.c[a][e];
-                                    gn[e] = g * xu.c[a][e];
-                                }
-                                gu.st(du + (size_t)ch * 4);
-                                gp.st(dp + (size_t)ch * 4);
-                                gn.st(dn + (size_t)ch * 4);
+                            for (int e = 0; e < 4; ++e) {
+                                gu[e] = g * (xn.c[a][e] - xp.c[a][e]);
+                                gp[e] = -g * xu.c[a][e];
+                                gn[e] = g * xu.c[a][e];
                             }
+                            gu.st(du + (size_t)ch * 4);
+                            gp.st(dp + (size_t)ch * 4);
+                            gn.st(dn + (size_t)ch * 4);
                         }
-                        if (gl == 0) {
-                            C.stage_b[qp][b] = -g;
-                            C.stage_b[qn][Bs + b] = g;
-                        }
+                    }
+                    if (gl == 0) {
+                        C.stage_b[qp][b] = -g;
+                        C.stage_b[qn][Bs + b] = g;
                     }
                 }
             }
         }
+        if (nS <= gfirst - goff && more) fetch_records(recA, lo + ep.batch, nS_next, gfirst);  // no round ran
+        nS_cur = nS_next;
+        // descriptors of my first phase-B round: plan data, in flight across the barrier
+        Desc dB;
+        fetch_descs(dB, lo, nU, nI, gfirst);
+
         hsum = warp_sum(hsum);
         if ((threadIdx.x & 31) == 0) s_loss[threadIdx.x >> 5] = hsum;
         __syncthreads();
@@ -452,79 +538,91 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
             C.loss_part[(size_t)si * cpr + c] = H;
         }
         ++bar_no;
-        cross_rank_barrier(C, sync_epoch + bar_no, bar_no * (unsigned)cpr, timeout_ns);
+        cross_rank_barrier(C, sync_epoch + bar_no, bar_no * (unsigned)cpr, timeout_ns, true);
 
         // ------------------------------ phase B ------------------------------------------
-        // owned rows: a row group takes sorted position k; only the first position of a run of equal rows works
-#pragma unroll 1
-        for (int space = 0; space < 2; ++space) {
-            const trs_table& t = space ? C.item[me] : C.user[me];
-            const int mult = space ? 2 : 1;
-            const uint32_t* K = (space ? C.ikey : C.ukey) + (size_t)mult * lo;
-            const uint32_t* P = (space ? C.ival : C.uval) + (size_t)mult * lo;
-            const int n = (int)C.own_cnt[2 * s + space];
-            const float* stage = space ? C.stage_i[me] : C.stage_u[me];
-            const float* stage_b = (space && t.lin) ? C.stage_b[me] : nullptr;
-            struct Seg {
-                bool head;
-                int k;
-                uint32_t key;
-                Row<4, IT> g, p, s0, s1;
-                float gb, pl, l0, l1;
-            };
-            auto seg_load = [&](Seg& S, int k) {
-                S.head = false;
-                S.k = k;
-                if (k >= n) return;
-                const uint32_t key = K[k];
-                if (k > 0 && K[k - 1] == key) return;
-                S.head = true;
-                S.key = key;
-                const uint32_t j = P[k];
-                const size_t roff = (size_t)key * dim;
-                S.g = ld_row(stage + (size_t)j * dim);
-                S.p = ld_row(t.emb + roff);
+        // owned rows: a row group takes PB positions of the step's sorted list per round; only the first position
+        // of a run of equal rows works (it sums the run's staged rows in slot order)
+        {
+            const int nP = nU + nI;
+            for (int p0 = gfirst - goff; p0 < nP; p0 += gstride * PB) {  // warp-uniform trip count
+                const int pb = p0 + goff;
+                float bsc[PB];  // lanes 0..3: staged bias gradient, bias, its state 0 / 1 of position i
 #pragma unroll
-                for (int a = 0; a < IT; ++a) S.s0.c[a] = S.s1.c[a] = Vec<4>::zero();
-                if (kind != TRS_OPT_SGD) S.s0 = ld_row(t.emb_s0 + roff);
-                if (kind == TRS_OPT_SPARSE_ADAM) S.s1 = ld_row(t.emb_s1 + roff);
-                S.gb = S.pl = S.l0 = S.l1 = 0.f;
-                if (stage_b && gl == 0) {
-                    S.gb = __ldcg(stage_b + j);
-                    S.pl = __ldcg(t.lin + key);
-                    if (kind != TRS_OPT_SGD) S.l0 = __ldcg(t.lin_s0 + key);
-                    if (kind == TRS_OPT_SPARSE_ADAM) S.l1 = __ldcg(t.lin_s1 + key);
+                for (int i = 0; i < PB; ++i) {
+                    const uint32_t key = __shfl_sync(0xffffffffu, dB.key[i / G], i % G, G);
+                    const uint32_t sf = __shfl_sync(0xffffffffu, dB.sf[i / G], i % G, G);
+                    const uint32_t sl = sf & 0x1FFFFFFFu;
+                    bsc[i] = 0.f;
+                    if (sf & (1u << 29)) {
+                        const bool it = (sf >> 31) != 0u;
+                        const trs_table& t = it ? tI : tU;
+                        const size_t roff = (size_t)key * dim;
+                        copy_row(i * 4 + 0, (it ? my_stage_i : my_stage_u) + (size_t)sl * dim);
+                        copy_row(i * 4 + 1, t.emb + roff);
+                        if (KIND != TRS_OPT_SGD) copy_row(i * 4 + 2, t.emb_s0 + roff);
+                        if (KIND == TRS_OPT_SPARSE_ADAM) copy_row(i * 4 + 3, t.emb_s1 + roff);
+                        if (it && item_lin && gl < 4) {
+                            if (gl == 0) bsc[i] = __ldcg(my_stage_b + sl);
+                            else if (gl == 1) bsc[i] = __ldcg(t.lin + key);
+                            else if (gl == 2) { if (KIND != TRS_OPT_SGD) bsc[i] = __ldcg(t.lin_s0 + key); }
+                            else { if (KIND == TRS_OPT_SPARSE_ADAM) bsc[i] = __ldcg(t.lin_s1 + key); }
+                        }
+                    }
+                    sh_cp_async_commit();
                 }
-            };
-            auto seg_finish = [&](Seg& S) {
-                if (!S.head) return;
-                for (int q = S.k + 1; q < n && K[q] == S.key; ++q) {  // duplicates, in slot order
-                    const uint32_t j = P[q];
-                    const Row<4, IT> r = ld_row(stage + (size_t)j * dim);
+                Desc cur = dB;
+                if (p0 + gstride * PB < nP) fetch_descs(dB, lo, nU, nI, pb + gstride * PB);
 #pragma unroll
-                    for (int a = 0; a < IT; ++a)
+                for (int i = 0; i < PB; ++i) {
+                    sh_cp_async_wait(PB - 1 - i);
+                    const uint32_t key = __shfl_sync(0xffffffffu, cur.key[i / G], i % G, G);
+                    const uint32_t sf = __shfl_sync(0xffffffffu, cur.sf[i / G], i % G, G);
+                    const bool it = (sf >> 31) != 0u;
+                    float gb = 0.f, pl = 0.f, l0 = 0.f, l1 = 0.f;
+                    if (G < 32 || it) {  // one row group per warp: the branch is warp-uniform
+                        gb = __shfl_sync(0xffffffffu, bsc[i], 0, G);
+                        pl = __shfl_sync(0xffffffffu, bsc[i], 1, G);
+                        if (KIND != TRS_OPT_SGD) l0 = __shfl_sync(0xffffffffu, bsc[i], 2, G);
+                        if (KIND == TRS_OPT_SPARSE_ADAM) l1 = __shfl_sync(0xffffffffu, bsc[i], 3, G);
+                    }
+                    if (!(sf & (1u << 29))) continue;
+                    const trs_table& t = it ? tI : tU;
+                    Row<4, IT> g = slot_row(i * 4 + 0), p = slot_row(i * 4 + 1), s0, s1;
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) S.g.c[a][e] = __fadd_rn(S.g.c[a][e], r.c[a][e]);
-                    if (stage_b && gl == 0) S.gb = __fadd_rn(S.gb, __ldcg(stage_b + j));
+                    for (int a = 0; a < IT; ++a) s0.c[a] = s1.c[a] = Vec<4>::zero();
+                    if (KIND != TRS_OPT_SGD) s0 = slot_row(i * 4 + 2);
+                    if (KIND == TRS_OPT_SPARSE_ADAM) s1 = slot_row(i * 4 + 3);
+                    if (sf & (1u << 30)) {  // duplicates (rare under uniform ids): the rest of the run, in slot order
+                        const int pos = pb + i * gstride;
+                        const int k = it ? pos - nU : pos, n = it ? nI : nU;
+                        const uint32_t* K = it ? C.ikey + 2 * lo : C.ukey + lo;
+                        const uint32_t* P = it ? C.ival + 2 * lo : C.uval + lo;
+                        const float* stage = it ? my_stage_i : my_stage_u;
+                        for (int q = k + 1; q < n && __ldg(K + q) == key; ++q) {
+                            const uint32_t j = __ldg(P + q);
+                            const Row<4, IT> r = ld_row(stage + (size_t)j * dim);
+#pragma unroll
+                            for (int a = 0; a < IT; ++a)
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) g.c[a][e] = __fadd_rn(g.c[a][e], r.c[a][e]);
+                            if (it && item_lin && gl == 0) gb = __fadd_rn(gb, __ldcg(my_stage_b + j));
+                        }
+                    }
+                    sh_update_store<KIND, IT>(t, (size_t)key * dim, nch, gl, G, opt, scale, p, s0, s1, g);
+                    if (it && item_lin && gl == 0) {
+                        OptScalars ok = opt;
+                        ok.kind = KIND;
+                        opt_update(ok, scale, gb, pl, l0, l1);
+                        t.lin[key] = pl;
+                        if (KIND != TRS_OPT_SGD) t.lin_s0[key] = l0;
+                        if (KIND == TRS_OPT_SPARSE_ADAM) t.lin_s1[key] = l1;
+                    }
                 }
-                sh_update_store<IT>(t, (size_t)S.key * dim, nch, gl, G, opt, scale, S.p, S.s0, S.s1, S.g);
-                if (stage_b && gl == 0) {
-                    opt_update(opt, scale, S.gb, S.pl, S.l0, S.l1);
-                    t.lin[S.key] = S.pl;
-                    if (kind != TRS_OPT_SGD) t.lin_s0[S.key] = S.l0;
-                    if (kind == TRS_OPT_SPARSE_ADAM) t.lin_s1[S.key] = S.l1;
-                }
-            };
-            for (int k = gfirst; k < n; k += 2 * gstride) {  // two rows in flight per group
-                Seg A, B_;
-                seg_load(A, k);
-                seg_load(B_, k + gstride);
-                seg_finish(A);
-                seg_finish(B_);
             }
         }
         ++bar_no;
-        cross_rank_barrier(C, sync_epoch + bar_no, bar_no * (unsigned)cpr, timeout_ns);
+        cross_rank_barrier(C, sync_epoch + bar_no, bar_no * (unsigned)cpr, timeout_ns, false);
     }
 
     // per-step hinge sums of this rank, CTAs added in a fixed order
@@ -555,17 +653,47 @@ static ShardStage shard_stage_layout(int dim, int64_t B) {
     return L;
 }
 
-template <int G, int IT>
-static cudaError_t launch_shard(const ShardCtx* ctx0, const ShardCtx* ctxs, int cpr, int n_local, const trs_epoch* ep,
-                                const OptScalars* os, int first_step, int n_steps, unsigned sync_epoch,
-                                unsigned long long timeout_ns, cudaStream_t stream) {
-    const void* fn = (const void*)shard_train_kernel<G, IT>;
+template <int KIND, int G, int IT>
+static cudaError_t launch_shard_k(const ShardCtx* ctx0, const ShardCtx* ctxs, int cpr, int n_local, const trs_epoch* ep,
+                                  const OptScalars* os, int first_step, int n_steps, unsigned sync_epoch,
+                                  unsigned long long timeout_ns, cudaStream_t stream) {
+    const void* fn = (const void*)shard_train_kernel<KIND, G, IT>;
     const size_t smem = shard_smem_bytes<IT>();
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     void* args[] = {(void*)ctx0, (void*)&ctxs, (void*)&cpr, (void*)ep, (void*)os, (void*)&first_step,
                     (void*)&n_steps, (void*)&sync_epoch, (void*)&timeout_ns};
     return cudaLaunchCooperativeKernel(fn, dim3(cpr * n_local), dim3(shard_threads<IT>()), args, smem, stream);
+}
+template <int G, int IT>
+static cudaError_t launch_shard(const ShardCtx* ctx0, const ShardCtx* ctxs, int cpr, int n_local, const trs_epoch* ep,
+                                const OptScalars* os, int first_step, int n_steps, unsigned sync_epoch,
+                                unsigned long long timeout_ns, cudaStream_t stream) {
+    switch (os->kind) {
+        case TRS_OPT_SGD:
+            return launch_shard_k<TRS_OPT_SGD, G, IT>(ctx0, ctxs, cpr, n_local, ep, os, first_step, n_steps, sync_epoch, timeout_ns, stream);
+        case TRS_OPT_ADAGRAD:
+            return launch_shard_k<TRS_OPT_ADAGRAD, G, IT>(ctx0, ctxs, cpr, n_local, ep, os, first_step, n_steps, sync_epoch, timeout_ns, stream);
+        default:
+            return launch_shard_k<TRS_OPT_SPARSE_ADAM, G, IT>(ctx0, ctxs, cpr, n_local, ep, os, first_step, n_steps, sync_epoch, timeout_ns, stream);
+    }
+}
+
+// Row shape of the sharded kernel: lanes per row group x 16-byte chunks per lane.  Two chunks per lane wherever a
+// row has >= 8 chunks: the per-row bookkeeping (shuffles, addresses, branches) is paid once per lane and is most
+// of the kernel's instructions.
+static int g_shard_prefer_it = 2;
+static bool pick_shard_shape(int dim, int* G, int* IT) {
+    if (dim <= 0 || dim % 4 || dim > 512) return false;
+    const int nch = dim / 4;
+    int it = nch >= 8 ? g_shard_prefer_it : 1;
+    int g = 4;
+    while (g * it < nch && g < 32) g <<= 1;
+    while (g * it < nch) it <<= 1;
+    if (it == 3) it = 4;
+    *G = g;
+    *IT = it;
+    return it <= 4;
 }
 
 static int check_shard(const trs_shard* sh, RowShape* shape) {
@@ -743,19 +871,32 @@ extern "C" int trs_shard_train_steps(const trs_shard* shards, int n_local, const
     const OptScalars os = make_opt_scalars(optim);
     const unsigned long long timeout_ns = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 20000) * 1000000ull;
     cudaError_t err = cudaErrorInvalidValue;
-    const int key = shape.G * 100 + shape.IT;
-    switch (key) {
-        case 401: err = launch_shard<4, 1>(&ctx[0], ctxs_dev, cpr, n_local, ep, &os, first_step, n_steps, (unsigned)sync_epoch, timeout_ns, st); break;
-        case 801: err = launch_shard<8, 1>(&ctx[0], ctxs_dev, cpr, n_local, ep, &os, first_step, n_steps, (unsigned)sync_epoch, timeout_ns, st); break;
-        case 1601: err = launch_shard<16, 1>(&ctx[0], ctxs_dev, cpr, n_local, ep, &os, first_step, n_steps, (unsigned)sync_epoch, timeout_ns, st); break;
-        case 3201: err = launch_shard<32, 1>(&ctx[0], ctxs_dev, cpr, n_local, ep, &os, first_step, n_steps, (unsigned)sync_epoch, timeout_ns, st); break;
-        case 3202: err = launch_shard<32, 2>(&ctx[0], ctxs_dev, cpr, n_local, ep, &os, first_step, n_steps, (unsigned)sync_epoch, timeout_ns, st); break;
-        case 3204: err = launch_shard<32, 4>(&ctx[0], ctxs_dev, cpr, n_local, ep, &os, first_step, n_steps, (unsigned)sync_epoch, timeout_ns, st); break;
+    int sg = 0, sit = 0;
+    TRS_REQUIRE(pick_shard_shape(shards[0].dim, &sg, &sit), "unsupported n_factors %d", shards[0].dim);
+#define TRS_SHARD_CASE(G_, IT_)                                                                                     \
+    case G_ * 100 + IT_:                                                                                            \
+        err = launch_shard<G_, IT_>(&ctx[0], ctxs_dev, cpr, n_local, ep, &os, first_step, n_steps, (unsigned)sync_epoch, \
+                                    timeout_ns, st);                                                                \
+        break;
+    switch (sg * 100 + sit) {
+        TRS_SHARD_CASE(4, 1)
+        TRS_SHARD_CASE(8, 1)
+        TRS_SHARD_CASE(16, 1)
+        TRS_SHARD_CASE(32, 1)
+        TRS_SHARD_CASE(4, 2)
+        TRS_SHARD_CASE(8, 2)
+        TRS_SHARD_CASE(16, 2)
+        TRS_SHARD_CASE(32, 2)
+        TRS_SHARD_CASE(32, 4)
         default: break;
     }
+#undef TRS_SHARD_CASE
     TRS_CUDA(err);
     return TRS_OK;
 }
+
+// tuning hook (not part of trs.h; results do not depend on it): chunks per lane the sharded kernel prefers (1 or 2)
+extern "C" void trs_debug_shard_chunks_per_lane(int it) { g_shard_prefer_it = it == 1 ? 1 : 2; }
 
 // ---- CUDA IPC plumbing ---------------------------------------------------------------------------------------
 extern "C" int trs_ipc_export(const void* ptr, void* handle64_host, uint64_t* offset_host) {
