@@ -193,6 +193,7 @@ struct ShardCtx {  // everything one (virtual) rank needs; copied to shared memo
     float* loss_part;  // [n_steps][cta_per_rank]
     float* loss_out;   // [n_steps]
     int* status;
+    unsigned long long* trace;  // debug (trs_debug_shard_trace): [n_steps][cta_per_rank][8] globaltimer stamps, or NULL
 };
 
 // sync words of one rank: word 0 = its own grid-barrier counter (memset before every launch: no peer touches it),
@@ -438,6 +439,8 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
         const bool more = si + 1 < n_steps;
         const int nS_next = more ? (int)C.samp_cnt[s + 1] : 0;
 
+        unsigned long long* tr = C.trace ? C.trace + ((size_t)si * cpr + c) * 8 : nullptr;
+        if (tr && threadIdx.x == 0) tr[0] = shard_now_ns();
         // ------------------------------ phase A ------------------------------------------
         float hsum = 0.f;
         for (int k0 = gfirst - goff; k0 < nS; k0 += gstride * SB) {  // warp-uniform trip count
@@ -536,9 +539,11 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
 #pragma unroll
             for (int w = 0; w < NT / 32; ++w) H += s_loss[w];
             C.loss_part[(size_t)si * cpr + c] = H;
+            if (tr) tr[1] = shard_now_ns();
         }
         ++bar_no;
         cross_rank_barrier(C, sync_epoch + bar_no, bar_no * (unsigned)cpr, timeout_ns, true);
+        if (tr && threadIdx.x == 0) tr[2] = shard_now_ns();
 
         // ------------------------------ phase B ------------------------------------------
         // owned rows: a row group takes PB positions of the step's sorted list per round; only the first position
@@ -621,8 +626,13 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                 }
             }
         }
+        if (tr) {
+            __syncthreads();
+            if (threadIdx.x == 0) tr[3] = shard_now_ns();
+        }
         ++bar_no;
         cross_rank_barrier(C, sync_epoch + bar_no, bar_no * (unsigned)cpr, timeout_ns, false);
+        if (tr && threadIdx.x == 0) tr[4] = shard_now_ns();
     }
 
     // per-step hinge sums of this rank, CTAs added in a fixed order
@@ -683,6 +693,7 @@ static cudaError_t launch_shard(const ShardCtx* ctx0, const ShardCtx* ctxs, int 
 // row has >= 8 chunks: the per-row bookkeeping (shuffles, addresses, branches) is paid once per lane and is most
 // of the kernel's instructions.
 static int g_shard_prefer_it = 2;
+static unsigned long long* g_shard_trace = nullptr;
 static bool pick_shard_shape(int dim, int* G, int* IT) {
     if (dim <= 0 || dim % 4 || dim > 512) return false;
     const int nch = dim / 4;
@@ -860,6 +871,7 @@ extern "C" int trs_shard_train_steps(const trs_shard* shards, int n_local, const
         c.loss_part = loss_part + (size_t)i * steps * cpr;
         c.loss_out = loss_sum_host[i];
         c.status = status;
+        c.trace = g_shard_trace ? g_shard_trace + (size_t)i * n_steps * cpr * 8 : nullptr;
         // the rank's own grid-barrier counter restarts with every launch (peers never touch it)
         TRS_CUDA(cudaMemsetAsync(sh.sync[sh.rank], 0, sizeof(unsigned), st));
     }
@@ -897,6 +909,9 @@ extern "C" int trs_shard_train_steps(const trs_shard* shards, int n_local, const
 
 // tuning hook (not part of trs.h; results do not depend on it): chunks per lane the sharded kernel prefers (1 or 2)
 extern "C" void trs_debug_shard_chunks_per_lane(int it) { g_shard_prefer_it = it == 1 ? 1 : 2; }
+// debug hook: device buffer of n_local * n_steps * CTAs-per-rank * 8 uint64 that the next launches fill with phase
+// time stamps (tools/shard_phases.py); NULL switches it off
+extern "C" void trs_debug_shard_trace(void* buf) { g_shard_trace = (unsigned long long*)buf; }
 
 // ---- CUDA IPC plumbing ---------------------------------------------------------------------------------------
 extern "C" int trs_ipc_export(const void* ptr, void* handle64_host, uint64_t* offset_host) {
