@@ -173,13 +173,70 @@ route_scatter_kernel(const int64_t* __restrict__ a, const int64_t* __restrict__ 
     }
 }
 
+// ---- which of a rank's samples read an item row that the PREVIOUS step updates ("dirty") ----------------------
+// The kernel fetches the item rows of step s+1 while step s's owners are still updating (phase B): legal for every
+// row step s does not touch.  Per step a hashed bitmap of the item rows looked up anywhere in the GLOBAL batch;
+// a sample's lookup whose bit is set in the previous step's bitmap is flagged in its samp entry (bit 30: positive,
+// bit 31: negative) and read after the step barrier instead.  False positives only cost latency.
+__device__ __forceinline__ uint32_t dirty_hash(uint32_t id, int log2_bits, bool exact) {
+    return exact ? id : (id * 2654435761u) >> (32 - log2_bits);
+}
+__global__ void __launch_bounds__(RT_THREADS)
+dirty_bitmap_kernel(const int64_t* __restrict__ pos, const int64_t* __restrict__ neg, int64_t n_samples, int B,
+                    uint32_t* __restrict__ bitmap, int log2_bits, bool exact) {
+    const int64_t step = blockIdx.y;
+    const int Bs = (int)min((int64_t)B, n_samples - step * B);
+    const int64_t s0 = step * (int64_t)B;
+    uint32_t* bm = bitmap + ((size_t)step << (log2_bits - 5));
+#pragma unroll
+    for (int r = 0; r < RT_ROWS; ++r) {
+        const int j = blockIdx.x * RT_TILE + r * RT_THREADS + threadIdx.x;
+        if (j < 2 * Bs) {
+            const uint32_t h = dirty_hash(route_id(pos, neg, s0, Bs, j), log2_bits, exact);
+            atomicOr(bm + (h >> 5), 1u << (h & 31u));
+        }
+    }
+}
+__global__ void __launch_bounds__(RT_THREADS)
+dirty_mark_kernel(const int64_t* __restrict__ pos, const int64_t* __restrict__ neg, int64_t n_samples, int B,
+                  const uint32_t* __restrict__ bitmap, int log2_bits, bool exact, const uint32_t* __restrict__ samp_cnt,
+                  uint32_t* __restrict__ samp) {
+    const int64_t step = blockIdx.y;
+    const int64_t s0 = step * (int64_t)B;
+    const int n = (int)samp_cnt[step];
+    const uint32_t* bm = step > 0 ? bitmap + ((size_t)(step - 1) << (log2_bits - 5)) : nullptr;
+#pragma unroll
+    for (int r = 0; r < RT_ROWS; ++r) {
+        const int k = blockIdx.x * RT_TILE + r * RT_THREADS + threadIdx.x;
+        if (k < n) {
+            const uint32_t b = samp[s0 + k];
+            uint32_t fl = 3u;  // the first step of a plan: nothing is known about the step before it
+            if (bm) {
+                const uint32_t hp = dirty_hash((uint32_t)pos[s0 + b], log2_bits, exact);
+                const uint32_t hn = dirty_hash((uint32_t)neg[s0 + b], log2_bits, exact);
+                fl = ((bm[hp >> 5] >> (hp & 31u)) & 1u) | (((bm[hn >> 5] >> (hn & 31u)) & 1u) << 1);
+            }
+            samp[s0 + k] = b | (fl << 30);
+        }
+    }
+}
+// bits of a step's bitmap: 16x the item lookups of a step (6 % false positives), or one bit per item if that is less
+static int dirty_log2_bits(const trs_epoch* ep, int64_t n_items, bool* exact) {
+    int lb = 10;
+    while (((int64_t)1 << lb) < 32ll * ep->batch && lb < 28) ++lb;
+    int le = 5;
+    while (((int64_t)1 << le) < n_items) ++le;
+    *exact = le <= lb;
+    return *exact ? le : lb;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------
 // Thread-private 16-byte shared-memory slots per chunk a lane owns: phase A keeps SB samples x {user, positive,
 // negative} row in flight per row group, phase B PB owned rows x {gradient, parameter, state 0, state 1}.
 template <int IT>
-constexpr int shard_slots() { return IT == 1 ? 24 : 12; }
+constexpr int shard_slots() { return 12; }
 
 struct ShardCtx {  // everything one (virtual) rank needs; copied to shared memory by each of its CTAs
     int rank, world, dim, pad;
@@ -312,6 +369,43 @@ __device__ __forceinline__ void sh_update_store(const trs_table& t, size_t roff,
     }
 }
 
+// ---- bulk async copies (TMA engine, no tensor map) completing on an mbarrier: the cross-step prefetch ---------
+__device__ __forceinline__ uint32_t sh_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sh_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sh_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sh_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(sh_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sh_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sh_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool sh_mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(sh_smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void sh_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sh_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(sh_smem_u32(bar))
+                 : "memory");
+}
+
+// samples per row group whose item rows are fetched a step ahead (IT == 1 only: shared memory)
+template <int IT>
+constexpr int shard_pf_samples() { return IT == 1 ? 7 : 0; }  // 7: what fits beside the 12 row slots in 227 KB
+template <int G, int IT>
+constexpr size_t shard_smem_total() {
+    constexpr size_t NT = shard_threads<IT>(), GPB = NT / G, PFS = shard_pf_samples<IT>();
+    return shard_smem_bytes<IT>() + GPB * PFS * 2 * ((size_t)G * IT * 16 + 16) + GPB * 8;
+}
+
 template <int KIND, int G, int IT>
 __global__ void __launch_bounds__((shard_threads<IT>()), 1)
 shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __restrict__ ctxs, const int cpr,
@@ -323,10 +417,16 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
     constexpr int PB = shard_slots<IT>() / 4;  // owned rows in flight per row group (phase B)
     constexpr int RPL = (SB + G - 1) / G;      // sample records a lane fetches per phase-A round
     constexpr int DPL = (PB + G - 1) / G;      // row descriptors a lane fetches per phase-B round
+    constexpr int PFS = shard_pf_samples<IT>();
+    constexpr int NPR = PFS ? (PFS + SB - 1) / SB : 1;  // phase-A rounds whose records are fetched a step ahead
+    constexpr int ROWB = G * IT * 16;          // bytes of a prefetched row's shared-memory slot
     __shared__ ShardCtx C;
     __shared__ float s_loss[NT / 32];
-    extern __shared__ __align__(16) unsigned char sh_smem[];
+    extern __shared__ __align__(128) unsigned char sh_smem[];
     float4* rows = reinterpret_cast<float4*>(sh_smem);  // [slot][IT][NT]
+    unsigned char* pf_rows = sh_smem + shard_smem_bytes<IT>();             // [GPB][PFS][2][ROWB]
+    unsigned char* pf_bias = pf_rows + (size_t)GPB * PFS * 2 * ROWB;       // [GPB][PFS][2][16]
+    uint64_t* pf_bars = reinterpret_cast<uint64_t*>(pf_bias + (size_t)GPB * PFS * 2 * 16);  // [GPB]
 
     const int vr = blockIdx.x / cpr, c = blockIdx.x % cpr;
     {
@@ -334,12 +434,17 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
         uint32_t* dst = reinterpret_cast<uint32_t*>(&C);
         for (int i = threadIdx.x; i < (int)(sizeof(ShardCtx) / 4); i += NT) dst[i] = src[i];
     }
+    const int gl = threadIdx.x % G, g_in_cta = threadIdx.x / G;
+    uint64_t* const my_bar = pf_bars + g_in_cta;
+    unsigned char* const my_pf_rows = pf_rows + (size_t)g_in_cta * PFS * 2 * ROWB;
+    unsigned char* const my_pf_bias = pf_bias + (size_t)g_in_cta * PFS * 2 * 16;
+    if (PFS && gl == 0) sh_mbar_init(my_bar, 1);
+    if (PFS) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     const uint32_t W = (uint32_t)C.world;
     const bool wpow2 = (W & (W - 1u)) == 0u;
     const int wshift = __ffs((int)W) - 1;
     const int me = C.rank, dim = C.dim, nch = dim / 4;
-    const int gl = threadIdx.x % G, g_in_cta = threadIdx.x / G;
     const int gfirst = c * GPB + g_in_cta, gstride = cpr * GPB;
     const int goff = g_in_cta % GPW;  // my group's position inside its warp: loops run on the warp's first group
     auto slot = [&](int j, int a) { return rows + ((j * IT + a) * NT + threadIdx.x); };
@@ -349,6 +454,15 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
         for (int a = 0; a < IT; ++a) {
             x.c[a] = Vec<4>::zero();
             if (gl + a * G < nch) x.c[a].v = *slot(j, a);
+        }
+        return x;
+    };
+    auto pf_row = [&](int j) {  // prefetched row j (= 2 * sample ordinal + {0 positive, 1 negative}) of my group
+        Row<4, IT> x;
+#pragma unroll
+        for (int a = 0; a < IT; ++a) {
+            x.c[a] = Vec<4>::zero();
+            if (gl + a * G < nch) x.c[a].v = *reinterpret_cast<const float4*>(my_pf_rows + (size_t)j * ROWB + (gl + a * G) * 16);
         }
         return x;
     };
@@ -369,8 +483,8 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
     unsigned bar_no = 0;  // cross-rank barriers passed in this launch
 
     // ---- records of a phase-A round: lane gl fetches samples gl, gl + G, ... of the round and splits their ids
-    //      into (owner, local row) ONCE (plan + epoch data: immutable, so the NEXT step's first round is fetched a
-    //      whole step ahead).  q packs the three owners, 4 bits each ----
+    //      into (owner, local row) ONCE (plan + epoch data: immutable, so the NEXT step's first rounds are fetched
+    //      a whole step ahead).  b = position in the step | dirty flags << 30; q packs the three owners ----
     struct Rec { uint32_t b[RPL], q[RPL], lu[RPL], lp[RPL], ln[RPL]; };
     auto split = [&](uint32_t id, uint32_t& owner, uint32_t& local) {
         if (wpow2) { owner = id & (W - 1u); local = id >> wshift; }
@@ -385,8 +499,9 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
             R.b[z] = 0xFFFFFFFFu;
             R.q[z] = R.lu[z] = R.lp[z] = R.ln[z] = 0u;
             if (i < SB && k < nS_) {
-                const uint32_t b = __ldg(samp + k);
-                R.b[z] = b;
+                const uint32_t bf = __ldg(samp + k);
+                const uint32_t b = bf & 0x3FFFFFFFu;
+                R.b[z] = bf;
                 uint32_t qu, qp, qn;
                 split((uint32_t)__ldg(ep.user + lo_ + b), qu, R.lu[z]);
                 split((uint32_t)__ldg(ep.pos + lo_ + b), qp, R.lp[z]);
@@ -420,13 +535,16 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
         }
     };
 
-    Rec recA;
+    Rec recN[NPR];      // records of the next phase A's first NPR rounds
     int nS_cur = 0;
     {
         const int64_t lo0 = (int64_t)first_step * ep.batch;
         nS_cur = (int)C.samp_cnt[first_step];
-        fetch_records(recA, lo0, nS_cur, gfirst);
+#pragma unroll
+        for (int r = 0; r < NPR; ++r) fetch_records(recN[r], lo0, nS_cur, gfirst + r * gstride * SB);
     }
+    bool pf_live = false;     // the current step's first rounds have prefetched item rows (all but the dirty ones)
+    uint32_t pf_parity = 0;
 
     for (int si = 0; si < n_steps; ++si) {
         const int64_t s = first_step + si;
@@ -438,52 +556,73 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
         const int nU = (int)C.own_cnt[2 * s], nI = (int)C.own_cnt[2 * s + 1];
         const bool more = si + 1 < n_steps;
         const int nS_next = more ? (int)C.samp_cnt[s + 1] : 0;
-
         unsigned long long* tr = C.trace ? C.trace + ((size_t)si * cpr + c) * 8 : nullptr;
         if (tr && threadIdx.x == 0) tr[0] = shard_now_ns();
+
         // ------------------------------ phase A ------------------------------------------
         float hsum = 0.f;
-        for (int k0 = gfirst - goff; k0 < nS; k0 += gstride * SB) {  // warp-uniform trip count
+        if (PFS && pf_live) {  // rows fetched while the previous step's owners were updating: landed?
+            while (!sh_mbar_try_wait(my_bar, pf_parity)) {
+            }
+            pf_parity ^= 1u;
+        }
+        int rnd = 0;
+        for (int k0 = gfirst - goff; k0 < nS; k0 += gstride * SB, ++rnd) {  // warp-uniform trip count
             const int kb = k0 + goff;
+            Rec cur;
+            if (rnd < NPR) {
+#pragma unroll
+                for (int r = 0; r < NPR; ++r)
+                    if (r == rnd) cur = recN[r];
+            } else {
+                fetch_records(cur, lo, nS, kb);
+            }
+            const bool pf_round = PFS && pf_live && rnd < NPR;  // this round's clean item rows sit in shared memory
             float bias_r[SB];  // lane t < 3 holds the width-1 companion of lookup t (user, positive, negative)
 #pragma unroll
             for (int i = 0; i < SB; ++i) {
-                const uint32_t b = __shfl_sync(0xffffffffu, recA.b[i / G], i % G, G);
-                const uint32_t q = __shfl_sync(0xffffffffu, recA.q[i / G], i % G, G);
-                const uint32_t lu = __shfl_sync(0xffffffffu, recA.lu[i / G], i % G, G);
-                const uint32_t lp = __shfl_sync(0xffffffffu, recA.lp[i / G], i % G, G);
-                const uint32_t ln = __shfl_sync(0xffffffffu, recA.ln[i / G], i % G, G);
+                const uint32_t bf = __shfl_sync(0xffffffffu, cur.b[i / G], i % G, G);
+                const uint32_t q = __shfl_sync(0xffffffffu, cur.q[i / G], i % G, G);
+                const uint32_t lu = __shfl_sync(0xffffffffu, cur.lu[i / G], i % G, G);
+                const uint32_t lp = __shfl_sync(0xffffffffu, cur.lp[i / G], i % G, G);
+                const uint32_t ln = __shfl_sync(0xffffffffu, cur.ln[i / G], i % G, G);
                 bias_r[i] = 0.f;
-                if (b != 0xFFFFFFFFu) {
+                if (bf != 0xFFFFFFFFu) {
+                    const bool pfs = pf_round && rnd * SB + i < PFS;
+                    const bool have_p = pfs && !(bf & (1u << 30)), have_n = pfs && !(bf & (1u << 31));
                     const trs_table& TU = C.user[q & 15u];
                     const trs_table& TP = C.item[(q >> 4) & 15u];
                     const trs_table& TN = C.item[(q >> 8) & 15u];
                     copy_row(i * 3 + 0, TU.emb + (size_t)lu * dim);
-                    copy_row(i * 3 + 1, TP.emb + (size_t)lp * dim);
-                    copy_row(i * 3 + 2, TN.emb + (size_t)ln * dim);
+                    if (!have_p) copy_row(i * 3 + 1, TP.emb + (size_t)lp * dim);
+                    if (!have_n) copy_row(i * 3 + 2, TN.emb + (size_t)ln * dim);
                     if (gl < 3) {
                         const float* lin = gl == 0 ? TU.lin : (gl == 1 ? TP.lin : TN.lin);
                         const uint32_t lrow = gl == 0 ? lu : (gl == 1 ? lp : ln);
-                        if (lin) bias_r[i] = __ldcg(lin + lrow);
+                        const bool have = gl == 1 ? have_p : (gl == 2 ? have_n : false);
+                        if (lin) {
+                            if (have) bias_r[i] = reinterpret_cast<const float*>(
+                                          my_pf_bias + (size_t)((rnd * SB + i) * 2 + (gl - 1)) * 16)[lrow & 3u];
+                            else bias_r[i] = __ldcg(lin + lrow);
+                        }
                     }
                 }
                 sh_cp_async_commit();
             }
-            Rec cur = recA;
-            // the next round's records -- or, after the last round, the next step's first round
-            if (k0 + gstride * SB < nS) fetch_records(recA, lo, nS, kb + gstride * SB);
-            else if (more) fetch_records(recA, lo + ep.batch, nS_next, gfirst);
 #pragma unroll
             for (int i = 0; i < SB; ++i) {
                 sh_cp_async_wait(SB - 1 - i);
-                const uint32_t b = __shfl_sync(0xffffffffu, cur.b[i / G], i % G, G);
+                const uint32_t bf = __shfl_sync(0xffffffffu, cur.b[i / G], i % G, G);
                 const uint32_t q = __shfl_sync(0xffffffffu, cur.q[i / G], i % G, G);
-                const bool valid = b != 0xFFFFFFFFu;
+                const bool valid = bf != 0xFFFFFFFFu;
+                const uint32_t b = bf & 0x3FFFFFFFu;
                 Row<4, IT> xu, xp, xn;
                 if (valid) {
+                    const bool pfs = pf_round && rnd * SB + i < PFS;
+                    const bool have_p = pfs && !(bf & (1u << 30)), have_n = pfs && !(bf & (1u << 31));
                     xu = slot_row(i * 3 + 0);
-                    xp = slot_row(i * 3 + 1);
-                    xn = slot_row(i * 3 + 2);
+                    xp = have_p ? pf_row((rnd * SB + i) * 2 + 0) : slot_row(i * 3 + 1);
+                    xn = have_n ? pf_row((rnd * SB + i) * 2 + 1) : slot_row(i * 3 + 2);
                 } else {
 #pragma unroll
                     for (int a = 0; a < IT; ++a) xu.c[a] = xp.c[a] = xn.c[a] = Vec<4>::zero();
@@ -525,9 +664,13 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                 }
             }
         }
-        if (nS <= gfirst - goff && more) fetch_records(recA, lo + ep.batch, nS_next, gfirst);  // no round ran
+        // the next step's first rounds of records (plan + epoch data), then my first phase-B descriptors: all in
+        // flight across the barrier
+        if (more) {
+#pragma unroll
+            for (int r = 0; r < NPR; ++r) fetch_records(recN[r], lo + ep.batch, nS_next, gfirst + r * gstride * SB);
+        }
         nS_cur = nS_next;
-        // descriptors of my first phase-B round: plan data, in flight across the barrier
         Desc dB;
         fetch_descs(dB, lo, nU, nI, gfirst);
 
@@ -546,6 +689,42 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
         if (tr && threadIdx.x == 0) tr[2] = shard_now_ns();
 
         // ------------------------------ phase B ------------------------------------------
+        // First the NEXT step's item rows: every clean one (not updated by this step, plan flag) of my group's
+        // first PFS samples starts its trip -- from the owner's HBM, mostly over NVLink -- into shared memory now
+        // and lands while the owners update (bulk async copies, one mbarrier per row group).  The lane that holds a
+        // sample's record issues its copies.
+        pf_live = false;
+        if (PFS && more) {
+#pragma unroll
+            for (int r = 0; r < NPR; ++r) {
+#pragma unroll
+                for (int z = 0; z < RPL; ++z) {
+                    const int i = gl + z * G;
+                    const uint32_t bf = recN[r].b[z];
+                    if (i < SB && r * SB + i < PFS && bf != 0xFFFFFFFFu) {
+                        const uint32_t q = recN[r].q[z];
+                        const trs_table& TP = C.item[(q >> 4) & 15u];
+                        const trs_table& TN = C.item[(q >> 8) & 15u];
+                        const bool fp = !(bf & (1u << 30)), fn = !(bf & (1u << 31));
+                        const uint32_t per = (uint32_t)dim * 4u + (TP.lin ? 16u : 0u);
+                        const uint32_t bytes = (fp ? per : 0u) + (fn ? per : 0u);
+                        if (bytes) sh_mbar_expect_tx(my_bar, bytes);
+                        const int j = (r * SB + i) * 2;
+                        if (fp) {
+                            sh_bulk_g2s(my_pf_rows + (size_t)j * ROWB, TP.emb + (size_t)recN[r].lp[z] * dim, (uint32_t)dim * 4u, my_bar);
+                            if (TP.lin) sh_bulk_g2s(my_pf_bias + (size_t)j * 16, TP.lin + (recN[r].lp[z] & ~3u), 16u, my_bar);
+                        }
+                        if (fn) {
+                            sh_bulk_g2s(my_pf_rows + (size_t)(j + 1) * ROWB, TN.emb + (size_t)recN[r].ln[z] * dim, (uint32_t)dim * 4u, my_bar);
+                            if (TN.lin) sh_bulk_g2s(my_pf_bias + (size_t)(j + 1) * 16, TN.lin + (recN[r].ln[z] & ~3u), 16u, my_bar);
+                        }
+                    }
+                }
+            }
+            __syncwarp();  // every expect_tx of the group precedes its one arrival
+            if (gl == 0) sh_mbar_arrive(my_bar);
+            pf_live = true;
+        }
         // owned rows: a row group takes PB positions of the step's sorted list per round; only the first position
         // of a run of equal rows works (it sums the run's staged rows in slot order)
         {
@@ -668,7 +847,7 @@ static cudaError_t launch_shard_k(const ShardCtx* ctx0, const ShardCtx* ctxs, in
                                   const OptScalars* os, int first_step, int n_steps, unsigned sync_epoch,
                                   unsigned long long timeout_ns, cudaStream_t stream) {
     const void* fn = (const void*)shard_train_kernel<KIND, G, IT>;
-    const size_t smem = shard_smem_bytes<IT>();
+    const size_t smem = shard_smem_total<G, IT>();
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     void* args[] = {(void*)ctx0, (void*)&ctxs, (void*)&cpr, (void*)ep, (void*)os, (void*)&first_step,
@@ -689,10 +868,10 @@ static cudaError_t launch_shard(const ShardCtx* ctx0, const ShardCtx* ctxs, int 
     }
 }
 
-// Row shape of the sharded kernel: lanes per row group x 16-byte chunks per lane.  Two chunks per lane wherever a
-// row has >= 8 chunks: the per-row bookkeeping (shuffles, addresses, branches) is paid once per lane and is most
-// of the kernel's instructions.
-static int g_shard_prefer_it = 2;
+// Row shape of the sharded kernel: lanes per row group x 16-byte chunks per lane.  One chunk per lane where the row
+// allows it (dim <= 128): only that shape leaves the shared memory for the cross-step prefetch of item rows.  (Two
+// chunks per lane halve the per-row bookkeeping instructions; measured equal at one rank, trs_debug_shard_chunks_per_lane.)
+static int g_shard_prefer_it = 1;
 static unsigned long long* g_shard_trace = nullptr;
 static bool pick_shard_shape(int dim, int* G, int* IT) {
     if (dim <= 0 || dim % 4 || dim > 512) return false;
@@ -737,10 +916,16 @@ static size_t shard_tmp_pairs_bytes(const trs_epoch* ep) {
 }
 static int route_tiles(const trs_epoch* ep) { return (int)((2ll * ep->batch + RT_TILE - 1) / RT_TILE); }
 
+static size_t dirty_bitmap_bytes(const trs_epoch* ep) {
+    bool exact;
+    const int lb = dirty_log2_bits(ep, (int64_t)1 << 40, &exact);  // the hashed size: an exact bitmap is never larger
+    return (((size_t)n_steps_of(ep) << lb) / 8 + 255) / 256 * 256;
+}
+
 extern "C" size_t trs_shard_plan_tmp_bytes(const trs_epoch* ep) {
     if (!ep || ep->batch <= 0) return 0;
     const size_t tile_cnt = ((size_t)n_steps_of(ep) * route_tiles(ep) * sizeof(uint32_t) + 255) / 256 * 256;
-    return shard_tmp_pairs_bytes(ep) + tile_cnt + hist_bytes(ep);
+    return shard_tmp_pairs_bytes(ep) + tile_cnt + (hist_bytes(ep) + 255) / 256 * 256 + dirty_bitmap_bytes(ep);
 }
 
 extern "C" int trs_shard_plan_build(const trs_shard* sh, const trs_epoch* ep, void* plan, size_t plan_bytes,
@@ -792,6 +977,16 @@ extern "C" int trs_shard_plan_build(const trs_shard* sh, const trs_epoch* ep, vo
     };
     space(ep->user, ep->user, 1, sh->n_users, (uint32_t*)(P + L.ukey), (uint32_t*)(P + L.uval), 0);
     space(ep->pos, ep->neg, 2, sh->n_items, (uint32_t*)(P + L.ikey), (uint32_t*)(P + L.ival), 1);
+    {   // dirty flags of the rank's samples (see dirty_bitmap_kernel)
+        bool exact;
+        const int lb = dirty_log2_bits(ep, sh->n_items, &exact);
+        uint32_t* bitmap = (uint32_t*)((char*)hist + (hist_bytes(ep) + 255) / 256 * 256);
+        TRS_CUDA(cudaMemsetAsync(bitmap, 0, ((size_t)steps << lb) / 8, st));
+        dim3 g2((unsigned)((2ll * ep->batch + RT_TILE - 1) / RT_TILE), (unsigned)steps);
+        dirty_bitmap_kernel<<<g2, RT_THREADS, 0, st>>>(ep->pos, ep->neg, n, ep->batch, bitmap, lb, exact);
+        dim3 g1((unsigned)(((int64_t)ep->batch + RT_TILE - 1) / RT_TILE), (unsigned)steps);
+        dirty_mark_kernel<<<g1, RT_THREADS, 0, st>>>(ep->pos, ep->neg, n, ep->batch, bitmap, lb, exact, samp_cnt, samp);
+    }
     TRS_CUDA(cudaGetLastError());
     return TRS_OK;
 }
