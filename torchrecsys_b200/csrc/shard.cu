@@ -239,7 +239,7 @@ template <int IT>
 constexpr int shard_slots() { return 12; }
 
 struct ShardCtx {  // everything one (virtual) rank needs; copied to shared memory by each of its CTAs
-    int rank, world, dim, pad;
+    int rank, world, dim, split_b;  // split_b (tuning): update the user rows behind a rank-local barrier first
     trs_table user[TRS_MAX_RANKS];
     trs_table item[TRS_MAX_RANKS];
     float* stage_u[TRS_MAX_RANKS];  // [B, dim]   gradient rows of the user lookups, slot = sample position in the step
@@ -253,9 +253,9 @@ struct ShardCtx {  // everything one (virtual) rank needs; copied to shared memo
     unsigned long long* trace;  // debug (trs_debug_shard_trace): [n_steps][cta_per_rank][8] globaltimer stamps, or NULL
 };
 
-// sync words of one rank: word 0 = its own grid-barrier counter (memset before every launch: no peer touches it),
-// word 64 + 32 * q = the number of the last cross-rank barrier rank q has reached (monotonic over launches)
-__device__ __forceinline__ unsigned* flag_of(unsigned* sync, int q) { return sync + 64 + 32 * q; }
+// sync words of one rank (zeroed ONCE when allocated): word 64 = arrivals at cross-rank barriers, added to by every
+// CTA of every rank, never reset; word 16 = arrivals of the rank's own CTAs at rank-local barriers (memset before
+// every launch: no peer touches it)
 
 __device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
     asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -302,48 +302,87 @@ constexpr int shard_threads() { return IT <= 2 ? 512 : 256; }
 template <int IT>
 constexpr size_t shard_smem_bytes() { return (size_t)shard_threads<IT>() * shard_slots<IT>() * IT * 16; }
 
-// Cross-rank barrier number e (1-based over the life of the group).  Every CTA of the rank arrives on the rank's
-// own counter; the last one posts e into every rank's flag words; everybody waits until all W flags of ITS OWN
-// sync words have reached e.  Writes of all threads happen-before the flag: bar.sync -> thread 0: fence -> atomic
-// -> (last CTA) fence.sys -> flag stores -> (peer) relaxed polls + fence.sys.  `remote_writes`: the phase before
-// the barrier stored into PEER memory (gradient rows): each CTA's fence is then system-scope, so that its own
-// stores are acknowledged by the peer before it arrives; after a phase that only wrote local memory (the owner's
-// update: peers read those rows through THIS GPU's L2) a gpu-scope fence per CTA is enough.  A group of one rank
-// never leaves gpu scope.  Fences are the expensive part of the barrier (a system-scope fence waits for every
-// outstanding store of the SM): there is exactly one per CTA on the way in and one on the way out.
-__device__ __forceinline__ void cross_rank_barrier(const ShardCtx& C, unsigned e, unsigned local_target,
+// ---- barriers -------------------------------------------------------------------------------------------------
+// One mechanism for both kinds: a monotonic arrival counter per rank (word 64 of its sync words: cross-rank; word
+// 16: the rank's own CTAs, restarted with every launch).  A CTA arrives with ONE release fence (bar.sync before it:
+// the stores of its whole CTA happen before the fence) followed by a relaxed add of 1 to the counter of every rank
+// it must meet, polls its OWN rank's counter with relaxed loads until all arrivals of this barrier are in, and ends
+// the wait with one acquire load (the counter is a chain of read-modify-writes: reading its final value
+// synchronises with every arrival).
+//   * the fence is SYSTEM scope only after a phase that stored into peer memory (the gradient rows: they must have
+//     landed before the peer sees the arrival).  After the owners' update -- stores into the rank's OWN memory, which
+//     peers read over NVLink through this GPU's L2 -- a gpu-scope fence puts them there.
+//   * measured on 2 x B200 with no work between barriers: 8.7 us per barrier with a release-add per peer plus an
+//     acq_rel.sys fence after the wait (each system-scope fence costs 2-3 us), and ~10 us with the
+//     sequentially-consistent __threadfence_system() of a last-CTA-posts-flags scheme.
+// Arrivals are never reset across launches: the target only depends on how many barriers the group has passed,
+// e * CTAs-per-rank * world.
+__device__ __forceinline__ void red_relaxed_sys(unsigned* p) {
+    asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ void red_relaxed_gpu(unsigned* p) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+__device__ __forceinline__ void spin_until(const ShardCtx& C, const unsigned* cnt, unsigned target, bool sys,
+                                           unsigned long long timeout_ns) {
+    volatile int* status = C.status;
+    const unsigned long long t0 = shard_now_ns();
+    unsigned spins = 0;
+    while ((int)((sys ? ld_relaxed_sys(cnt) : ld_relaxed_gpu(cnt)) - target) < 0) {
+        if ((++spins & 1023u) == 0) {
+            if (*status != 0) break;
+            if (shard_now_ns() - t0 > timeout_ns) {
+                atomicExch(C.status, 1);
+                break;
+            }
+        }
+    }
+}
+
+// the CTAs of ONE rank (gpu scope)
+__device__ __forceinline__ void rank_barrier(const ShardCtx& C, unsigned target, unsigned long long timeout_ns) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned* cnt = C.sync[C.rank] + 16;
+        fence_acq_rel_gpu();
+        red_relaxed_gpu(cnt);
+        spin_until(C, cnt, target, false, timeout_ns);
+        (void)ld_acquire_gpu(cnt);
+    }
+    __syncthreads();
+}
+
+// every CTA of every rank; e = number of this barrier over the life of the group (1-based)
+__device__ __forceinline__ void cross_rank_barrier(const ShardCtx& C, unsigned e, unsigned cpr,
                                                    unsigned long long timeout_ns, bool remote_writes) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned* mine = C.sync[C.rank];
-        const bool multi = C.world > 1;
-        if (multi && remote_writes) __threadfence_system(); else __threadfence();
-        const unsigned old = atomicAdd(mine, 1u);
-        if (old + 1u == local_target) {
-            if (multi) {
-                __threadfence_system();
-                for (int q = 0; q < C.world; ++q) st_relaxed_sys(flag_of(C.sync[q], C.rank), e);
-            } else {
-                __threadfence();
-                st_relaxed_gpu(flag_of(mine, 0), e);
-            }
+        unsigned* mine = C.sync[C.rank] + 64;
+        const unsigned target = e * cpr * (unsigned)C.world;
+        if (C.world > 1) {
+            if (remote_writes) fence_acq_rel_sys(); else fence_acq_rel_gpu();
+            for (int q = 0; q < C.world; ++q) red_relaxed_sys(C.sync[q] + 64);
+            spin_until(C, mine, target, true, timeout_ns);
+            (void)ld_acquire_sys(mine);
+        } else {
+            fence_acq_rel_gpu();
+            red_relaxed_gpu(mine);
+            spin_until(C, mine, target, false, timeout_ns);
+            (void)ld_acquire_gpu(mine);
         }
-        volatile int* status = C.status;
-        const unsigned long long t0 = shard_now_ns();
-        for (int q = 0; q < C.world; ++q) {
-            const unsigned* f = flag_of(mine, q);
-            unsigned spins = 0;
-            while ((int)((multi ? ld_relaxed_sys(f) : ld_relaxed_gpu(f)) - e) < 0) {
-                if ((++spins & 1023u) == 0) {
-                    if (*status != 0) break;
-                    if (shard_now_ns() - t0 > timeout_ns) {
-                        atomicExch(C.status, 1);
-                        break;
-                    }
-                }
-            }
-        }
-        if (multi) __threadfence_system(); else __threadfence();
     }
     __syncthreads();
 }
@@ -398,11 +437,11 @@ __device__ __forceinline__ void sh_bulk_g2s(void* smem_dst, const void* gsrc, ui
 }
 
 // samples per row group whose item rows are fetched a step ahead (IT == 1 only: shared memory)
-template <int IT>
-constexpr int shard_pf_samples() { return IT == 1 ? 7 : 0; }  // 7: what fits beside the 12 row slots in 227 KB
+template <int G, int IT>
+constexpr int shard_pf_samples() { return IT == 1 ? (G >= 8 ? 7 : 6) : 0; }  // what fits beside the 12 row slots in 227 KB
 template <int G, int IT>
 constexpr size_t shard_smem_total() {
-    constexpr size_t NT = shard_threads<IT>(), GPB = NT / G, PFS = shard_pf_samples<IT>();
+    constexpr size_t NT = shard_threads<IT>(), GPB = NT / G, PFS = shard_pf_samples<G, IT>();
     return shard_smem_bytes<IT>() + GPB * PFS * 2 * ((size_t)G * IT * 16 + 16) + GPB * 8;
 }
 
@@ -417,7 +456,8 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
     constexpr int PB = shard_slots<IT>() / 4;  // owned rows in flight per row group (phase B)
     constexpr int RPL = (SB + G - 1) / G;      // sample records a lane fetches per phase-A round
     constexpr int DPL = (PB + G - 1) / G;      // row descriptors a lane fetches per phase-B round
-    constexpr int PFS = shard_pf_samples<IT>();
+    constexpr int PFS = shard_pf_samples<G, IT>();
+    static_assert(shard_smem_total<G, IT>() + 2048 <= 227 * 1024, "shared memory budget");
     constexpr int NPR = PFS ? (PFS + SB - 1) / SB : 1;  // phase-A rounds whose records are fetched a step ahead
     constexpr int ROWB = G * IT * 16;          // bytes of a prefetched row's shared-memory slot
     __shared__ ShardCtx C;
@@ -480,7 +520,8 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
     float* const my_stage_u = C.stage_u[me];
     float* const my_stage_i = C.stage_i[me];
     const float* const my_stage_b = C.stage_b[me];
-    unsigned bar_no = 0;  // cross-rank barriers passed in this launch
+    unsigned bar_no = 0;   // cross-rank barriers passed in this launch
+    unsigned lbar_no = 0;  // barriers of this rank alone
 
     // ---- records of a phase-A round: lane gl fetches samples gl, gl + G, ... of the round and splits their ids
     //      into (owner, local row) ONCE (plan + epoch data: immutable, so the NEXT step's first rounds are fetched
@@ -515,13 +556,13 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
     // sf = slot | flags << 29; flag bits: 1 head (first position of a run of equal rows), 2 the run continues,
     // 4 item space
     struct Desc { uint32_t key[DPL], sf[DPL]; };
-    auto fetch_descs = [&](Desc& Dd, int64_t lo_, int nU_, int nI_, int pb) {
+    auto fetch_descs = [&](Desc& Dd, int64_t lo_, int nU_, int nI_, int pb, int pend) {
 #pragma unroll
         for (int z = 0; z < DPL; ++z) {
             const int i = gl + z * G;
             const int p = pb + i * gstride;
             Dd.key[z] = Dd.sf[z] = 0u;
-            if (i < PB && p < nU_ + nI_) {
+            if (i < PB && p < pend) {
                 const bool it = p >= nU_;
                 const int k = it ? p - nU_ : p, n = it ? nI_ : nU_;
                 const uint32_t* K = it ? C.ikey + 2 * lo_ : C.ukey + lo_;
@@ -671,65 +712,11 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
             for (int r = 0; r < NPR; ++r) fetch_records(recN[r], lo + ep.batch, nS_next, gfirst + r * gstride * SB);
         }
         nS_cur = nS_next;
-        Desc dB;
-        fetch_descs(dB, lo, nU, nI, gfirst);
-
-        hsum = warp_sum(hsum);
-        if ((threadIdx.x & 31) == 0) s_loss[threadIdx.x >> 5] = hsum;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float H = 0.f;
-#pragma unroll
-            for (int w = 0; w < NT / 32; ++w) H += s_loss[w];
-            C.loss_part[(size_t)si * cpr + c] = H;
-            if (tr) tr[1] = shard_now_ns();
-        }
-        ++bar_no;
-        cross_rank_barrier(C, sync_epoch + bar_no, bar_no * (unsigned)cpr, timeout_ns, true);
-        if (tr && threadIdx.x == 0) tr[2] = shard_now_ns();
-
-        // ------------------------------ phase B ------------------------------------------
-        // First the NEXT step's item rows: every clean one (not updated by this step, plan flag) of my group's
-        // first PFS samples starts its trip -- from the owner's HBM, mostly over NVLink -- into shared memory now
-        // and lands while the owners update (bulk async copies, one mbarrier per row group).  The lane that holds a
-        // sample's record issues its copies.
-        pf_live = false;
-        if (PFS && more) {
-#pragma unroll
-            for (int r = 0; r < NPR; ++r) {
-#pragma unroll
-                for (int z = 0; z < RPL; ++z) {
-                    const int i = gl + z * G;
-                    const uint32_t bf = recN[r].b[z];
-                    if (i < SB && r * SB + i < PFS && bf != 0xFFFFFFFFu) {
-                        const uint32_t q = recN[r].q[z];
-                        const trs_table& TP = C.item[(q >> 4) & 15u];
-                        const trs_table& TN = C.item[(q >> 8) & 15u];
-                        const bool fp = !(bf & (1u << 30)), fn = !(bf & (1u << 31));
-                        const uint32_t per = (uint32_t)dim * 4u + (TP.lin ? 16u : 0u);
-                        const uint32_t bytes = (fp ? per : 0u) + (fn ? per : 0u);
-                        if (bytes) sh_mbar_expect_tx(my_bar, bytes);
-                        const int j = (r * SB + i) * 2;
-                        if (fp) {
-                            sh_bulk_g2s(my_pf_rows + (size_t)j * ROWB, TP.emb + (size_t)recN[r].lp[z] * dim, (uint32_t)dim * 4u, my_bar);
-                            if (TP.lin) sh_bulk_g2s(my_pf_bias + (size_t)j * 16, TP.lin + (recN[r].lp[z] & ~3u), 16u, my_bar);
-                        }
-                        if (fn) {
-                            sh_bulk_g2s(my_pf_rows + (size_t)(j + 1) * ROWB, TN.emb + (size_t)recN[r].ln[z] * dim, (uint32_t)dim * 4u, my_bar);
-                            if (TN.lin) sh_bulk_g2s(my_pf_bias + (size_t)(j + 1) * 16, TN.lin + (recN[r].ln[z] & ~3u), 16u, my_bar);
-                        }
-                    }
-                }
-            }
-            __syncwarp();  // every expect_tx of the group precedes its one arrival
-            if (gl == 0) sh_mbar_arrive(my_bar);
-            pf_live = true;
-        }
-        // owned rows: a row group takes PB positions of the step's sorted list per round; only the first position
-        // of a run of equal rows works (it sums the run's staged rows in slot order)
-        {
-            const int nP = nU + nI;
-            for (int p0 = gfirst - goff; p0 < nP; p0 += gstride * PB) {  // warp-uniform trip count
+        // Phase B over positions [pbeg, pend) of the step's owned-lookup list; dB holds my first round's descriptors.
+        // A row group takes PB positions per round; only the first position of a run of equal rows works (it sums
+        // the run's staged rows in slot order).
+        auto phase_b = [&](Desc& dB, int pbeg, int pend) {
+            for (int p0 = pbeg + gfirst - goff; p0 < pend; p0 += gstride * PB) {  // warp-uniform trip count
                 const int pb = p0 + goff;
                 float bsc[PB];  // lanes 0..3: staged bias gradient, bias, its state 0 / 1 of position i
 #pragma unroll
@@ -756,7 +743,7 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                     sh_cp_async_commit();
                 }
                 Desc cur = dB;
-                if (p0 + gstride * PB < nP) fetch_descs(dB, lo, nU, nI, pb + gstride * PB);
+                if (p0 + gstride * PB < pend) fetch_descs(dB, lo, nU, nI, pb + gstride * PB, pend);
 #pragma unroll
                 for (int i = 0; i < PB; ++i) {
                     sh_cp_async_wait(PB - 1 - i);
@@ -804,13 +791,89 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                     }
                 }
             }
+        };
+        // The NEXT step's item rows: every clean one (not updated by this step, plan flag) of my group's first PFS
+        // samples starts its trip -- from the owner's HBM, mostly over NVLink -- into shared memory and lands while
+        // the owners update (bulk async copies, one mbarrier per row group).  The lane that holds a sample's record
+        // issues its copies.
+        auto issue_prefetch = [&]() {
+            pf_live = false;
+            if (PFS && more) {
+#pragma unroll
+                for (int r = 0; r < NPR; ++r) {
+#pragma unroll
+                    for (int z = 0; z < RPL; ++z) {
+                        const int i = gl + z * G;
+                        const uint32_t bf = recN[r].b[z];
+                        if (i < SB && r * SB + i < PFS && bf != 0xFFFFFFFFu) {
+                            const uint32_t q = recN[r].q[z];
+                            const trs_table& TP = C.item[(q >> 4) & 15u];
+                            const trs_table& TN = C.item[(q >> 8) & 15u];
+                            const bool fp = !(bf & (1u << 30)), fn = !(bf & (1u << 31));
+                            const uint32_t per = (uint32_t)dim * 4u + (TP.lin ? 16u : 0u);
+                            const uint32_t bytes = (fp ? per : 0u) + (fn ? per : 0u);
+                            if (bytes) sh_mbar_expect_tx(my_bar, bytes);
+                            const int j = (r * SB + i) * 2;
+                            if (fp) {
+                                sh_bulk_g2s(my_pf_rows + (size_t)j * ROWB, TP.emb + (size_t)recN[r].lp[z] * dim, (uint32_t)dim * 4u, my_bar);
+                                if (TP.lin) sh_bulk_g2s(my_pf_bias + (size_t)j * 16, TP.lin + (recN[r].lp[z] & ~3u), 16u, my_bar);
+                            }
+                            if (fn) {
+                                sh_bulk_g2s(my_pf_rows + (size_t)(j + 1) * ROWB, TN.emb + (size_t)recN[r].ln[z] * dim, (uint32_t)dim * 4u, my_bar);
+                                if (TN.lin) sh_bulk_g2s(my_pf_bias + (size_t)(j + 1) * 16, TN.lin + (recN[r].ln[z] & ~3u), 16u, my_bar);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();  // every expect_tx of the group precedes its one arrival
+                if (gl == 0) sh_mbar_arrive(my_bar);
+                pf_live = true;
+            }
+        };
+
+        hsum = warp_sum(hsum);
+        if ((threadIdx.x & 31) == 0) s_loss[threadIdx.x >> 5] = hsum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float H = 0.f;
+#pragma unroll
+            for (int w = 0; w < NT / 32; ++w) H += s_loss[w];
+            C.loss_part[(size_t)si * cpr + c] = H;
+            if (tr) tr[1] = shard_now_ns();
+        }
+        const int nP = nU + nI;
+        Desc dB;
+        if (W > 1 && C.split_b) {
+            // Several ranks: the gradient rows of USER lookups are staged by this rank's own CTAs only (samples run on
+            // their user row's owner), so the user rows update behind a barrier of THIS rank -- while the rows just
+            // stored into the peers' staging buffers drain over NVLink -- and the cross-rank barrier sits between
+            // the user rows and the item rows.
+            fetch_descs(dB, lo, nU, nI, gfirst, nU);
+            ++lbar_no;
+            rank_barrier(C, lbar_no * (unsigned)cpr, timeout_ns);
+            if (tr && threadIdx.x == 0) tr[5] = shard_now_ns();
+            issue_prefetch();
+            phase_b(dB, 0, nU);
+            fetch_descs(dB, lo, nU, nI, nU + gfirst, nP);
+            if (tr && threadIdx.x == 0) tr[6] = shard_now_ns();
+            ++bar_no;
+            cross_rank_barrier(C, sync_epoch + bar_no, (unsigned)cpr, timeout_ns, true);
+            if (tr && threadIdx.x == 0) tr[2] = shard_now_ns();
+            phase_b(dB, nU, nP);
+        } else {
+            fetch_descs(dB, lo, nU, nI, gfirst, nP);  // plan data: in flight across the barrier
+            ++bar_no;
+            cross_rank_barrier(C, sync_epoch + bar_no, (unsigned)cpr, timeout_ns, true);
+            if (tr && threadIdx.x == 0) tr[2] = shard_now_ns();
+            issue_prefetch();
+            phase_b(dB, 0, nP);
         }
         if (tr) {
             __syncthreads();
             if (threadIdx.x == 0) tr[3] = shard_now_ns();
         }
         ++bar_no;
-        cross_rank_barrier(C, sync_epoch + bar_no, bar_no * (unsigned)cpr, timeout_ns, false);
+        cross_rank_barrier(C, sync_epoch + bar_no, (unsigned)cpr, timeout_ns, false);
         if (tr && threadIdx.x == 0) tr[4] = shard_now_ns();
     }
 
@@ -873,6 +936,7 @@ static cudaError_t launch_shard(const ShardCtx* ctx0, const ShardCtx* ctxs, int 
 // chunks per lane halve the per-row bookkeeping instructions; measured equal at one rank, trs_debug_shard_chunks_per_lane.)
 static int g_shard_prefer_it = 1;
 static unsigned long long* g_shard_trace = nullptr;
+static int g_shard_split_b = 0;
 static bool pick_shard_shape(int dim, int* G, int* IT) {
     if (dim <= 0 || dim % 4 || dim > 512) return false;
     const int nch = dim / 4;
@@ -1038,6 +1102,7 @@ extern "C" int trs_shard_train_steps(const trs_shard* shards, int n_local, const
         c.rank = sh.rank;
         c.world = sh.world;
         c.dim = sh.dim;
+        c.split_b = g_shard_split_b;
         for (int q = 0; q < sh.world; ++q) {
             TRS_REQUIRE(sh.user[q].emb && sh.item[q].emb && sh.stage[q] && sh.sync[q], "rank %d: peer %d is not mapped",
                         sh.rank, q);
@@ -1068,7 +1133,7 @@ extern "C" int trs_shard_train_steps(const trs_shard* shards, int n_local, const
         c.status = status;
         c.trace = g_shard_trace ? g_shard_trace + (size_t)i * n_steps * cpr * 8 : nullptr;
         // the rank's own grid-barrier counter restarts with every launch (peers never touch it)
-        TRS_CUDA(cudaMemsetAsync(sh.sync[sh.rank], 0, sizeof(unsigned), st));
+        TRS_CUDA(cudaMemsetAsync(sh.sync[sh.rank], 0, 128, st));  // words 0 and 16
     }
     const ShardCtx* ctxs_dev = nullptr;
     if (n_local > 1) {  // emulation of a whole group on one GPU (tests): contexts travel through the workspace
@@ -1107,6 +1172,9 @@ extern "C" void trs_debug_shard_chunks_per_lane(int it) { g_shard_prefer_it = it
 // debug hook: device buffer of n_local * n_steps * CTAs-per-rank * 8 uint64 that the next launches fill with phase
 // time stamps (tools/shard_phases.py); NULL switches it off
 extern "C" void trs_debug_shard_trace(void* buf) { g_shard_trace = (unsigned long long*)buf; }
+// tuning hook: 1 = several ranks update their user rows behind a rank-local barrier while the gradient rows stored
+// into peer memory drain, and meet the peers between the user rows and the item rows (results do not change)
+extern "C" void trs_debug_shard_split_b(int on) { g_shard_split_b = on ? 1 : 0; }
 
 // ---- CUDA IPC plumbing ---------------------------------------------------------------------------------------
 extern "C" int trs_ipc_export(const void* ptr, void* handle64_host, uint64_t* offset_host) {
