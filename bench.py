@@ -681,26 +681,31 @@ def sharded_bench(args, wl, name):
     parity = shard_parity_check(dev, world, rank) if world > 1 else None
     tr = ShardedLinearTrainer(wl["n_users"], wl["n_items"], D, global_batch=Bg, optimizer=wl["opt"], lr=wl["lr"],
                               device=dev, emulate_world=emu or (1 if world == 1 else None))
-    # every rank's loader output: (K + W) steps of its own B samples (in emulation this process holds all G of them)
+    # every rank's loader output: (K + W) steps of its own B samples, stored [step, {user, positive}, B] so that a
+    # run of steps is one contiguous block (in emulation this process holds all G ranks' outputs)
     mine = list(range(G)) if world == 1 else [rank]
-    ids_h = {q: [torch.from_numpy(a).pin_memory() for a in synth_ids(wl, (K + W) * B, seed=1234 + q)] for q in mine}
-    ids_d = {q: [t.to(dev) for t in v] for q, v in ids_h.items()}
+
+    def loader_output(q):
+        import numpy as np
+        u, p = synth_ids(wl, (K + W) * B, seed=1234 + q)
+        return torch.from_numpy(np.stack([u.reshape(K + W, B), p.reshape(K + W, B)], 1)).pin_memory()
+
+    ids_h = {q: loader_output(q) for q in mine}
+    ids_d = {q: t.to(dev) for q, t in ids_h.items()}
 
     def global_epoch(src, lo_step, n_steps):
         """All ranks' samples of steps [lo_step, lo_step + n_steps) in loader order: step-major, rank-major inside a
-        step.  One all-gather per id column and epoch (NCCL) -- the only collective besides the loss all-reduce."""
-        cols = []
-        for c in range(2):
-            if world > 1:
-                part = src[rank][c][lo_step * B:(lo_step + n_steps) * B]
-                if not part.is_cuda:
-                    part = part.to(dev, non_blocking=True)
-                allr = torch.empty(world * n_steps * B, dtype=torch.int64, device=dev)
-                dist.all_gather_into_tensor(allr, part.contiguous())
-            else:
-                allr = torch.cat([src[q][c][lo_step * B:(lo_step + n_steps) * B].to(dev, non_blocking=True) for q in mine])
-            cols.append(allr.view(G, n_steps, B).permute(1, 0, 2).reshape(-1))
-        return cols
+        step.  ONE all-gather per epoch (NCCL) -- the only collective besides the loss all-reduce."""
+        if world > 1:
+            part = src[rank][lo_step:lo_step + n_steps]
+            if not part.is_cuda:
+                part = part.to(dev, non_blocking=True)
+            allr = torch.empty((world,) + tuple(part.shape), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allr, part)
+        else:
+            allr = torch.stack([src[q][lo_step:lo_step + n_steps].to(dev, non_blocking=True) for q in mine])
+        cols = allr.permute(2, 1, 0, 3).contiguous()     # [G, steps, 2, B] -> [2, steps, G, B]
+        return cols[0].view(-1), cols[1].view(-1)
 
     seen = [0]
 

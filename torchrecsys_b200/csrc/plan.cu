@@ -65,6 +65,7 @@ sort_hist_kernel(SortSrc src, uint32_t* __restrict__ hist, int tiles, int64_t n_
     const int Bs = (int)min((int64_t)B, n_samples - step * B);
     // len_arr (pairs only): the segment of step s holds len_arr[s * len_stride] pairs instead of mult * B_s
     const int len = len_arr ? (int)len_arr[step * len_stride] : mult * Bs;
+    if (tile * SORT_TILE >= len) return;  // a tile beyond the segment: the scatter pass never reads its counts
     s_hist[threadIdx.x] = 0;
     __syncthreads();
 #pragma unroll
@@ -93,6 +94,8 @@ sort_scatter_kernel(SortSrc src, uint32_t* __restrict__ dst_key, uint32_t* __res
     const int tile = blockIdx.x;
     const int Bs = (int)min((int64_t)B, n_samples - step * B);
     const int len = len_arr ? (int)len_arr[step * len_stride] : mult * Bs;
+    if (tile * SORT_TILE >= len) return;
+    const int tiles_used = (len + SORT_TILE - 1) / SORT_TILE;  // the histogram pass filled only these
     const int64_t base = (int64_t)mult * step * B;
     const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
 
@@ -100,7 +103,7 @@ sort_scatter_kernel(SortSrc src, uint32_t* __restrict__ dst_key, uint32_t* __res
     {
         const uint32_t* h = hist + ((size_t)step * 256 + d) * tiles;
         uint32_t total = 0, before = 0;
-        for (int t = 0; t < tiles; ++t) {
+        for (int t = 0; t < tiles_used; ++t) {
             uint32_t c = h[t];
             total += c;
             if (t < tile) before += c;

@@ -129,6 +129,7 @@ class ShardedLinearTrainer:
         self._plans: Dict[int, torch.Tensor] = {}
         self._plan_tmp = None
         self._ws = None
+        self._inv_counts = None
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.launches = 0
 
@@ -219,14 +220,17 @@ class ShardedLinearTrainer:
         self.sync_epoch += 2 * n_steps
         self.launches += 1 + len(self.local_ranks) * self.plan_launches()
         b.step0 += n_steps
-        total = sums.sum(0)
+        total = sums[0] if len(self.local_ranks) == 1 else sums.sum(0)
         if len(self.local_ranks) < self.world:
             dist.all_reduce(total, group=self.group)
-        counts = torch.full((n_steps,), float(B), device=self.device)
-        counts[-1] = float(n - (n_steps - 1) * B)
+        key = (n, B)
+        if self._inv_counts is None or self._inv_counts[0] != key:  # 1 / samples per step, cached per epoch shape
+            c = torch.full((n_steps,), 1.0 / B, dtype=torch.float64)
+            c[-1] = 1.0 / (n - (n_steps - 1) * B)
+            self._inv_counts = (key, c.to(torch.float32).to(self.device))
         if check:
             self.check_status()
-        return total / counts
+        return total * self._inv_counts[1]
 
     def plan_launches(self) -> int:
         """CUDA kernels one trs_shard_plan_build launches for one rank (bench.py's gpu_launches)."""
