@@ -276,6 +276,34 @@ int trs_linear_rows_step(int dim, int64_t batch, float inv_batch, const float* u
 int trs_topk_merge(const float* score, const int64_t* idx, int n_lists, int k, int64_t n_query,
                    int64_t* out_idx, float* out_score, trs_stream_t stream);
 
+/* ---- a7 for callers that drive autograd themselves: TorchRecSys.forward -> hinge_loss -> backward (model.py:171-200) */
+/* Backward of trs_scores (Linear / FM): grad_out[b] = d loss / d score[b]; writes ONE gradient row per lookup --
+ * g_user / g_item [n, dim], g_meta[f] [n, dim], and (nullable) the width-1 companions' gradients g_lin_* [n] -- exactly
+ * the (index, value) pairs the reference's nn.Embedding(sparse=True) backward emits (uncoalesced; torch's optimizers
+ * coalesce).  The host wraps them as sparse COO tensors so that ANY torch optimizer can step on them. */
+int trs_scores_backward(const trs_model* model, const int64_t* user, const int64_t* item, const int64_t* meta, int64_t n,
+                        const float* grad_out, float* g_user, float* g_item, float* const* g_meta_host,
+                        float* g_lin_user, float* g_lin_item, float* const* g_lin_meta_host, trs_stream_t stream);
+
+/* ---- a10 (north_star): sort-based ROC-AUC on the device --------------------------------------------------- */
+/* auc_out[0] (device double) = P(score+ > score-) + 0.5 P(score+ == score-) over all n_pos x n_neg pairs, computed as
+ * the Mann-Whitney U statistic: radix sort of the n_pos + n_neg scores, tie-averaged ranks, exact integer rank sum
+ * (equals sklearn.metrics.roc_auc_score, which the reference's legacy helper/evaluate.py:8-18 calls).  NaN for an
+ * empty class.  n_pos + n_neg <= 2^23 per call.  workspace: trs_sort_workspace_bytes(n_pos + n_neg). */
+size_t trs_sort_workspace_bytes(int64_t n);
+int trs_sorted_auc(const float* pos, int64_t n_pos, const float* neg, int64_t n_neg, double* auc_out, void* workspace,
+                   size_t workspace_bytes, trs_stream_t stream);
+
+/* ---- a9: the loader's per-epoch shuffle (dataset/dataset.py:359-373, 420-427) ------------------------------ */
+/* perm = a pseudo-random permutation of [0, n): Philox4x32-10 keys (key = seed, counter = position), stable radix
+ * sort.  n <= 2^23 per call; workspace: trs_sort_workspace_bytes(n). */
+int trs_epoch_shuffle(uint64_t seed, int64_t n, int64_t* perm, void* workspace, size_t workspace_bytes,
+                      trs_stream_t stream);
+/* dst[c][k, :] = src[c][perm[k], :] for up to 8 int64 id columns of `width[c]` ids per sample at once (what
+ * FastDataLoader.__next__ does per key and batch with tensor[current_indices]). */
+int trs_gather_rows_i64(const int64_t* const* src_host, int64_t* const* dst_host, const int32_t* width_host, int n_cols,
+                        const int64_t* perm, int64_t n, trs_stream_t stream);
+
 /* ---- e1: row-sharded training over PEER-MAPPED table shards (BASELINE configs[3]) ------------ */
 /* The reference is single-device (model.py:74); this is the multi-GPU form of model.py:274-284 for
  * net_type='linear'.  Row r of the user / item table lives on rank r % world at local row r / world.  Every rank

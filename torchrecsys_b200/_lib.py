@@ -27,7 +27,8 @@ SYMBOLS = [
     "trs_predict_topk", "trs_sparse_update_workspace_bytes", "trs_sparse_row_update", "trs_linear_rows_step",
     "trs_topk_merge", "trs_shard_stage_bytes", "trs_shard_plan_bytes", "trs_shard_plan_tmp_bytes",
     "trs_shard_plan_build", "trs_shard_workspace_bytes", "trs_shard_train_steps", "trs_ipc_export",
-    "trs_ipc_open", "trs_ipc_close",
+    "trs_ipc_open", "trs_ipc_close", "trs_scores_backward", "trs_sort_workspace_bytes", "trs_sorted_auc",
+    "trs_epoch_shuffle", "trs_gather_rows_i64",
 ]
 
 
@@ -74,7 +75,8 @@ def lib() -> C.CDLL:
         L = C.CDLL(LIB_PATH)
         L.trs_last_error.restype = C.c_char_p
         for name in ("trs_plan_bytes", "trs_plan_tmp_bytes", "trs_train_workspace_bytes", "trs_shard_stage_bytes",
-                     "trs_shard_plan_bytes", "trs_shard_plan_tmp_bytes", "trs_shard_workspace_bytes"):
+                     "trs_shard_plan_bytes", "trs_shard_plan_tmp_bytes", "trs_shard_workspace_bytes",
+                     "trs_sort_workspace_bytes"):
             getattr(L, name).restype = C.c_size_t
         if L.trs_abi_version() != 1:
             raise RuntimeError("libtrs_b200.so ABI version mismatch")
@@ -432,3 +434,69 @@ def ipc_open(handle: bytes) -> int:
 
 def ipc_close(base: int) -> None:
     _check(lib().trs_ipc_close(C.c_void_p(base)))
+
+
+# ---- autograd-visible forward, sorted AUC, epoch shuffle (csrc/extra.cu) ---------------------------------
+def scores_backward(model: Model, user, item, meta, grad_out, with_lin_user: bool, with_lin_item: bool,
+                    meta_lin: Sequence[bool]):
+    """Per-lookup gradient rows of ``scores``: (g_user [n, D], g_item [n, D], [g_meta_f], g_lin_user, g_lin_item,
+    [g_lin_meta_f]); absent companions are None."""
+    n, dim, F = user.shape[0], model.dim, model.n_meta
+    dev = user.device
+    f32 = torch.float32
+    row = lambda: torch.empty((n, dim), dtype=f32, device=dev)
+    vec = lambda: torch.empty(n, dtype=f32, device=dev)
+    g_user, g_item = row(), row()
+    g_meta = [row() for _ in range(F)]
+    g_lu = vec() if with_lin_user else None
+    g_li = vec() if with_lin_item else None
+    g_lm = [vec() if (f < len(meta_lin) and meta_lin[f]) else None for f in range(F)]
+    pm = (C.c_void_p * max(F, 1))(*[t.data_ptr() for t in g_meta])
+    plm = (C.c_void_p * max(F, 1))(*[None if t is None else t.data_ptr() for t in g_lm])
+    _check(lib().trs_scores_backward(C.byref(model), C.c_void_p(_ptr(user, torch.int64)),
+                                     C.c_void_p(_ptr(item, torch.int64)), C.c_void_p(_ptr(meta, torch.int64)),
+                                     C.c_int64(n), C.c_void_p(_ptr(grad_out, f32)), C.c_void_p(g_user.data_ptr()),
+                                     C.c_void_p(g_item.data_ptr()), pm, C.c_void_p(_ptr(g_lu)), C.c_void_p(_ptr(g_li)),
+                                     plm, _stream()))
+    return g_user, g_item, g_meta, g_lu, g_li, g_lm
+
+
+def _sort_ws(n: int, device) -> torch.Tensor:
+    return torch.empty(lib().trs_sort_workspace_bytes(C.c_int64(n)), dtype=torch.uint8, device=device)
+
+
+def sorted_auc(pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
+    """ROC-AUC of positive vs negative scores (fp32 CUDA tensors) -> device float64 scalar tensor [1]."""
+    pos, neg = pos.reshape(-1).contiguous(), neg.reshape(-1).contiguous()
+    dev = pos.device
+    out = torch.empty(1, dtype=torch.float64, device=dev)
+    n = pos.numel() + neg.numel()
+    ws = _sort_ws(n, dev)
+    _check(lib().trs_sorted_auc(C.c_void_p(_ptr(pos, torch.float32) if pos.numel() else None), C.c_int64(pos.numel()),
+                                C.c_void_p(_ptr(neg, torch.float32) if neg.numel() else None), C.c_int64(neg.numel()),
+                                C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()), _stream()))
+    return out
+
+
+def epoch_shuffle(seed: int, n: int, device) -> torch.Tensor:
+    """A Philox-keyed permutation of [0, n) as an int64 device tensor."""
+    perm = torch.empty(n, dtype=torch.int64, device=device)
+    if n:
+        ws = _sort_ws(n, device)
+        _check(lib().trs_epoch_shuffle(C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), C.c_int64(n), C.c_void_p(perm.data_ptr()),
+                                       C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()), _stream()))
+    return perm
+
+
+def gather_rows(columns: Sequence[torch.Tensor], perm: torch.Tensor):
+    """[col[perm] for col in columns] for int64 id columns ([n] or [n, w]) in ONE launch."""
+    n = perm.shape[0]
+    outs = [torch.empty((n,) + tuple(c.shape[1:]), dtype=torch.int64, device=perm.device) for c in columns]
+    k = len(columns)
+    if n == 0 or k == 0:
+        return outs
+    src = (C.c_void_p * k)(*[_ptr(c, torch.int64) for c in columns])
+    dst = (C.c_void_p * k)(*[o.data_ptr() for o in outs])
+    width = (C.c_int32 * k)(*[int(c.numel() // max(c.shape[0], 1)) for c in columns])
+    _check(lib().trs_gather_rows_i64(src, dst, width, k, C.c_void_p(_ptr(perm, torch.int64)), C.c_int64(n), _stream()))
+    return outs

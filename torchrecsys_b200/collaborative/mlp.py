@@ -12,7 +12,7 @@ import torch
 
 from .. import _lib
 from ..embeddings.init_embeddings import ScaledEmbedding
-from ._base import canonical_meta
+from ._base import canonical_meta, check_ids
 
 
 class MLP(torch.nn.Module):
@@ -105,9 +105,27 @@ class MLP(torch.nn.Module):
         meta = canonical_meta(batch.get(metadata_key) if metadata_key else None, self.n_meta_features)
         if self.n_meta_features and meta is None:
             raise KeyError(f"model uses metadata but batch has no '{metadata_key}'")
+        user, item = user.long().contiguous(), item.long().contiguous()
+        if not getattr(self, "_trusted_ids", False):
+            check_ids(user, self.n_users, "user")
+            check_ids(item, self.n_items, "item")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # A graph is being recorded (TorchRecSys.forward -> hinge_loss -> backward, model.py:171-200): the tower
+            # is 4 library GEMMs + BatchNorm, and autograd needs their saved activations -- run the reference's own
+            # op sequence (mlp.py:93-113) on the device.  fit() / evaluate() / predict() never come here: they use
+            # the fused tcgen05 path below and in trs_mlp_train_steps.
+            cols = [self.user(user), self.item(item)]
+            for f in range(self.n_meta_features):
+                cols.append(self.metadata_embeddings[f](meta[:, f]))
+            h = torch.cat(cols, dim=1)
+            for l, fc in enumerate(self.fcs):
+                h = fc(h)
+                if self.use_batch_norm:
+                    h = self.bns[l](h)
+                h = torch.relu(h)
+            return self.output_layer(h)
         stats = self.training and self.use_batch_norm
-        out = _lib.mlp_forward(self.abi_model(), self.abi_mlp(), user.long().contiguous(),
-                               item.long().contiguous(), meta, batch_stats=stats)
+        out = _lib.mlp_forward(self.abi_model(), self.abi_mlp(), user, item, meta, batch_stats=stats)
         if stats:
             for bn in self.bns:
                 bn.num_batches_tracked += 1

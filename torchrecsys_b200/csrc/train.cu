@@ -1051,10 +1051,14 @@ template <int V, int G, int IT>
 static void launch_train(const trs_model* m, const trs_epoch* ep, const OptScalars* opt,
                          const PlanPtrs* plan, const Stage* st, int first_step, int n_steps,
                          float* loss, int grid, cudaStream_t stream, cudaError_t* err) {
-    // TRS_DEBUG_SKIP (timing experiments only, results are wrong): 1 phase A, 2 long segments, 4 ring,
-    // 8 grid barriers, 16 L2 prefetches, 32 width-1 companions, 64 phase trace, 128 no phase-A updates
+    // Timing experiments only (results are wrong), compiled in with -DTRS_DEBUG and then read from the environment:
+    // TRS_DEBUG_SKIP bits 1 phase A, 2 long segments, 4 ring, 8 grid barriers, 16 L2 prefetches, 32 width-1
+    // companions, 64 phase trace, 128 no phase-A updates.  A production build ignores the variable.
+    int dbg = 0;
+#ifdef TRS_DEBUG
     const char* dbg_env = getenv("TRS_DEBUG_SKIP");
-    int dbg = dbg_env ? atoi(dbg_env) : 0;
+    dbg = dbg_env ? atoi(dbg_env) : 0;
+#endif
     void* args[] = {(void*)m, (void*)ep, (void*)opt, (void*)plan, (void*)st,
                     (void*)&first_step, (void*)&n_steps, (void*)&loss, (void*)&dbg};
     const void* fn = m->net == TRS_NET_LINEAR ? (const void*)train_kernel<TRS_NET_LINEAR, V, G, IT>

@@ -41,12 +41,30 @@ def _get_step(state: dict) -> int:
     return int(s.item()) if torch.is_tensor(s) else int(s)
 
 
+_ADAM_WARNED = False
+
+
+def _warn_adam_once() -> None:
+    """torch.optim.Adam cannot run on these models at all (sparse gradients); it is accepted and bound to
+    the row-wise kernel, whose semantics are SparseAdam's, not dense Adam's -- say so once."""
+    global _ADAM_WARNED
+    if not _ADAM_WARNED:
+        _ADAM_WARNED = True
+        import warnings
+        warnings.warn("torch.optim.Adam is applied ROW-WISE with torch.optim.SparseAdam semantics: only rows looked up "
+                      "in a step are updated (no moment decay of untouched rows), denominator sqrt(v) + eps with the "
+                      "bias corrections folded into the step size.  Dense Adam itself raises on sparse gradients.",
+                      stacklevel=3)
+
+
 def bind_optimizer(optimizer: torch.optim.Optimizer, params: List[torch.nn.Parameter]) -> OptBinding:
     """Recognise the optimizer and make sure ``optimizer.state[p]`` holds torch-compatible state
     tensors for every sparse table (created lazily exactly as torch's own ``step()`` would)."""
     groups = optimizer.param_groups
     name = type(optimizer).__name__
     if name in ("SparseAdam", "Adam"):
+        if name == "Adam":
+            _warn_adam_once()
         hp = _same_hparams(groups, ("lr", "betas", "eps", "maximize", "weight_decay", "amsgrad"))
         if hp.get("weight_decay") or hp.get("amsgrad") or hp.get("maximize"):
             raise NotImplementedError(f"{name}: weight_decay / amsgrad / maximize are not supported on sparse tables")
@@ -208,10 +226,14 @@ class MlpEpochRunner(_Chunked):
             raise NotImplementedError(
                 "net_type='mlp' has dense parameters: use Adagrad or SGD (torch's SparseAdam rejects dense "
                 "gradients and Adam rejects the sparse ones, SURVEY.md D2)")
+        # gradient buffers of the dense tower parameters: workspace of the fused step, NOT installed as p.grad
+        # (the user's module is left as it is; `dense_grads()` hands them out on request)
         self.grads = {p: torch.zeros_like(p) for p in net.dense_parameters()}
-        for p, g in self.grads.items():
-            p.grad = g  # the last step's dense gradient stays visible to user code
         self.launches = 0
+
+    def dense_grads(self) -> Dict[torch.nn.Parameter, torch.Tensor]:
+        """The dense gradients of the LAST step run (read-only view of the step's workspace)."""
+        return self.grads
 
     def _run(self, samples: Dict[str, torch.Tensor], batch_size: int) -> torch.Tensor:
         b = self.binding
@@ -241,3 +263,54 @@ class MlpEpochRunner(_Chunked):
             for m in self.net.bns:
                 m.num_batches_tracked += 2 * n_steps  # two forward passes per step (model.py:173-183)
         return loss
+
+
+class AutogradEpochRunner(_Chunked):
+    """ANY torch optimizer (SGD with momentum, a user-defined one, ...): the reference's own loop body
+    (model.py:274-284) -- ``forward x2 -> hinge_loss -> zero_grad -> backward -> optimizer.step()`` -- with the scorer
+    kernels under autograd (collaborative/_base.py: _ScoreFn; the MLP tower's torch ops) and the sparse gradients
+    coalesced before the step, as SURVEY.md §8(b) prescribes for optimizers the fused row-wise update does not know.
+    One Python iteration per step; the loss stays on the device (no per-step ``.item()``)."""
+
+    def __init__(self, net, optimizer):
+        self.net = net
+        self.optimizer = optimizer
+        self.params = [p for p in net.parameters()]
+        self.launches = 0
+
+    def _run(self, samples: Dict[str, torch.Tensor], batch_size: int) -> torch.Tensor:
+        from .helper.loss import hinge_loss
+        n = samples["user"].shape[0]
+        names = {"user": "user_id", "pos": "pos_item_id", "neg": "neg_item_id", "pos_meta": "pos_metadata_id",
+                 "neg_meta": "neg_metadata_id"}
+        losses = []
+        self.net._trusted_ids = True
+        try:
+            for lo in range(0, n, batch_size):
+                batch = {names[k]: v[lo:lo + batch_size] for k, v in samples.items() if k in names}
+                has_meta = "pos_metadata_id" in batch
+                pos = self.net.forward(batch, "user_id", "pos_item_id", "pos_metadata_id" if has_meta else None)
+                neg = self.net.forward(batch, "user_id", "neg_item_id", "neg_metadata_id" if has_meta else None)
+                loss = hinge_loss(pos, neg)
+                self.optimizer.zero_grad()
+                loss.backward()
+                for p in self.params:
+                    if p.grad is not None and p.grad.is_sparse:
+                        p.grad = p.grad.coalesce()
+                self.optimizer.step()
+                losses.append(loss.detach())
+        finally:
+            self.net._trusted_ids = False
+        return torch.stack(losses) if losses else torch.empty(0, device=samples["user"].device)
+
+
+def make_runner(net, optimizer, is_mlp: bool):
+    """The fused runner when the optimizer has a row-wise kernel, otherwise the autograd loop (with a warning)."""
+    try:
+        return (MlpEpochRunner if is_mlp else EpochRunner)(net, optimizer)
+    except NotImplementedError as e:
+        import warnings
+        warnings.warn(f"{e} -- falling back to the per-step autograd loop (forward kernels + torch autograd + "
+                      f"{type(optimizer).__name__}.step() on coalesced sparse gradients): correct, but far slower than "
+                      "the fused path.", stacklevel=3)
+        return AutogradEpochRunner(net, optimizer)

@@ -1,16 +1,26 @@
 """Evaluation metrics with the reference's interface (evaluate/metrics.py:6-31)."""
-import numpy as np
 import torch
 
 
 class Metrics:
     def hit_rate(self, y_hat, y_pred):
         """Share of rows of ``y_pred`` (recommended ids, [n, k]) containing at least one id of the
-        matching row of ``y_hat`` (held-out ids, [n, m], padded with values that never occur)."""
-        truth = np.asarray(y_hat.cpu() if torch.is_tensor(y_hat) else y_hat)
-        recs = np.asarray(y_pred.cpu() if torch.is_tensor(y_pred) else y_pred)
-        hit = (recs[:, :, None] == truth[:, None, :]).any(axis=(1, 2))
-        return hit.sum() / recs.shape[0]
+        matching row of ``y_hat`` (held-out ids, [n, m], padded with values that never occur) --
+        evaluate/metrics.py:6-20, with tensor ops on whatever device the inputs live on (no numpy round trip:
+        ``predict_batch`` output can stay on the GPU)."""
+        truth = torch.as_tensor(y_hat)
+        recs = torch.as_tensor(y_pred).to(truth.device)
+        if recs.shape[0] == 0:
+            return float("nan")
+        hit = (recs[:, :, None] == truth[:, None, :]).flatten(1).any(dim=1)
+        return float(hit.sum().item()) / recs.shape[0]
+
+    def roc_auc(self, positive, negative):
+        """Sort-based ROC-AUC of positive vs negative scores on the device (csrc/extra.cu: trs_sorted_auc): the
+        probability that a random positive outranks a random negative, ties counted half -- what
+        ``sklearn.metrics.roc_auc_score`` returns (the reference's legacy helper/evaluate.py:8-18 calls it)."""
+        from .. import _lib
+        return float(_lib.sorted_auc(positive.float(), negative.float()).item())
 
     def auc_score(self, positive, negative):
         """Pairwise accuracy ``#(pos > neg) / len(pos)`` (strict), what the reference calls AUC."""

@@ -26,7 +26,7 @@ from .collaborative.fm import FM
 from .collaborative.linear import Linear
 from .collaborative.mlp import MLP
 from .dataset.dataset import FastDataLoader, ProcessData
-from .engine import EpochRunner, MlpEpochRunner
+from .engine import make_runner
 from .evaluate.metrics import Metrics
 from .helper.cuda import gpu
 from .helper.loss import hinge_loss
@@ -156,22 +156,23 @@ class TorchRecSys(torch.nn.Module):
         dev = self._require_cuda()
         base = self._device_split("train_data")
         n = base["user"].shape[0] if base else 0
-        runner = (MlpEpochRunner if self.net_type == "mlp" else EpochRunner)(self.net, optimizer)
+        # the fused row-wise update for SGD / Adagrad / SparseAdam (/ Adam); the per-step autograd loop for anything
+        # else (engine.make_runner)
+        runner = make_runner(self.net, optimizer, self.net_type == "mlp")
         self._last_runner = runner
-        # the reference loader shuffles once when constructed and again at every __iter__
-        # (dataset.py:359-373); consuming the CPU generator the same way keeps seeded runs comparable
-        if n:
-            torch.randperm(n)
-            if hasattr(runner, "reserve"):
-                runner.reserve(n, batch_size)  # plan / workspace blocks of an epoch of this shape, once
+        if n and hasattr(runner, "reserve"):
+            runner.reserve(n, batch_size)  # plan / workspace blocks of an epoch of this shape, once
+        keys = list(base.keys()) if base else []
         for epoch in range(epochs):
             self.net = self.net.train()
 
             def one_epoch():
                 if n == 0:
                     return 0.0
-                perm = torch.randperm(n).to(dev, non_blocking=True)
-                samples = {k: v[perm] for k, v in base.items()}
+                # the loader's shuffle (dataset.py:369-373) and batch slicing (:420-427) on the device: a Philox-keyed
+                # permutation and ONE gather launch for all id columns -- no host randperm, no H2D copy
+                perm = self._epoch_permutation(n, dev)
+                samples = dict(zip(keys, _lib.gather_rows([base[k] for k in keys], perm)))
                 samples = self._with_negatives(samples, self._epochs_seen * n)
                 losses = runner.run(samples, batch_size)
                 self._epochs_seen += 1
@@ -188,6 +189,16 @@ class TorchRecSys(torch.nn.Module):
             else:
                 avg_loss = one_epoch()
             print(f"|--- Epoch {epoch + 1}/{epochs} --- Training Loss: {avg_loss:.4f}")
+
+    def _epoch_permutation(self, n: int, dev, epoch_index: Optional[int] = None) -> torch.Tensor:
+        """The shuffle of the ``epoch_index``-th epoch this model trains (default: the next one): a pure function of
+        (seed, epoch index, n), so a run can be replayed."""
+        e = self._epochs_seen if epoch_index is None else epoch_index
+        seed = (self.seed * 0x9E3779B97F4A7C15 + e + 1) & 0xFFFFFFFFFFFFFFFF
+        if n <= (1 << 23):
+            return _lib.epoch_shuffle(seed, n, dev)
+        g = torch.Generator(device=dev).manual_seed(seed & 0x7FFFFFFFFFFFFFFF)   # beyond one sort call: torch's device sort
+        return torch.randperm(n, device=dev, generator=g)
 
     # ------------------------------------------------------------------------------------
     def evaluate(self, batch_size=512, eval_metrics=["loss", "auc"]):
@@ -212,15 +223,27 @@ class TorchRecSys(torch.nn.Module):
         else:
             epoch = _lib.make_epoch(test["user"], test["pos"], test["neg"], test.get("pos_meta"),
                                     test.get("neg_meta"), batch_size)
-            loss, auc, _, _ = _lib.eval_pairwise(self.net.abi_model(), epoch)
+            loss, auc, pos, neg = _lib.eval_pairwise(self.net.abi_model(), epoch, want_scores="roc_auc" in eval_metrics)
         results = {"loss": loss, "auc": auc}
         for metric in eval_metrics:
             if metric in results:
                 value = float(results[metric].mean().item())  # unweighted mean over batches
+            elif metric == "roc_auc":
+                # sort-based ROC-AUC over the WHOLE split (not per batch): every positive score against every
+                # negative score, ties counted half (csrc/extra.cu: trs_sorted_auc)
+                value = self._roc_auc(pos, neg)
             else:
                 value = 0
             self.last_eval[metric] = value
             print(f"|--- Testing {metric}: {value:.4f}")
+
+    @staticmethod
+    def _roc_auc(pos: torch.Tensor, neg: torch.Tensor) -> float:
+        limit = 1 << 22  # trs_sorted_auc sorts at most 2^23 scores per call: beyond that, an evenly strided sample
+        if pos.numel() > limit:
+            stride = -(-pos.numel() // limit)
+            pos, neg = pos.reshape(-1)[::stride].contiguous(), neg.reshape(-1)[::stride].contiguous()
+        return float(_lib.sorted_auc(pos.reshape(-1).float(), neg.reshape(-1).float()).item())
 
     # ------------------------------------------------------------------------------------
     def predict(self, user_id: int, top_k: int = 10, prediction_batch_size: int = 4096):
@@ -229,9 +252,18 @@ class TorchRecSys(torch.nn.Module):
         ``prediction_batch_size`` is accepted for compatibility; all items are scored in one pass."""
         dev = self._require_cuda()
         self.net = self.net.eval()
-        if self.net_type != "mlp" and 1 <= top_k <= 128:
+        if not 0 <= int(user_id) < self.n_users:  # the reference: IndexError out of aten::embedding
+            raise IndexError(f"user_id {user_id} is outside [0, {self.n_users})")
+        if self._topk_kernel_ok(top_k):
             return self.predict_batch(torch.tensor([int(user_id)]), top_k)[0]
         return self._predict_exact(int(user_id), top_k, dev)
+
+    # the tensor-core top-k kernel packs [row, bias] into <= 240 bf16 columns (csrc/topk.cu: check_topk) and keeps
+    # at most 128 results per user; everything else takes the exact fp32 path
+    TOPK_MAX_FACTORS = 239
+
+    def _topk_kernel_ok(self, top_k: int) -> bool:
+        return self.net_type != "mlp" and 1 <= top_k <= 128 and self.n_factors <= self.TOPK_MAX_FACTORS
 
     def _predict_exact(self, user_id: int, top_k: int, dev) -> torch.Tensor:
         """Score every item in fp32 and sort (stable, descending): the MLP tower, top_k > 128, and users
@@ -246,16 +278,23 @@ class TorchRecSys(torch.nn.Module):
         order = torch.sort(scores, descending=True, stable=True)[1]
         return order[:top_k].cpu()
 
-    def predict_batch(self, user_ids, top_k: int = 10) -> torch.Tensor:
+    def predict_batch(self, user_ids, top_k: int = 10, exclude_seen: bool = False) -> torch.Tensor:
         """Top-k item ids for MANY users at once -> CPU int64 ``[n_users, top_k]`` (new entry point; the
         reference API is one user per call, model.py:341).  Linear / FM: user tiles x all items on the
         tensor cores with the top-k fused into the epilogue, exact fp32 re-scoring of the candidates
-        (csrc/topk.cu); same indices and tie-break as ``predict``."""
+        (csrc/topk.cu); same indices and tie-break as ``predict``.  ``exclude_seen=True`` leaves out the items a
+        user interacted with in the training split (rows with fewer than top_k unseen items are padded with -1)."""
         dev = self._require_cuda()
         self.net = self.net.eval()
-        users = torch.as_tensor(user_ids, dtype=torch.int64).to(dev).contiguous()
-        if self.net_type == "mlp" or not (1 <= top_k <= 128):
-            return torch.stack([self._predict_exact(int(u), top_k, dev) for u in users.tolist()])
+        users = torch.as_tensor(user_ids, dtype=torch.int64).reshape(-1)
+        if users.numel() and (int(users.min()) < 0 or int(users.max()) >= self.n_users):
+            raise IndexError(f"user ids must lie in [0, {self.n_users})")
+        users = users.to(dev).contiguous()
+        if exclude_seen:
+            return self._predict_unseen(users, top_k, dev)
+        if not self._topk_kernel_ok(top_k):
+            return torch.stack([self._predict_exact(int(u), top_k, dev) for u in users.tolist()]) if users.numel() \
+                else torch.empty((0, min(top_k, self.n_items)), dtype=torch.int64)
         if self.use_metadata and "item_meta" not in self._dev_cache:
             self._device_split("train_data")
         meta = self._dev_cache.get("item_meta") if self.use_metadata else None
@@ -266,3 +305,29 @@ class TorchRecSys(torch.nn.Module):
         if top_k > self.n_items:
             idx = idx[:, :self.n_items]
         return idx
+
+    def _seen_pairs(self, dev):
+        """Sorted unique (user * n_items + item) codes of the training split, on the device (cached)."""
+        if "seen" not in self._dev_cache:
+            tr = self._device_split("train_data")
+            self._dev_cache["seen"] = torch.unique(tr["user"] * self.n_items + tr["pos"]) if tr else \
+                torch.empty(0, dtype=torch.int64, device=dev)
+        return self._dev_cache["seen"]
+
+    def _predict_unseen(self, users: torch.Tensor, top_k: int, dev) -> torch.Tensor:
+        """Ask the ranking kernel for top_k + (most items any requested user has seen) candidates, drop the seen ones,
+        keep the first top_k -- the order among unseen items is the order of the unfiltered ranking."""
+        seen = self._seen_pairs(dev)
+        lo = torch.searchsorted(seen, users * self.n_items)
+        hi = torch.searchsorted(seen, (users + 1) * self.n_items)
+        most = int((hi - lo).max().item()) if users.numel() else 0
+        want = min(top_k + most, self.n_items)
+        if self._topk_kernel_ok(want):
+            cand = self.predict_batch(users.cpu(), want).to(dev)
+        else:
+            cand = torch.stack([self._predict_exact(int(u), want, dev) for u in users.tolist()]).to(dev) if users.numel() \
+                else torch.empty((0, want), dtype=torch.int64, device=dev)
+        is_seen = torch.isin(users[:, None] * self.n_items + cand, seen) | (cand < 0)
+        order = torch.sort(is_seen.to(torch.int8), dim=1, stable=True)[1]          # unseen first, ranking order kept
+        out = torch.gather(torch.where(is_seen, torch.full_like(cand, -1), cand), 1, order)[:, :top_k]
+        return out.cpu()
