@@ -88,7 +88,6 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the other_workloads sub-results")
     ap.add_argument("--shard-it", type=int, default=0, help="tuning: 16-byte chunks per lane of the sharded kernel (1 or 2)")
-    ap.add_argument("--shard-split", type=int, default=-1, help="tuning: 1 = user rows behind a rank-local barrier (see csrc/shard.cu)")
     ap.add_argument("--emulate-world", type=int, default=0,
                     help="c4_linear on ONE GPU: host a group of this many ranks in one launch (structure check, no NVLink)")
     return ap.parse_args()
@@ -672,8 +671,6 @@ def sharded_bench(args, wl, name):
         dist.init_process_group("nccl", device_id=dev)
     if args.shard_it:
         _lib.lib().trs_debug_shard_chunks_per_lane(args.shard_it)
-    if args.shard_split >= 0:
-        _lib.lib().trs_debug_shard_split_b(args.shard_split)
     G = emu or world                       # ranks of the group
     K, W, B = args.steps, max(args.warmup, 3), wl["batch"]
     Bg = B * G

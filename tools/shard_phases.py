@@ -24,7 +24,6 @@ ap.add_argument("--dim", type=int, default=128)
 ap.add_argument("--batch", type=int, default=16384)
 ap.add_argument("--steps", type=int, default=12)
 ap.add_argument("--it", type=int, default=1)
-ap.add_argument("--split", type=int, default=0)
 a = ap.parse_args()
 real = "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1
 local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -36,7 +35,6 @@ if real:
     rank, a.world = dist.get_rank(), dist.get_world_size()
 L = _lib.lib()
 L.trs_debug_shard_chunks_per_lane(a.it)
-L.trs_debug_shard_split_b(a.split)
 G, B = a.world, a.batch * a.world
 tr = ShardedLinearTrainer(a.users, a.items, a.dim, global_batch=B, device=dev, emulate_world=None if real else G)
 rng = np.random.default_rng(0)
@@ -71,7 +69,7 @@ for r in range(n_local):
     d = t[r, 2:, :, :]
     step = np.mean(d[1:, :, 0].min(axis=1) - d[:-1, :, 0].min(axis=1))
     who = rank if real else r
-    if G > 1 and a.split:   # A | rank barrier | B(user rows) | cross-rank barrier | B(item rows) | cross-rank barrier
+    if False:   # (the split of phase B was removed) | B(user rows) | cross-rank barrier | B(item rows) | cross-rank barrier
         print(f"rank {who} mean over steps (avg CTA): A {np.mean(d[:, :, 1] - d[:, :, 0]):.1f}  "
               f"rank-bar {np.mean(d[:, :, 5] - d[:, :, 1]):.1f}  B-user {np.mean(d[:, :, 6] - d[:, :, 5]):.1f}  "
               f"x-bar1 {np.mean(d[:, :, 2] - d[:, :, 6]):.1f}  B-item {np.mean(d[:, :, 3] - d[:, :, 2]):.1f}  "

@@ -66,7 +66,7 @@ class _ScoreFn(torch.autograd.Function):
         def coo(ids, values, weight):
             if values.dim() == 1:
                 values = values[:, None]
-            return torch.sparse_coo_tensor(ids[None], values, weight.shape)
+            return torch.sparse_coo_tensor(ids[None], values, weight.shape, check_invariants=False)
 
         grads = {id(u_emb): coo(user, g_user, u_emb), id(i_emb): coo(item, g_item, i_emb)}
         if u_lin is not None:

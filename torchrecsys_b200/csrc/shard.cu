@@ -220,6 +220,37 @@ dirty_mark_kernel(const int64_t* __restrict__ pos, const int64_t* __restrict__ n
         }
     }
 }
+// A user row looked up exactly ONCE in a step has no other reader or writer in that step (every sample of a user runs
+// on the user row's owner): its sample updates it in phase A.  Marks the sample (SAMP_USER_SINGLE) and the sorted
+// pair (VAL_DONE_IN_A: phase B skips it).  Runs after dirty_mark_kernel (which rewrites the samp entries).
+__global__ void __launch_bounds__(RT_THREADS)
+single_mark_kernel(const uint32_t* __restrict__ ukey, uint32_t* __restrict__ uval, const uint32_t* __restrict__ own_cnt,
+                   const uint32_t* __restrict__ samp_cnt, uint32_t* __restrict__ samp, int B) {
+    const int64_t step = blockIdx.y;
+    const int64_t s0 = step * (int64_t)B;
+    const int n = (int)own_cnt[2 * step], nS = (int)samp_cnt[step];
+    const uint32_t* K = ukey + s0;
+    uint32_t* P = uval + s0;
+    uint32_t* S = samp + s0;
+#pragma unroll
+    for (int r = 0; r < RT_ROWS; ++r) {
+        const int k = blockIdx.x * RT_TILE + r * RT_THREADS + threadIdx.x;
+        if (k >= n) continue;
+        const uint32_t key = K[k];
+        if ((k > 0 && K[k - 1] == key) || (k + 1 < n && K[k + 1] == key)) continue;
+        const uint32_t b = P[k];
+        int lo = 0, hi = nS;  // the rank's samples are its owned user lookups in slot order: find slot b
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((S[mid] & 0x07FFFFFFu) < b) lo = mid + 1; else hi = mid;
+        }
+        if (lo < nS && (S[lo] & 0x07FFFFFFu) == b) {
+            atomicOr(S + lo, 1u << 27);
+            P[k] = b | (1u << 31);
+        }
+    }
+}
+
 // bits of a step's bitmap: 16x the item lookups of a step (6 % false positives), or one bit per item if that is less
 static int dirty_log2_bits(const trs_epoch* ep, int64_t n_items, bool* exact) {
     int lb = 10;
@@ -233,13 +264,20 @@ static int dirty_log2_bits(const trs_epoch* ep, int64_t n_items, bool* exact) {
 // ------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------
+// samp entries of the plan: position of the sample in its step | flags
+constexpr uint32_t SAMP_POS = 0x07FFFFFFu;          // position b in the global step (global batch < 2^27)
+constexpr uint32_t SAMP_USER_SINGLE = 1u << 27;     // the user row is looked up once in the step: phase A updates it
+constexpr uint32_t SAMP_DIRTY_POS = 1u << 30;       // the positive / negative item row is updated by the previous step
+constexpr uint32_t SAMP_DIRTY_NEG = 1u << 31;
+constexpr uint32_t VAL_DONE_IN_A = 1u << 31;        // sorted (row, slot) pair whose row phase A updates itself
+
 // Thread-private 16-byte shared-memory slots per chunk a lane owns: phase A keeps SB samples x {user, positive,
 // negative} row in flight per row group, phase B PB owned rows x {gradient, parameter, state 0, state 1}.
 template <int IT>
 constexpr int shard_slots() { return 12; }
 
 struct ShardCtx {  // everything one (virtual) rank needs; copied to shared memory by each of its CTAs
-    int rank, world, dim, split_b;  // split_b (tuning): update the user rows behind a rank-local barrier first
+    int rank, world, dim, pad;
     trs_table user[TRS_MAX_RANKS];
     trs_table item[TRS_MAX_RANKS];
     float* stage_u[TRS_MAX_RANKS];  // [B, dim]   gradient rows of the user lookups, slot = sample position in the step
@@ -303,8 +341,7 @@ template <int IT>
 constexpr size_t shard_smem_bytes() { return (size_t)shard_threads<IT>() * shard_slots<IT>() * IT * 16; }
 
 // ---- barriers -------------------------------------------------------------------------------------------------
-// One mechanism for both kinds: a monotonic arrival counter per rank (word 64 of its sync words: cross-rank; word
-// 16: the rank's own CTAs, restarted with every launch).  A CTA arrives with ONE release fence (bar.sync before it:
+// A monotonic arrival counter per rank (word 64 of its sync words).  A CTA arrives with ONE release fence (bar.sync before it:
 // the stores of its whole CTA happen before the fence) followed by a relaxed add of 1 to the counter of every rank
 // it must meet, polls its OWN rank's counter with relaxed loads until all arrivals of this barrier are in, and ends
 // the wait with one acquire load (the counter is a chain of read-modify-writes: reading its final value
@@ -350,19 +387,6 @@ __device__ __forceinline__ void spin_until(const ShardCtx& C, const unsigned* cn
             }
         }
     }
-}
-
-// the CTAs of ONE rank (gpu scope)
-__device__ __forceinline__ void rank_barrier(const ShardCtx& C, unsigned target, unsigned long long timeout_ns) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned* cnt = C.sync[C.rank] + 16;
-        fence_acq_rel_gpu();
-        red_relaxed_gpu(cnt);
-        spin_until(C, cnt, target, false, timeout_ns);
-        (void)ld_acquire_gpu(cnt);
-    }
-    __syncthreads();
 }
 
 // every CTA of every rank; e = number of this barrier over the life of the group (1-based)
@@ -452,14 +476,21 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                    const int n_steps, const unsigned sync_epoch, const unsigned long long timeout_ns) {
     constexpr int NT = shard_threads<IT>();
     constexpr int GPB = NT / G, GPW = 32 / G;
-    constexpr int SB = shard_slots<IT>() / 3;  // samples in flight per row group (phase A)
-    constexpr int PB = shard_slots<IT>() / 4;  // owned rows in flight per row group (phase B)
-    constexpr int RPL = (SB + G - 1) / G;      // sample records a lane fetches per phase-A round
+    constexpr int PB = shard_slots<IT>() / 4;  // owned rows in flight per row group (phase B): 4 slots each
     constexpr int DPL = (PB + G - 1) / G;      // row descriptors a lane fetches per phase-B round
+    // Phase A rounds.  The item rows of a group's first PFS samples live in a per-group region of contiguous row
+    // slots (filled a step ahead by bulk copies, or at the start of phase A for rows the previous step updated);
+    // the 12 thread-private slots then hold the USER row with its optimizer state for SBA = 4 samples at a time:
+    // regular rounds [0, SBA) and [SBA, PFS).  Samples beyond PFS (and every sample when there is no region, IT > 1)
+    // go SBO = 2 per round with all five rows in the thread-private slots.
     constexpr int PFS = shard_pf_samples<G, IT>();
+    constexpr int SBA = 4, SBO = 2;
+    constexpr int NREG = PFS ? 2 : 0;          // regular rounds
+    constexpr int NPR = NREG ? NREG : 1;       // rounds whose records are fetched a step ahead
+    constexpr int RPL = (SBA + G - 1) / G;     // sample records a lane holds per round
+    constexpr int ROWB = G * IT * 16;          // bytes of a region row slot
     static_assert(shard_smem_total<G, IT>() + 2048 <= 227 * 1024, "shared memory budget");
-    constexpr int NPR = PFS ? (PFS + SB - 1) / SB : 1;  // phase-A rounds whose records are fetched a step ahead
-    constexpr int ROWB = G * IT * 16;          // bytes of a prefetched row's shared-memory slot
+    static_assert(!PFS || (PFS > SBA && PFS <= 2 * SBA), "round layout");
     __shared__ ShardCtx C;
     __shared__ float s_loss[NT / 32];
     extern __shared__ __align__(128) unsigned char sh_smem[];
@@ -497,7 +528,7 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
         }
         return x;
     };
-    auto pf_row = [&](int j) {  // prefetched row j (= 2 * sample ordinal + {0 positive, 1 negative}) of my group
+    auto region_row = [&](int j) {  // region row j = 2 * sample ordinal + {0 positive, 1 negative} of my group
         Row<4, IT> x;
 #pragma unroll
         for (int a = 0; a < IT; ++a) {
@@ -513,6 +544,13 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
             if (ch < nch) sh_cp_async16(slot(j, a), base + (size_t)ch * 4);
         }
     };
+    auto copy_region = [&](int j, const float* base) {
+#pragma unroll
+        for (int a = 0; a < IT; ++a) {
+            const int ch = gl + a * G;
+            if (ch < nch) sh_cp_async16(my_pf_rows + (size_t)j * ROWB + ch * 16, base + (size_t)ch * 4);
+        }
+    };
     auto ld_row = [&](const float* base) { return load_row_cg<4, G, IT>(base, nch, gl); };
     const trs_table& tU = C.user[me];
     const trs_table& tI = C.item[me];
@@ -521,17 +559,16 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
     float* const my_stage_i = C.stage_i[me];
     const float* const my_stage_b = C.stage_b[me];
     unsigned bar_no = 0;   // cross-rank barriers passed in this launch
-    unsigned lbar_no = 0;  // barriers of this rank alone
 
     // ---- records of a phase-A round: lane gl fetches samples gl, gl + G, ... of the round and splits their ids
     //      into (owner, local row) ONCE (plan + epoch data: immutable, so the NEXT step's first rounds are fetched
-    //      a whole step ahead).  b = position in the step | dirty flags << 30; q packs the three owners ----
+    //      a whole step ahead).  b = position in the step | flags (SAMP_*); q packs the three owners ----
     struct Rec { uint32_t b[RPL], q[RPL], lu[RPL], lp[RPL], ln[RPL]; };
     auto split = [&](uint32_t id, uint32_t& owner, uint32_t& local) {
         if (wpow2) { owner = id & (W - 1u); local = id >> wshift; }
         else { owner = id % W; local = id / W; }
     };
-    auto fetch_records = [&](Rec& R, int64_t lo_, int nS_, int kb) {
+    auto fetch_records = [&](Rec& R, int64_t lo_, int nS_, int kb, int cnt) {
         const uint32_t* samp = C.samp + lo_;
 #pragma unroll
         for (int z = 0; z < RPL; ++z) {
@@ -539,9 +576,9 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
             const int k = kb + i * gstride;
             R.b[z] = 0xFFFFFFFFu;
             R.q[z] = R.lu[z] = R.lp[z] = R.ln[z] = 0u;
-            if (i < SB && k < nS_) {
+            if (i < cnt && k < nS_) {
                 const uint32_t bf = __ldg(samp + k);
-                const uint32_t b = bf & 0x3FFFFFFFu;
+                const uint32_t b = bf & SAMP_POS;
                 R.b[z] = bf;
                 uint32_t qu, qp, qn;
                 split((uint32_t)__ldg(ep.user + lo_ + b), qu, R.lu[z]);
@@ -551,10 +588,12 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
             }
         }
     };
+    auto round_lo = [&](int r) { return r < NREG ? (r == 0 ? 0 : SBA) : PFS + SBO * (r - NREG); };
+    auto round_n = [&](int r) { return r < NREG ? (r == 0 ? SBA : PFS - SBA) : SBO; };
     // ---- descriptors of a phase-B round: the owned lookups of a step are one list of positions, user space
     //      [0, nU) then item space [nU, nU + nI); lane gl fetches positions gl, gl + G, ... of the round ----
-    // sf = slot | flags << 29; flag bits: 1 head (first position of a run of equal rows), 2 the run continues,
-    // 4 item space
+    // sf = slot | flags << 29; flag bits: 1 head (first position of a run of equal rows that phase A has not
+    // updated already), 2 the run continues, 4 item space
     struct Desc { uint32_t key[DPL], sf[DPL]; };
     auto fetch_descs = [&](Desc& Dd, int64_t lo_, int nU_, int nI_, int pb, int pend) {
 #pragma unroll
@@ -570,8 +609,10 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                 const uint32_t key = __ldg(K + k);
                 const uint32_t prev = k > 0 ? __ldg(K + k - 1) : ~key;
                 const uint32_t next = k + 1 < n ? __ldg(K + k + 1) : ~key;
+                const uint32_t v = __ldg(P + k);
                 Dd.key[z] = key;
-                Dd.sf[z] = __ldg(P + k) | ((prev != key ? 1u : 0u) | (next == key ? 2u : 0u) | (it ? 4u : 0u)) << 29;
+                Dd.sf[z] = (v & 0x1FFFFFFFu) |
+                           ((prev != key && !(v & VAL_DONE_IN_A) ? 1u : 0u) | (next == key ? 2u : 0u) | (it ? 4u : 0u)) << 29;
             }
         }
     };
@@ -582,9 +623,9 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
         const int64_t lo0 = (int64_t)first_step * ep.batch;
         nS_cur = (int)C.samp_cnt[first_step];
 #pragma unroll
-        for (int r = 0; r < NPR; ++r) fetch_records(recN[r], lo0, nS_cur, gfirst + r * gstride * SB);
+        for (int r = 0; r < NPR; ++r) fetch_records(recN[r], lo0, nS_cur, gfirst + round_lo(r) * gstride, round_n(r));
     }
-    bool pf_live = false;     // the current step's first rounds have prefetched item rows (all but the dirty ones)
+    bool pf_live = false;     // the current step's region holds prefetched item rows (all but the dirty ones)
     uint32_t pf_parity = 0;
 
     for (int si = 0; si < n_steps; ++si) {
@@ -607,8 +648,63 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
             }
             pf_parity ^= 1u;
         }
-        int rnd = 0;
-        for (int k0 = gfirst - goff; k0 < nS; k0 += gstride * SB, ++rnd) {  // warp-uniform trip count
+        // One sample: scores, hinge, gradient rows.  linear.py:78: s = <u, v> + b_u + b_i; loss.py:7-9:
+        // h = s- - s+ + 1, d/ds = [h >= 0] / B.  A user row that this step looks up ONCE (plan flag: no other sample of
+        // the global batch reads or writes it, and its owner is this rank) is updated right here from its state rows
+        // in slots su_slot + 1 / + 2; every other gradient row goes to its owner's staging buffer.
+        auto process = [&](bool valid, uint32_t bf, uint32_t q, uint32_t lu, const Row<4, IT>& xu, const Row<4, IT>& xp,
+                           const Row<4, IT>& xn, float bu, float bip, float bin, int su_slot) {
+            const float sp = (group_sum<G>(row_dot_partial(xu, xp)) + bu) + bip;
+            const float sn = (group_sum<G>(row_dot_partial(xu, xn)) + bu) + bin;
+            const float h = __fadd_rn(__fsub_rn(sn, sp), 1.0f);
+            const float g = (h >= 0.f) ? invB : 0.f;
+            if (!valid) return;
+            if (gl == 0) hsum += fmaxf(h, 0.f);
+            const uint32_t b = bf & SAMP_POS;
+            const uint32_t qu = q & 15u, qp = (q >> 4) & 15u, qn = (q >> 8) & 15u;
+            float* dp = C.stage_i[qp] + (size_t)b * dim;
+            float* dn = C.stage_i[qn] + (size_t)(Bs + b) * dim;
+            Row<4, IT> gu;
+#pragma unroll
+            for (int a = 0; a < IT; ++a) {
+                const int ch = gl + a * G;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) gu.c[a][e] = g * (xn.c[a][e] - xp.c[a][e]);
+                if (ch < nch) {
+                    Vec<4> gp, gn;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        gp[e] = -g * xu.c[a][e];
+                        gn[e] = g * xu.c[a][e];
+                    }
+                    gp.st(dp + (size_t)ch * 4);
+                    gn.st(dn + (size_t)ch * 4);
+                }
+            }
+            if (gl == 0) {
+                C.stage_b[qp][b] = -g;
+                C.stage_b[qn][Bs + b] = g;
+            }
+            if (bf & SAMP_USER_SINGLE) {
+                Row<4, IT> p = xu, s0, s1;
+#pragma unroll
+                for (int a = 0; a < IT; ++a) s0.c[a] = s1.c[a] = Vec<4>::zero();
+                if (KIND != TRS_OPT_SGD) s0 = slot_row(su_slot + 1);
+                if (KIND == TRS_OPT_SPARSE_ADAM) s1 = slot_row(su_slot + 2);
+                sh_update_store<KIND, IT>(C.user[qu], (size_t)lu * dim, nch, gl, G, opt, scale, p, s0, s1, gu);
+            } else {
+                float* du = C.stage_u[qu] + (size_t)b * dim;
+#pragma unroll
+                for (int a = 0; a < IT; ++a) {
+                    const int ch = gl + a * G;
+                    if (ch < nch) gu.c[a].st(du + (size_t)ch * 4);
+                }
+            }
+        };
+        for (int rnd = 0;; ++rnd) {
+            const int o_lo = round_lo(rnd), n_r = round_n(rnd);
+            const int k0 = gfirst - goff + o_lo * gstride;
+            if (k0 >= nS) break;  // warp-uniform
             const int kb = k0 + goff;
             Rec cur;
             if (rnd < NPR) {
@@ -616,92 +712,116 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                 for (int r = 0; r < NPR; ++r)
                     if (r == rnd) cur = recN[r];
             } else {
-                fetch_records(cur, lo, nS, kb);
+                fetch_records(cur, lo, nS, kb, n_r);
             }
-            const bool pf_round = PFS && pf_live && rnd < NPR;  // this round's clean item rows sit in shared memory
-            float bias_r[SB];  // lane t < 3 holds the width-1 companion of lookup t (user, positive, negative)
+            if (rnd < NREG) {
+                // ---- regular round: item rows in the region, user row + state in slots 3i .. 3i + 2 ----
+                float bias_r[SBA];  // lane t < 3 holds the width-1 companion of lookup t (user, positive, negative)
 #pragma unroll
-            for (int i = 0; i < SB; ++i) {
-                const uint32_t bf = __shfl_sync(0xffffffffu, cur.b[i / G], i % G, G);
-                const uint32_t q = __shfl_sync(0xffffffffu, cur.q[i / G], i % G, G);
-                const uint32_t lu = __shfl_sync(0xffffffffu, cur.lu[i / G], i % G, G);
-                const uint32_t lp = __shfl_sync(0xffffffffu, cur.lp[i / G], i % G, G);
-                const uint32_t ln = __shfl_sync(0xffffffffu, cur.ln[i / G], i % G, G);
-                bias_r[i] = 0.f;
-                if (bf != 0xFFFFFFFFu) {
-                    const bool pfs = pf_round && rnd * SB + i < PFS;
-                    const bool have_p = pfs && !(bf & (1u << 30)), have_n = pfs && !(bf & (1u << 31));
-                    const trs_table& TU = C.user[q & 15u];
-                    const trs_table& TP = C.item[(q >> 4) & 15u];
-                    const trs_table& TN = C.item[(q >> 8) & 15u];
-                    copy_row(i * 3 + 0, TU.emb + (size_t)lu * dim);
-                    if (!have_p) copy_row(i * 3 + 1, TP.emb + (size_t)lp * dim);
-                    if (!have_n) copy_row(i * 3 + 2, TN.emb + (size_t)ln * dim);
-                    if (gl < 3) {
-                        const float* lin = gl == 0 ? TU.lin : (gl == 1 ? TP.lin : TN.lin);
-                        const uint32_t lrow = gl == 0 ? lu : (gl == 1 ? lp : ln);
-                        const bool have = gl == 1 ? have_p : (gl == 2 ? have_n : false);
-                        if (lin) {
-                            if (have) bias_r[i] = reinterpret_cast<const float*>(
-                                          my_pf_bias + (size_t)((rnd * SB + i) * 2 + (gl - 1)) * 16)[lrow & 3u];
-                            else bias_r[i] = __ldcg(lin + lrow);
+                for (int i = 0; i < SBA; ++i) {
+                    const uint32_t bf = __shfl_sync(0xffffffffu, cur.b[i / G], i % G, G);
+                    const uint32_t q = __shfl_sync(0xffffffffu, cur.q[i / G], i % G, G);
+                    const uint32_t lu = __shfl_sync(0xffffffffu, cur.lu[i / G], i % G, G);
+                    const uint32_t lp = __shfl_sync(0xffffffffu, cur.lp[i / G], i % G, G);
+                    const uint32_t ln = __shfl_sync(0xffffffffu, cur.ln[i / G], i % G, G);
+                    bias_r[i] = 0.f;
+                    if (i < n_r && bf != 0xFFFFFFFFu) {
+                        const int ord = o_lo + i;
+                        const bool have_p = pf_live && !(bf & SAMP_DIRTY_POS), have_n = pf_live && !(bf & SAMP_DIRTY_NEG);
+                        const trs_table& TU = C.user[q & 15u];
+                        const trs_table& TP = C.item[(q >> 4) & 15u];
+                        const trs_table& TN = C.item[(q >> 8) & 15u];
+                        copy_row(i * 3 + 0, TU.emb + (size_t)lu * dim);
+                        if (bf & SAMP_USER_SINGLE) {
+                            if (KIND != TRS_OPT_SGD) copy_row(i * 3 + 1, TU.emb_s0 + (size_t)lu * dim);
+                            if (KIND == TRS_OPT_SPARSE_ADAM) copy_row(i * 3 + 2, TU.emb_s1 + (size_t)lu * dim);
                         }
-                    }
-                }
-                sh_cp_async_commit();
-            }
-#pragma unroll
-            for (int i = 0; i < SB; ++i) {
-                sh_cp_async_wait(SB - 1 - i);
-                const uint32_t bf = __shfl_sync(0xffffffffu, cur.b[i / G], i % G, G);
-                const uint32_t q = __shfl_sync(0xffffffffu, cur.q[i / G], i % G, G);
-                const bool valid = bf != 0xFFFFFFFFu;
-                const uint32_t b = bf & 0x3FFFFFFFu;
-                Row<4, IT> xu, xp, xn;
-                if (valid) {
-                    const bool pfs = pf_round && rnd * SB + i < PFS;
-                    const bool have_p = pfs && !(bf & (1u << 30)), have_n = pfs && !(bf & (1u << 31));
-                    xu = slot_row(i * 3 + 0);
-                    xp = have_p ? pf_row((rnd * SB + i) * 2 + 0) : slot_row(i * 3 + 1);
-                    xn = have_n ? pf_row((rnd * SB + i) * 2 + 1) : slot_row(i * 3 + 2);
-                } else {
-#pragma unroll
-                    for (int a = 0; a < IT; ++a) xu.c[a] = xp.c[a] = xn.c[a] = Vec<4>::zero();
-                }
-                const float bu = __shfl_sync(0xffffffffu, bias_r[i], 0, G);
-                const float bip = __shfl_sync(0xffffffffu, bias_r[i], 1, G);
-                const float bin = __shfl_sync(0xffffffffu, bias_r[i], 2, G);
-                // linear.py:78: s = <u, v> + b_u + b_i; loss.py:7-9: h = s- - s+ + 1, d/ds = [h >= 0] / B
-                const float sp = (group_sum<G>(row_dot_partial(xu, xp)) + bu) + bip;
-                const float sn = (group_sum<G>(row_dot_partial(xu, xn)) + bu) + bin;
-                const float h = __fadd_rn(__fsub_rn(sn, sp), 1.0f);
-                const float g = (h >= 0.f) ? invB : 0.f;
-                if (valid) {
-                    if (gl == 0) hsum += fmaxf(h, 0.f);
-                    const uint32_t qu = q & 15u, qp = (q >> 4) & 15u, qn = (q >> 8) & 15u;
-                    float* du = C.stage_u[qu] + (size_t)b * dim;
-                    float* dp = C.stage_i[qp] + (size_t)b * dim;
-                    float* dn = C.stage_i[qn] + (size_t)(Bs + b) * dim;
-#pragma unroll
-                    for (int a = 0; a < IT; ++a) {
-                        const int ch = gl + a * G;
-                        if (ch < nch) {
-                            Vec<4> gu, gp, gn;
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                gu[e] = g * (xn.c[a][e] - xp.c[a][e]);
-                                gp[e] = -g * xu.c[a][e];
-                                gn[e] = g * xu.c[a][e];
+                        if (!have_p) copy_region(ord * 2 + 0, TP.emb + (size_t)lp * dim);
+                        if (!have_n) copy_region(ord * 2 + 1, TN.emb + (size_t)ln * dim);
+                        if (gl < 3) {
+                            const float* lin = gl == 0 ? TU.lin : (gl == 1 ? TP.lin : TN.lin);
+                            const uint32_t lrow = gl == 0 ? lu : (gl == 1 ? lp : ln);
+                            const bool have = gl == 1 ? have_p : (gl == 2 ? have_n : false);
+                            if (lin) {
+                                if (have) bias_r[i] = reinterpret_cast<const float*>(
+                                              my_pf_bias + (size_t)(ord * 2 + (gl - 1)) * 16)[lrow & 3u];
+                                else bias_r[i] = __ldcg(lin + lrow);
                             }
-                            gu.st(du + (size_t)ch * 4);
-                            gp.st(dp + (size_t)ch * 4);
-                            gn.st(dn + (size_t)ch * 4);
                         }
                     }
-                    if (gl == 0) {
-                        C.stage_b[qp][b] = -g;
-                        C.stage_b[qn][Bs + b] = g;
+                    sh_cp_async_commit();
+                }
+#pragma unroll
+                for (int i = 0; i < SBA; ++i) {
+                    sh_cp_async_wait(SBA - 1 - i);
+                    const uint32_t bf = __shfl_sync(0xffffffffu, cur.b[i / G], i % G, G);
+                    const uint32_t q = __shfl_sync(0xffffffffu, cur.q[i / G], i % G, G);
+                    const uint32_t lu = __shfl_sync(0xffffffffu, cur.lu[i / G], i % G, G);
+                    const bool valid = i < n_r && bf != 0xFFFFFFFFu;
+                    Row<4, IT> xu, xp, xn;
+                    if (valid) {
+                        xu = slot_row(i * 3 + 0);
+                        xp = region_row((o_lo + i) * 2 + 0);
+                        xn = region_row((o_lo + i) * 2 + 1);
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < IT; ++a) xu.c[a] = xp.c[a] = xn.c[a] = Vec<4>::zero();
                     }
+                    const float bu = __shfl_sync(0xffffffffu, bias_r[i], 0, G);
+                    const float bip = __shfl_sync(0xffffffffu, bias_r[i], 1, G);
+                    const float bin = __shfl_sync(0xffffffffu, bias_r[i], 2, G);
+                    process(valid, bf, q, lu, xu, xp, xn, bu, bip, bin, i * 3);
+                }
+            } else {
+                // ---- overflow round: two samples, all five rows in the thread-private slots 5i .. 5i + 4 ----
+                float bias_r[SBO];
+#pragma unroll
+                for (int i = 0; i < SBO; ++i) {
+                    const uint32_t bf = __shfl_sync(0xffffffffu, cur.b[i / G], i % G, G);
+                    const uint32_t q = __shfl_sync(0xffffffffu, cur.q[i / G], i % G, G);
+                    const uint32_t lu = __shfl_sync(0xffffffffu, cur.lu[i / G], i % G, G);
+                    const uint32_t lp = __shfl_sync(0xffffffffu, cur.lp[i / G], i % G, G);
+                    const uint32_t ln = __shfl_sync(0xffffffffu, cur.ln[i / G], i % G, G);
+                    bias_r[i] = 0.f;
+                    if (bf != 0xFFFFFFFFu) {
+                        const trs_table& TU = C.user[q & 15u];
+                        const trs_table& TP = C.item[(q >> 4) & 15u];
+                        const trs_table& TN = C.item[(q >> 8) & 15u];
+                        copy_row(i * 5 + 0, TU.emb + (size_t)lu * dim);
+                        if (bf & SAMP_USER_SINGLE) {
+                            if (KIND != TRS_OPT_SGD) copy_row(i * 5 + 1, TU.emb_s0 + (size_t)lu * dim);
+                            if (KIND == TRS_OPT_SPARSE_ADAM) copy_row(i * 5 + 2, TU.emb_s1 + (size_t)lu * dim);
+                        }
+                        copy_row(i * 5 + 3, TP.emb + (size_t)lp * dim);
+                        copy_row(i * 5 + 4, TN.emb + (size_t)ln * dim);
+                        if (gl < 3) {
+                            const float* lin = gl == 0 ? TU.lin : (gl == 1 ? TP.lin : TN.lin);
+                            const uint32_t lrow = gl == 0 ? lu : (gl == 1 ? lp : ln);
+                            if (lin) bias_r[i] = __ldcg(lin + lrow);
+                        }
+                    }
+                    sh_cp_async_commit();
+                }
+#pragma unroll
+                for (int i = 0; i < SBO; ++i) {
+                    sh_cp_async_wait(SBO - 1 - i);
+                    const uint32_t bf = __shfl_sync(0xffffffffu, cur.b[i / G], i % G, G);
+                    const uint32_t q = __shfl_sync(0xffffffffu, cur.q[i / G], i % G, G);
+                    const uint32_t lu = __shfl_sync(0xffffffffu, cur.lu[i / G], i % G, G);
+                    const bool valid = bf != 0xFFFFFFFFu;
+                    Row<4, IT> xu, xp, xn;
+                    if (valid) {
+                        xu = slot_row(i * 5 + 0);
+                        xp = slot_row(i * 5 + 3);
+                        xn = slot_row(i * 5 + 4);
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < IT; ++a) xu.c[a] = xp.c[a] = xn.c[a] = Vec<4>::zero();
+                    }
+                    const float bu = __shfl_sync(0xffffffffu, bias_r[i], 0, G);
+                    const float bip = __shfl_sync(0xffffffffu, bias_r[i], 1, G);
+                    const float bin = __shfl_sync(0xffffffffu, bias_r[i], 2, G);
+                    process(valid, bf, q, lu, xu, xp, xn, bu, bip, bin, i * 5);
                 }
             }
         }
@@ -709,127 +829,13 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
         // flight across the barrier
         if (more) {
 #pragma unroll
-            for (int r = 0; r < NPR; ++r) fetch_records(recN[r], lo + ep.batch, nS_next, gfirst + r * gstride * SB);
+            for (int r = 0; r < NPR; ++r)
+                fetch_records(recN[r], lo + ep.batch, nS_next, gfirst + round_lo(r) * gstride, round_n(r));
         }
         nS_cur = nS_next;
-        // Phase B over positions [pbeg, pend) of the step's owned-lookup list; dB holds my first round's descriptors.
-        // A row group takes PB positions per round; only the first position of a run of equal rows works (it sums
-        // the run's staged rows in slot order).
-        auto phase_b = [&](Desc& dB, int pbeg, int pend) {
-            for (int p0 = pbeg + gfirst - goff; p0 < pend; p0 += gstride * PB) {  // warp-uniform trip count
-                const int pb = p0 + goff;
-                float bsc[PB];  // lanes 0..3: staged bias gradient, bias, its state 0 / 1 of position i
-#pragma unroll
-                for (int i = 0; i < PB; ++i) {
-                    const uint32_t key = __shfl_sync(0xffffffffu, dB.key[i / G], i % G, G);
-                    const uint32_t sf = __shfl_sync(0xffffffffu, dB.sf[i / G], i % G, G);
-                    const uint32_t sl = sf & 0x1FFFFFFFu;
-                    bsc[i] = 0.f;
-                    if (sf & (1u << 29)) {
-                        const bool it = (sf >> 31) != 0u;
-                        const trs_table& t = it ? tI : tU;
-                        const size_t roff = (size_t)key * dim;
-                        copy_row(i * 4 + 0, (it ? my_stage_i : my_stage_u) + (size_t)sl * dim);
-                        copy_row(i * 4 + 1, t.emb + roff);
-                        if (KIND != TRS_OPT_SGD) copy_row(i * 4 + 2, t.emb_s0 + roff);
-                        if (KIND == TRS_OPT_SPARSE_ADAM) copy_row(i * 4 + 3, t.emb_s1 + roff);
-                        if (it && item_lin && gl < 4) {
-                            if (gl == 0) bsc[i] = __ldcg(my_stage_b + sl);
-                            else if (gl == 1) bsc[i] = __ldcg(t.lin + key);
-                            else if (gl == 2) { if (KIND != TRS_OPT_SGD) bsc[i] = __ldcg(t.lin_s0 + key); }
-                            else { if (KIND == TRS_OPT_SPARSE_ADAM) bsc[i] = __ldcg(t.lin_s1 + key); }
-                        }
-                    }
-                    sh_cp_async_commit();
-                }
-                Desc cur = dB;
-                if (p0 + gstride * PB < pend) fetch_descs(dB, lo, nU, nI, pb + gstride * PB, pend);
-#pragma unroll
-                for (int i = 0; i < PB; ++i) {
-                    sh_cp_async_wait(PB - 1 - i);
-                    const uint32_t key = __shfl_sync(0xffffffffu, cur.key[i / G], i % G, G);
-                    const uint32_t sf = __shfl_sync(0xffffffffu, cur.sf[i / G], i % G, G);
-                    const bool it = (sf >> 31) != 0u;
-                    float gb = 0.f, pl = 0.f, l0 = 0.f, l1 = 0.f;
-                    if (G < 32 || it) {  // one row group per warp: the branch is warp-uniform
-                        gb = __shfl_sync(0xffffffffu, bsc[i], 0, G);
-                        pl = __shfl_sync(0xffffffffu, bsc[i], 1, G);
-                        if (KIND != TRS_OPT_SGD) l0 = __shfl_sync(0xffffffffu, bsc[i], 2, G);
-                        if (KIND == TRS_OPT_SPARSE_ADAM) l1 = __shfl_sync(0xffffffffu, bsc[i], 3, G);
-                    }
-                    if (!(sf & (1u << 29))) continue;
-                    const trs_table& t = it ? tI : tU;
-                    Row<4, IT> g = slot_row(i * 4 + 0), p = slot_row(i * 4 + 1), s0, s1;
-#pragma unroll
-                    for (int a = 0; a < IT; ++a) s0.c[a] = s1.c[a] = Vec<4>::zero();
-                    if (KIND != TRS_OPT_SGD) s0 = slot_row(i * 4 + 2);
-                    if (KIND == TRS_OPT_SPARSE_ADAM) s1 = slot_row(i * 4 + 3);
-                    if (sf & (1u << 30)) {  // duplicates (rare under uniform ids): the rest of the run, in slot order
-                        const int pos = pb + i * gstride;
-                        const int k = it ? pos - nU : pos, n = it ? nI : nU;
-                        const uint32_t* K = it ? C.ikey + 2 * lo : C.ukey + lo;
-                        const uint32_t* P = it ? C.ival + 2 * lo : C.uval + lo;
-                        const float* stage = it ? my_stage_i : my_stage_u;
-                        for (int q = k + 1; q < n && __ldg(K + q) == key; ++q) {
-                            const uint32_t j = __ldg(P + q);
-                            const Row<4, IT> r = ld_row(stage + (size_t)j * dim);
-#pragma unroll
-                            for (int a = 0; a < IT; ++a)
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) g.c[a][e] = __fadd_rn(g.c[a][e], r.c[a][e]);
-                            if (it && item_lin && gl == 0) gb = __fadd_rn(gb, __ldcg(my_stage_b + j));
-                        }
-                    }
-                    sh_update_store<KIND, IT>(t, (size_t)key * dim, nch, gl, G, opt, scale, p, s0, s1, g);
-                    if (it && item_lin && gl == 0) {
-                        OptScalars ok = opt;
-                        ok.kind = KIND;
-                        opt_update(ok, scale, gb, pl, l0, l1);
-                        t.lin[key] = pl;
-                        if (KIND != TRS_OPT_SGD) t.lin_s0[key] = l0;
-                        if (KIND == TRS_OPT_SPARSE_ADAM) t.lin_s1[key] = l1;
-                    }
-                }
-            }
-        };
-        // The NEXT step's item rows: every clean one (not updated by this step, plan flag) of my group's first PFS
-        // samples starts its trip -- from the owner's HBM, mostly over NVLink -- into shared memory and lands while
-        // the owners update (bulk async copies, one mbarrier per row group).  The lane that holds a sample's record
-        // issues its copies.
-        auto issue_prefetch = [&]() {
-            pf_live = false;
-            if (PFS && more) {
-#pragma unroll
-                for (int r = 0; r < NPR; ++r) {
-#pragma unroll
-                    for (int z = 0; z < RPL; ++z) {
-                        const int i = gl + z * G;
-                        const uint32_t bf = recN[r].b[z];
-                        if (i < SB && r * SB + i < PFS && bf != 0xFFFFFFFFu) {
-                            const uint32_t q = recN[r].q[z];
-                            const trs_table& TP = C.item[(q >> 4) & 15u];
-                            const trs_table& TN = C.item[(q >> 8) & 15u];
-                            const bool fp = !(bf & (1u << 30)), fn = !(bf & (1u << 31));
-                            const uint32_t per = (uint32_t)dim * 4u + (TP.lin ? 16u : 0u);
-                            const uint32_t bytes = (fp ? per : 0u) + (fn ? per : 0u);
-                            if (bytes) sh_mbar_expect_tx(my_bar, bytes);
-                            const int j = (r * SB + i) * 2;
-                            if (fp) {
-                                sh_bulk_g2s(my_pf_rows + (size_t)j * ROWB, TP.emb + (size_t)recN[r].lp[z] * dim, (uint32_t)dim * 4u, my_bar);
-                                if (TP.lin) sh_bulk_g2s(my_pf_bias + (size_t)j * 16, TP.lin + (recN[r].lp[z] & ~3u), 16u, my_bar);
-                            }
-                            if (fn) {
-                                sh_bulk_g2s(my_pf_rows + (size_t)(j + 1) * ROWB, TN.emb + (size_t)recN[r].ln[z] * dim, (uint32_t)dim * 4u, my_bar);
-                                if (TN.lin) sh_bulk_g2s(my_pf_bias + (size_t)(j + 1) * 16, TN.lin + (recN[r].ln[z] & ~3u), 16u, my_bar);
-                            }
-                        }
-                    }
-                }
-                __syncwarp();  // every expect_tx of the group precedes its one arrival
-                if (gl == 0) sh_mbar_arrive(my_bar);
-                pf_live = true;
-            }
-        };
+        const int nP = nU + nI;
+        Desc dB;
+        fetch_descs(dB, lo, nU, nI, gfirst, nP);
 
         hsum = warp_sum(hsum);
         if ((threadIdx.x & 31) == 0) s_loss[threadIdx.x >> 5] = hsum;
@@ -841,32 +847,123 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
             C.loss_part[(size_t)si * cpr + c] = H;
             if (tr) tr[1] = shard_now_ns();
         }
-        const int nP = nU + nI;
-        Desc dB;
-        if (W > 1 && C.split_b) {
-            // Several ranks: the gradient rows of USER lookups are staged by this rank's own CTAs only (samples run on
-            // their user row's owner), so the user rows update behind a barrier of THIS rank -- while the rows just
-            // stored into the peers' staging buffers drain over NVLink -- and the cross-rank barrier sits between
-            // the user rows and the item rows.
-            fetch_descs(dB, lo, nU, nI, gfirst, nU);
-            ++lbar_no;
-            rank_barrier(C, lbar_no * (unsigned)cpr, timeout_ns);
-            if (tr && threadIdx.x == 0) tr[5] = shard_now_ns();
-            issue_prefetch();
-            phase_b(dB, 0, nU);
-            fetch_descs(dB, lo, nU, nI, nU + gfirst, nP);
-            if (tr && threadIdx.x == 0) tr[6] = shard_now_ns();
-            ++bar_no;
-            cross_rank_barrier(C, sync_epoch + bar_no, (unsigned)cpr, timeout_ns, true);
-            if (tr && threadIdx.x == 0) tr[2] = shard_now_ns();
-            phase_b(dB, nU, nP);
-        } else {
-            fetch_descs(dB, lo, nU, nI, gfirst, nP);  // plan data: in flight across the barrier
-            ++bar_no;
-            cross_rank_barrier(C, sync_epoch + bar_no, (unsigned)cpr, timeout_ns, true);
-            if (tr && threadIdx.x == 0) tr[2] = shard_now_ns();
-            issue_prefetch();
-            phase_b(dB, 0, nP);
+        ++bar_no;
+        cross_rank_barrier(C, sync_epoch + bar_no, (unsigned)cpr, timeout_ns, true);
+        if (tr && threadIdx.x == 0) tr[2] = shard_now_ns();
+
+        // ------------------------------ phase B ------------------------------------------
+        // First the NEXT step's item rows: every clean one (not updated by this step, plan flag) of my group's first
+        // PFS samples starts its trip -- from the owner's HBM, mostly over NVLink -- into the region and lands while
+        // the owners update (bulk async copies, one mbarrier per row group).  The lane that holds a sample's record
+        // issues its copies.
+        pf_live = false;
+        if (PFS && more) {
+#pragma unroll
+            for (int r = 0; r < NREG; ++r) {
+#pragma unroll
+                for (int z = 0; z < RPL; ++z) {
+                    const int i = gl + z * G;
+                    const uint32_t bf = recN[r].b[z];
+                    if (i < round_n(r) && bf != 0xFFFFFFFFu) {
+                        const uint32_t q = recN[r].q[z];
+                        const trs_table& TP = C.item[(q >> 4) & 15u];
+                        const trs_table& TN = C.item[(q >> 8) & 15u];
+                        const bool fp = !(bf & SAMP_DIRTY_POS), fn = !(bf & SAMP_DIRTY_NEG);
+                        const uint32_t per = (uint32_t)dim * 4u + (TP.lin ? 16u : 0u);
+                        const uint32_t bytes = (fp ? per : 0u) + (fn ? per : 0u);
+                        if (bytes) sh_mbar_expect_tx(my_bar, bytes);
+                        const int j = (round_lo(r) + i) * 2;
+                        if (fp) {
+                            sh_bulk_g2s(my_pf_rows + (size_t)j * ROWB, TP.emb + (size_t)recN[r].lp[z] * dim, (uint32_t)dim * 4u, my_bar);
+                            if (TP.lin) sh_bulk_g2s(my_pf_bias + (size_t)j * 16, TP.lin + (recN[r].lp[z] & ~3u), 16u, my_bar);
+                        }
+                        if (fn) {
+                            sh_bulk_g2s(my_pf_rows + (size_t)(j + 1) * ROWB, TN.emb + (size_t)recN[r].ln[z] * dim, (uint32_t)dim * 4u, my_bar);
+                            if (TN.lin) sh_bulk_g2s(my_pf_bias + (size_t)(j + 1) * 16, TN.lin + (recN[r].ln[z] & ~3u), 16u, my_bar);
+                        }
+                    }
+                }
+            }
+            __syncwarp();  // every expect_tx of the group precedes its one arrival
+            if (gl == 0) sh_mbar_arrive(my_bar);
+            pf_live = true;
+        }
+        // Owned rows: a row group takes PB positions of the step's sorted list per round; only the first position of
+        // a run of equal rows works (it sums the run's staged rows in slot order); rows phase A updated are skipped.
+        for (int p0 = gfirst - goff; p0 < nP; p0 += gstride * PB) {  // warp-uniform trip count
+            const int pb = p0 + goff;
+            float bsc[PB];  // lanes 0..3: staged bias gradient, bias, its state 0 / 1 of position i
+#pragma unroll
+            for (int i = 0; i < PB; ++i) {
+                const uint32_t key = __shfl_sync(0xffffffffu, dB.key[i / G], i % G, G);
+                const uint32_t sf = __shfl_sync(0xffffffffu, dB.sf[i / G], i % G, G);
+                const uint32_t sl = sf & 0x1FFFFFFFu;
+                bsc[i] = 0.f;
+                if (sf & (1u << 29)) {
+                    const bool it = (sf >> 31) != 0u;
+                    const trs_table& t = it ? tI : tU;
+                    const size_t roff = (size_t)key * dim;
+                    copy_row(i * 4 + 0, (it ? my_stage_i : my_stage_u) + (size_t)sl * dim);
+                    copy_row(i * 4 + 1, t.emb + roff);
+                    if (KIND != TRS_OPT_SGD) copy_row(i * 4 + 2, t.emb_s0 + roff);
+                    if (KIND == TRS_OPT_SPARSE_ADAM) copy_row(i * 4 + 3, t.emb_s1 + roff);
+                    if (it && item_lin && gl < 4) {
+                        if (gl == 0) bsc[i] = __ldcg(my_stage_b + sl);
+                        else if (gl == 1) bsc[i] = __ldcg(t.lin + key);
+                        else if (gl == 2) { if (KIND != TRS_OPT_SGD) bsc[i] = __ldcg(t.lin_s0 + key); }
+                        else { if (KIND == TRS_OPT_SPARSE_ADAM) bsc[i] = __ldcg(t.lin_s1 + key); }
+                    }
+                }
+                sh_cp_async_commit();
+            }
+            Desc cur = dB;
+            if (p0 + gstride * PB < nP) fetch_descs(dB, lo, nU, nI, pb + gstride * PB, nP);
+#pragma unroll
+            for (int i = 0; i < PB; ++i) {
+                sh_cp_async_wait(PB - 1 - i);
+                const uint32_t key = __shfl_sync(0xffffffffu, cur.key[i / G], i % G, G);
+                const uint32_t sf = __shfl_sync(0xffffffffu, cur.sf[i / G], i % G, G);
+                const bool it = (sf >> 31) != 0u;
+                float gb = 0.f, pl = 0.f, l0 = 0.f, l1 = 0.f;
+                if (G < 32 || it) {  // one row group per warp: the branch is warp-uniform
+                    gb = __shfl_sync(0xffffffffu, bsc[i], 0, G);
+                    pl = __shfl_sync(0xffffffffu, bsc[i], 1, G);
+                    if (KIND != TRS_OPT_SGD) l0 = __shfl_sync(0xffffffffu, bsc[i], 2, G);
+                    if (KIND == TRS_OPT_SPARSE_ADAM) l1 = __shfl_sync(0xffffffffu, bsc[i], 3, G);
+                }
+                if (!(sf & (1u << 29))) continue;
+                const trs_table& t = it ? tI : tU;
+                Row<4, IT> g = slot_row(i * 4 + 0), p = slot_row(i * 4 + 1), s0, s1;
+#pragma unroll
+                for (int a = 0; a < IT; ++a) s0.c[a] = s1.c[a] = Vec<4>::zero();
+                if (KIND != TRS_OPT_SGD) s0 = slot_row(i * 4 + 2);
+                if (KIND == TRS_OPT_SPARSE_ADAM) s1 = slot_row(i * 4 + 3);
+                if (sf & (1u << 30)) {  // duplicates (rare under uniform ids): the rest of the run, in slot order
+                    const int pos = pb + i * gstride;
+                    const int k = it ? pos - nU : pos, n = it ? nI : nU;
+                    const uint32_t* K = it ? C.ikey + 2 * lo : C.ukey + lo;
+                    const uint32_t* P = it ? C.ival + 2 * lo : C.uval + lo;
+                    const float* stage = it ? my_stage_i : my_stage_u;
+                    for (int q = k + 1; q < n && __ldg(K + q) == key; ++q) {
+                        const uint32_t j = __ldg(P + q) & 0x1FFFFFFFu;
+                        const Row<4, IT> r = ld_row(stage + (size_t)j * dim);
+#pragma unroll
+                        for (int a = 0; a < IT; ++a)
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) g.c[a][e] = __fadd_rn(g.c[a][e], r.c[a][e]);
+                        if (it && item_lin && gl == 0) gb = __fadd_rn(gb, __ldcg(my_stage_b + j));
+                    }
+                }
+                sh_update_store<KIND, IT>(t, (size_t)key * dim, nch, gl, G, opt, scale, p, s0, s1, g);
+                if (it && item_lin && gl == 0) {
+                    OptScalars ok = opt;
+                    ok.kind = KIND;
+                    opt_update(ok, scale, gb, pl, l0, l1);
+                    t.lin[key] = pl;
+                    if (KIND != TRS_OPT_SGD) t.lin_s0[key] = l0;
+                    if (KIND == TRS_OPT_SPARSE_ADAM) t.lin_s1[key] = l1;
+                }
+            }
         }
         if (tr) {
             __syncthreads();
@@ -936,7 +1033,7 @@ static cudaError_t launch_shard(const ShardCtx* ctx0, const ShardCtx* ctxs, int 
 // chunks per lane halve the per-row bookkeeping instructions; measured equal at one rank, trs_debug_shard_chunks_per_lane.)
 static int g_shard_prefer_it = 1;
 static unsigned long long* g_shard_trace = nullptr;
-static int g_shard_split_b = 0;
+
 static bool pick_shard_shape(int dim, int* G, int* IT) {
     if (dim <= 0 || dim % 4 || dim > 512) return false;
     const int nch = dim / 4;
@@ -998,7 +1095,7 @@ extern "C" int trs_shard_plan_build(const trs_shard* sh, const trs_epoch* ep, vo
     int rc = check_shard(sh, &shape);
     if (rc) return rc;
     TRS_REQUIRE(ep && ep->user && ep->pos && ep->neg, "epoch ids are NULL");
-    TRS_REQUIRE(ep->batch > 0 && ep->batch <= (1 << 29), "global batch out of range");
+    TRS_REQUIRE(ep->batch > 0 && ep->batch < (1 << 27), "global batch out of range (< 2^27)");
     TRS_REQUIRE(ep->pos_meta == nullptr && ep->neg_meta == nullptr, "row-sharded training does not take metadata");
     TRS_REQUIRE(plan && tmp, "plan / tmp is NULL");
     if (ep->n_samples == 0) return TRS_OK;
@@ -1050,6 +1147,8 @@ extern "C" int trs_shard_plan_build(const trs_shard* sh, const trs_epoch* ep, vo
         dirty_bitmap_kernel<<<g2, RT_THREADS, 0, st>>>(ep->pos, ep->neg, n, ep->batch, bitmap, lb, exact);
         dim3 g1((unsigned)(((int64_t)ep->batch + RT_TILE - 1) / RT_TILE), (unsigned)steps);
         dirty_mark_kernel<<<g1, RT_THREADS, 0, st>>>(ep->pos, ep->neg, n, ep->batch, bitmap, lb, exact, samp_cnt, samp);
+        single_mark_kernel<<<g1, RT_THREADS, 0, st>>>((const uint32_t*)(P + L.ukey), (uint32_t*)(P + L.uval), own_cnt, samp_cnt,
+                                                     samp, ep->batch);
     }
     TRS_CUDA(cudaGetLastError());
     return TRS_OK;
@@ -1102,7 +1201,6 @@ extern "C" int trs_shard_train_steps(const trs_shard* shards, int n_local, const
         c.rank = sh.rank;
         c.world = sh.world;
         c.dim = sh.dim;
-        c.split_b = g_shard_split_b;
         for (int q = 0; q < sh.world; ++q) {
             TRS_REQUIRE(sh.user[q].emb && sh.item[q].emb && sh.stage[q] && sh.sync[q], "rank %d: peer %d is not mapped",
                         sh.rank, q);
@@ -1172,9 +1270,7 @@ extern "C" void trs_debug_shard_chunks_per_lane(int it) { g_shard_prefer_it = it
 // debug hook: device buffer of n_local * n_steps * CTAs-per-rank * 8 uint64 that the next launches fill with phase
 // time stamps (tools/shard_phases.py); NULL switches it off
 extern "C" void trs_debug_shard_trace(void* buf) { g_shard_trace = (unsigned long long*)buf; }
-// tuning hook: 1 = several ranks update their user rows behind a rank-local barrier while the gradient rows stored
-// into peer memory drain, and meet the peers between the user rows and the item rows (results do not change)
-extern "C" void trs_debug_shard_split_b(int on) { g_shard_split_b = on ? 1 : 0; }
+
 
 // ---- CUDA IPC plumbing ---------------------------------------------------------------------------------------
 extern "C" int trs_ipc_export(const void* ptr, void* handle64_host, uint64_t* offset_host) {

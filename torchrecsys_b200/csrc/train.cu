@@ -135,18 +135,21 @@ __device__ __forceinline__ Row<V, IT> row_scaled(float a, const Row<V, IT>& x) {
 }
 
 // Grid-wide barrier for a cooperative launch (all CTAs resident).  `counter` only ever grows:
-// after the g-th barrier it holds g * gridDim.x.
+// after the g-th barrier it holds g * gridDim.x.  One release fence on the way in (bar.sync before it: the stores of
+// the whole CTA happen before the fence), a relaxed add, relaxed polling, one acquire load on the way out -- acq_rel
+// fences instead of the sequentially-consistent __threadfence() (= fence.sc.gpu), which measured ~1 us more per
+// barrier on the row-sharded kernel (csrc/shard.cu).
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
     __syncthreads();
     target += gridDim.x;
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         unsigned seen;
-        do {  // relaxed polling; the fence below orders everything after the barrier
+        do {
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
         } while ((int)(seen - target) < 0);
-        __threadfence();
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
     }
     __syncthreads();
 }
