@@ -7,15 +7,15 @@ A "step" is one training step of the named workload: forward x2 + hinge + backwa
 over one batch (reference model.py:274-284).
 
 Default workload ("c4") = BASELINE.json configs[3], the large-table config north_star scales: Linear 50M users x
-5M items, dim 128, SparseAdam, batch 16384 PER GPU (weak scaling: the global batch is 16384 * N).
-  N = 1   the whole tables (84.5 GB with optimizer state) on one GPU through the fused persistent kernel
-          (csrc/train.cu).
-  N > 1   (under torchrun, one rank per GPU) the tables are ROW-SHARDED: row r lives on rank r % N; every rank
-          maps its peers' shards (CUDA IPC) and one persistent kernel per rank reads item rows from / stores
-          gradient rows into the owners' HBM over NVLink (csrc/shard.cu).  NCCL carries the per-epoch id
-          all-gather and the loss all-reduce; nothing per step.
+5M items, dim 128, SparseAdam, batch 16384 PER GPU (weak scaling: the global batch is 16384 * N), through the
+ROW-SHARDED persistent kernel (csrc/shard.cu) at every N:
+  N = 1   a group of one rank: the whole tables (84.5 GB with optimizer state) on one GPU.
+  N > 1   (under torchrun, one rank per GPU) row r lives on rank r % N; every rank maps its peers' shards (CUDA
+          IPC) and one persistent kernel per rank reads item rows from / stores gradient rows into the owners'
+          HBM over NVLink.  NCCL carries the per-epoch id all-gather and the loss all-reduce; nothing per step.
 The other BASELINE configs ride along in the same JSON line under "other_workloads" (N = 1: C2 FM, C3 MLP, C5
-predict, and the sharded kernel hosting a 1-rank group; N > 1: item-sharded C5 predict).  `--workload c2_fm`,
+predict, and the SAME C4 tables through fit()'s fused single-GPU kernel, csrc/train.cu; N > 1: item-sharded C5
+predict).  `--workload c2_fm`,
 `c3_mlp`, `c5_predict`, `c1_linear`, `c4_fused`, `c4_linear` select one of them as the headline instead.
 
   value      whole-job samples/s, every input already resident in HBM, CUDA events, max over ranks.  The K-step
@@ -260,6 +260,17 @@ def pick_repeats(probe_ms, min_ms, world, dev):
     return int(max(1, min(200, math.ceil(min_ms / max(float(t.item()), 1e-3)))))
 
 
+SAMPLE_CAP = 1 << 26  # samples (over all ranks) of one timed launch: bounds the id / plan buffers
+
+
+def split_repeats(R, samples_per_block):
+    """The K-step block is replayed R times; r_in replays go into ONE epoch (one plan build, one persistent launch --
+    what a real epoch of thousands of steps looks like), as many as the sample cap allows; the rest as further
+    launches.  Returns (replays per launch, launches)."""
+    r_in = max(1, min(R, SAMPLE_CAP // max(samples_per_block, 1)))
+    return r_in, -(-R // r_in)
+
+
 def traffic_of(workload, K):
     """dram bytes of the dominant kernel per launch, from the committed ncu --set full capture (STATIC: it is not
     measured by this run; profiles/traffic.json holds bytes per step, one launch = K steps)."""
@@ -360,43 +371,48 @@ def gpu_bench(args, wl, name):
         runner.reserve(K * B, B)
     uK, pK = user[W * B:], pos[W * B:]
     uK_h, pK_h = user_h[W * B:], pos_h[W * B:]
-    loss_host = torch.empty(K, dtype=torch.float32).pin_memory()
     seen = [W * B]
 
-    def resident_block():
-        loss = step_block(uK, pK, seen[0])
-        seen[0] += K * B
+    def run_block(u, p, n_samples, loss_host=None):
+        loss = step_block(u, p, seen[0])
+        seen[0] += n_samples
+        if loss_host is not None:
+            loss_host.copy_(loss, non_blocking=True)
         return loss
 
-    def e2e_block():
-        u_d = uK_h.to(dev, non_blocking=True)
-        p_d = pK_h.to(dev, non_blocking=True)
-        loss = step_block(u_d, p_d, seen[0])
-        seen[0] += K * B
-        loss_host.copy_(loss, non_blocking=True)
-        return loss
-
-    def timed(block, R):
+    def timed(fn, n):
         e0, e1 = ev(), ev()
         sync_all()
         e0.record()
-        for _ in range(R):
-            loss = block()
+        for _ in range(n):
+            loss = fn()
         e1.record()
         sync_all()
         return e0.elapsed_time(e1), loss
 
-    # both regions are warmed the same way: one untimed block each (allocator sizes), then R timed blocks
+    # how many replays of the K-step block make a timed region of >= min_ms: probe one block, then put the replays
+    # into ONE epoch (r_in x K steps: one plan build, one persistent launch) as far as the sample cap allows
+    run_block(uK, pK, K * B)
+    probe_ms, _ = timed(lambda: run_block(uK, pK, K * B), 1)
+    R = pick_repeats(probe_ms, args.min_ms, world, dev)
+    r_in, n_launch = split_repeats(R, K * B)
+    R = r_in * n_launch
+    uR, pR = uK.repeat(r_in), pK.repeat(r_in)
+    uR_h, pR_h = uK_h.repeat(r_in).pin_memory(), pK_h.repeat(r_in).pin_memory()
+    loss_host = torch.empty(r_in * K, dtype=torch.float32).pin_memory()
+    if hasattr(runner, "reserve"):
+        runner.reserve(r_in * K * B, B)
+    resident_block = lambda: run_block(uR, pR, r_in * K * B)
+    e2e_block = lambda: run_block(uR_h.to(dev, non_blocking=True), pR_h.to(dev, non_blocking=True), r_in * K * B, loss_host)
+    # both regions are warmed the same way: one untimed block each (allocator sizes), then the timed ones
     resident_block()
     e2e_block()
-    probe_ms, _ = timed(resident_block, 1)
-    R = pick_repeats(probe_ms, args.min_ms, world, dev)
     launches0 = runner.launches
     with ClockSampler(local) as clocks:
-        ms, loss = timed(resident_block, R)
-    launches = (runner.launches - launches0) // R + 1  # per K-step block; + the Philox kernel
+        ms, loss = timed(resident_block, n_launch)
+    launches = (runner.launches - launches0) // n_launch + 1  # per launch of r_in x K steps; + the Philox kernel
     mean_loss = float(loss.mean().item())
-    e2e_ms, _ = timed(e2e_block, R)
+    e2e_ms, _ = timed(e2e_block, n_launch)
 
     # ---- the fused kernel alone (roofline): the same K steps once more ----
     neg, neg_meta = _lib.philox_negatives(1234, seen[0], pK, wl["n_items"], item_meta)
@@ -469,12 +485,14 @@ def gpu_bench(args, wl, name):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if is_mlp else "f32", "data": "synthetic",
         "config": {"workload": wl["desc"], "name": name, "batch_per_gpu": B, "global_batch": B * world,
-                   "optimizer": wl["opt"], "repeats": R, "l2": "inputs larger than L2: tables+optimizer state "
+                   "optimizer": wl["opt"], "repeats": R, "steps_per_launch": r_in * K, "launches": n_launch,
+                   "l2": "inputs larger than L2: tables+optimizer state "
                    f"{(wl['n_users'] + wl['n_items']) * (wl['dim'] + 1) * 4 * (1 + S) / 1e9:.2f} GB, rows hit at random",
-                   "timed_region": ("Philox negatives + sort plan + K fused MLP steps (one C call), x repeats"
+                   "timed_region": ("Philox negatives + sort plan + fused MLP steps (one C call per launch); the K-step "
+                                    "block replayed `repeats` times, `steps_per_launch` steps per epoch call"
                                     if is_mlp else
-                                    "Philox negatives + sort plan + persistent fused train kernel (K steps in one "
-                                    "launch), x repeats"),
+                                    "Philox negatives + sort plan + persistent fused train kernel; the K-step block "
+                                    "replayed `repeats` times, `steps_per_launch` steps per plan build + kernel launch"),
                    "parallelism": (f"{world} INDEPENDENT REPLICAS of a single-GPU workload (no data-path collective: "
                                    "not a scaling result)") if world > 1 else "single GPU",
                    "clock_ramp": "0.3 s of device copies before the warm-up steps",
@@ -706,11 +724,14 @@ def sharded_bench(args, wl, name):
 
     seen = [0]
 
-    def block(src, lo_step, n_steps, timing=False):
+    def block(src, lo_step, n_steps, timing=False, loss_host=None):
         gu, gp = global_epoch(src, lo_step, n_steps)
         neg, _ = _lib.philox_negatives(1234, seen[0], gp, wl["n_items"])
         seen[0] += n_steps * Bg
-        return tr.train_epoch(gu, gp, neg, Bg, check=False, timing=timing), (gu, gp, neg)
+        loss = tr.train_epoch(gu, gp, neg, Bg, check=False, timing=timing)
+        if loss_host is not None:
+            loss_host.copy_(loss, non_blocking=True)
+        return loss, (gu, gp, neg)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     sync_all = (lambda: (torch.cuda.synchronize(), dist.barrier(), torch.cuda.synchronize())) if world > 1 \
@@ -720,37 +741,38 @@ def sharded_bench(args, wl, name):
     sync_all()
     tr.check_status()
     first_loss = float(loss_w[0].item())
-    loss_host = torch.empty(K, dtype=torch.float32).pin_memory()
 
-    def resident_block():
-        return block(ids_d, W, K)[0]
-
-    def e2e_block():
-        loss = block(ids_h, W, K)[0]
-        loss_host.copy_(loss, non_blocking=True)
-        return loss
-
-    def timed(fn, R):
+    def timed(fn, n):
         e0, e1 = ev(), ev()
         sync_all()
         e0.record()
-        for _ in range(R):
+        for _ in range(n):
             loss = fn()
         e1.record()
         sync_all()
         return e0.elapsed_time(e1), loss
 
+    # how many replays of the K-step block make a timed region of >= min_ms: probe one block, then put the replays
+    # into ONE epoch (r_in x K steps: one id all-gather, one plan build, one persistent launch per rank)
+    block(ids_d, W, K)
+    probe_ms, _ = timed(lambda: block(ids_d, W, K)[0], 1)
+    R = pick_repeats(probe_ms, args.min_ms, world, dev)
+    r_in, n_launch = split_repeats(R, K * Bg)
+    R = r_in * n_launch
+    rep_d = {q: t[W:].repeat(r_in, 1, 1) for q, t in ids_d.items()}
+    rep_h = {q: t[W:].repeat(r_in, 1, 1).pin_memory() for q, t in ids_h.items()}
+    loss_host = torch.empty(r_in * K, dtype=torch.float32).pin_memory()
+    resident_block = lambda: block(rep_d, 0, r_in * K)[0]
+    e2e_block = lambda: block(rep_h, 0, r_in * K, loss_host=loss_host)[0]
     resident_block()
     e2e_block()
-    probe_ms, _ = timed(resident_block, 1)
-    R = pick_repeats(probe_ms, args.min_ms, world, dev)
     launches0 = tr.launches
     with ClockSampler(local) as clocks:
-        ms, loss = timed(resident_block, R)
-    launches = (tr.launches - launches0) // R + 1
+        ms, loss = timed(resident_block, n_launch)
+    launches = (tr.launches - launches0) // n_launch + 1
     tr.check_status()
     mean_loss = float(loss.mean().item())
-    e2e_ms, _ = timed(e2e_block, R)
+    e2e_ms, _ = timed(e2e_block, n_launch)
     # the persistent kernel (and the plan) alone
     sync_all()
     _, (gu, gp, neg) = block(ids_d, W, K, timing=True)
@@ -779,7 +801,7 @@ def sharded_bench(args, wl, name):
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / (R * K), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["desc"], "name": name, "batch_per_gpu": B, "global_batch": Bg, "optimizer": wl["opt"],
-                   "repeats": R,
+                   "repeats": R, "steps_per_launch": r_in * K, "launches": n_launch,
                    "parallelism": (f"user / item tables ROW-SHARDED over {G} ranks (row % {G}); samples run on their "
                                    "user row's owner; item rows read from and gradient rows stored into the owner's "
                                    "HBM over NVLink by one persistent kernel per rank (CUDA-IPC mapped shards, flag "
@@ -788,7 +810,8 @@ def sharded_bench(args, wl, name):
                    "l2": f"inputs larger than L2: {(wl['n_users'] + wl['n_items']) * (D + 1) * 4 * (1 + S_) / G / 1e9:.1f} "
                          "GB of tables + optimizer state per rank, rows hit at random",
                    "timed_region": "id all-gather (NCCL) + Philox negatives + routing / sort plan + persistent sharded "
-                                   "kernel (K steps in one launch) + loss all-reduce, x repeats",
+                                   "kernel + loss all-reduce; the K-step block replayed `repeats` times, `steps_per_launch` "
+                                   "steps per all-gather + plan build + kernel launch",
                    "clock_ramp": "0.3 s of device copies before the warm-up steps",
                    "first_step_loss": first_loss, "mean_loss_last_block": mean_loss,
                    "loss_note": "the K-step block is replayed `repeats` times (fresh negatives each time): the model "
@@ -833,7 +856,7 @@ def brief(line):
 def resolve(args):
     name = args.workload
     if name == "c4":
-        name = "c4_fused" if args.gpus == 1 and not args.emulate_world else "c4_linear"
+        name = "c4_linear"   # every N runs the row-sharded kernel (N = 1: a group of one rank)
     wl = dict(WORKLOADS[name])
     if args.batch:
         wl["batch"] = args.batch
@@ -900,8 +923,8 @@ def main():
                 others["c2_fm"] = brief(gpu_bench(sub, dict(WORKLOADS["c2_fm"]), "c2_fm")[0])
                 others["c3_mlp"] = brief(gpu_bench(sub, dict(WORKLOADS["c3_mlp"]), "c3_mlp")[0])
                 others["c5_predict"] = brief(predict_bench(sub, dict(WORKLOADS["c5_predict"]), "c5_predict", K=5, W=3))
-                sub.steps, sub.warmup, sub.emulate_world = args.steps, args.warmup, 1
-                others["c4_sharded_kernel_1rank"] = brief(sharded_bench(sub, dict(WORKLOADS["c4_linear"]), "c4_linear")[0])
+                sub.steps, sub.warmup = args.steps, args.warmup
+                others["c4_fused_fit_kernel"] = brief(gpu_bench(sub, dict(WORKLOADS["c4_fused"]), "c4_fused")[0])
             elif world > 1:
                 others["c5_predict"] = brief(predict_bench(sub, dict(WORKLOADS["c5_predict"]), "c5_predict", K=5, W=3))
         except Exception as e:  # a sub-result must never cost the headline line

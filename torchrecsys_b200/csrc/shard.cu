@@ -642,6 +642,17 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
         if (tr && threadIdx.x == 0) tr[0] = shard_now_ns();
 
         // ------------------------------ phase A ------------------------------------------
+        {   // this step's phase-B lists (sorted keys and slots, streamed from HBM exactly once) -> L2 now: a round's
+            // descriptor fetch then costs an L2 hit instead of a DRAM round trip in front of every round
+            const int lu = (nU * 4 + 127) / 128, li = (nI * 4 + 127) / 128;
+            for (int t = c * NT + (int)threadIdx.x; t < 2 * (lu + li); t += cpr * NT) {
+                const char* base = t < lu ? (const char*)(C.ukey + lo)
+                                 : t < 2 * lu ? (const char*)(C.uval + lo)
+                                 : t < 2 * lu + li ? (const char*)(C.ikey + 2 * lo) : (const char*)(C.ival + 2 * lo);
+                const int line = t < lu ? t : t < 2 * lu ? t - lu : t < 2 * lu + li ? t - 2 * lu : t - 2 * lu - li;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)line * 128));
+            }
+        }
         float hsum = 0.f;
         if (PFS && pf_live) {  // rows fetched while the previous step's owners were updating: landed?
             while (!sh_mbar_try_wait(my_bar, pf_parity)) {
