@@ -249,6 +249,12 @@ size_t trs_predict_topk_workspace_bytes(const trs_model* model, int64_t n_query,
 int trs_predict_topk(const trs_model* model, const int64_t* users, int64_t n_query, const int64_t* item_meta,
                      int k, int64_t item_offset, int64_t* out_idx, float* out_score, int32_t* overflow,
                      void* workspace, size_t workspace_bytes, trs_stream_t stream);
+/* The same with the caller's promise `items_prepared` != 0: `workspace` was last used by a call with the same item
+ * tables (contents unchanged), item_meta and n_query, so the prepared bf16 item operand inside it is still valid and
+ * is not rebuilt -- serving many user batches against an unchanged model (model.py:383 loops the same way). */
+int trs_predict_topk_reuse(const trs_model* model, const int64_t* users, int64_t n_query, const int64_t* item_meta,
+                           int k, int64_t item_offset, int64_t* out_idx, float* out_score, int32_t* overflow,
+                           void* workspace, size_t workspace_bytes, int items_prepared, trs_stream_t stream);
 
 /* ---- multi-GPU building blocks (the reference is single-device, model.py:74) ----------- */
 /* a7 for the OWNER of a table shard: grad.coalesce() + the row-wise optimizer step (torch:

@@ -34,20 +34,28 @@ def parse_train_name(name):
 
 
 def well_conditioned_rows(net_type, opt, init, batch0, key, n_rows):
-    """Rows of table ``key`` whose first update is a stable function of the gradient.
+    """ENTRIES (not whole rows: the name is historic) of table ``key`` whose first update is a stable function of the
+    gradient, as a boolean mask of the table's shape.
 
-    The first Adagrad / Adam step is lr * g / (|g| + eps): where the true gradient is ~eps (pos and
-    neg contributions cancelling, a saturated sigmoid) its rounding noise decides the step, and no
-    two implementations -- nor the reference at two thread counts -- agree.  Those rows are left out
-    of the one-step comparison."""
+    The first Adagrad / Adam step is lr * g / (|g| + eps): where the summed gradient is tiny but NOT zero (pos and neg
+    contributions cancelling to rounding noise, a saturated sigmoid) the noise decides the step, and no two
+    implementations -- nor the reference at two thread counts -- agree.  Exactly-zero gradients (an inactive hinge,
+    -g + g on a bias) give an exactly-zero step and stay in.  Only 0 < |g| < 1e-5 is left out of the one-step comparison,
+    and the share of touched entries this drops is bounded here: < 2 % of an embedding table's touched entries, and at
+    most a quarter of the handful of touched entries of an FM first-order table (delta+ + delta- nearly cancels at
+    initialisation, where both sigmoids sit at 0.5)."""
     import numpy as np
     from oracle import cf_oracle as O
-    ok = np.ones(n_rows, dtype=bool)
+    shape = init[key].shape
+    ok = np.ones(shape, dtype=bool)
     if opt == "sgd":
         return ok
     _, grads = (O.linear_grads if net_type == "linear" else O.fm_grads)(init, batch0)
     rows, gsum = O.coalesce(*grads[key])
-    tiny = np.abs(gsum).min(axis=1) < 1e-5
-    if not (net_type == "linear" and key == "user_bias.weight"):  # exactly-zero gradient: no step at all
-        ok[rows[tiny]] = False
+    a = np.abs(gsum.reshape(len(rows), -1))
+    tiny = (a > 0) & (a < 1e-5)
+    share = float(tiny.mean()) if tiny.size else 0.0
+    limit = 0.02 if shape[1] > 1 else 0.25
+    assert share <= limit, f"{key}: {share:.1%} of the touched entries are ill-conditioned (limit {limit:.0%})"
+    ok[rows] = ~tiny
     return ok

@@ -151,3 +151,25 @@ def test_topk_long_item_stream_many_user_tiles(dev):
     assert bool((score[:, :-1] >= score[:, 1:]).all())
     assert int(idx.min()) >= 0 and int(idx.max()) < I
     assert bool((torch.sort(idx, dim=1).values[:, 1:] != torch.sort(idx, dim=1).values[:, :-1]).all())
+
+
+def test_item_operand_reuse_gives_identical_results_and_is_dropped_when_the_model_changes(dev):
+    """trs_predict_topk_reuse: a second call on the same workspace skips the re-cast of the item tables; a changed key
+    (the model was trained / loaded) rebuilds it."""
+    from torchrecsys_b200 import _lib
+    from torchrecsys_b200.collaborative.linear import Linear
+    torch.manual_seed(5)
+    net = Linear(400, 3000, {}, 64, use_metadata=False, use_cuda=True).to(dev).eval()
+    with torch.no_grad():
+        net.item_bias.weight.normal_(0, 0.05)
+    users = torch.arange(300, device=dev)
+    cache = _lib.TopkCache()
+    a = _lib.predict_topk(net.abi_model(), users, 20, cache=cache, cache_key=1)
+    ws = cache.ws
+    b = _lib.predict_topk(net.abi_model(), users, 20, cache=cache, cache_key=1)      # reuses the operand
+    assert cache.ws is ws and torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    with torch.no_grad():
+        net.item.weight.mul_(-1.0)                                                   # the model changes ...
+    c = _lib.predict_topk(net.abi_model(), users, 20, cache=cache, cache_key=2)      # ... and so does the key
+    fresh = _lib.predict_topk(net.abi_model(), users, 20)
+    assert cache.ws is not ws and torch.equal(c[0], fresh[0]) and not torch.equal(c[0], a[0])

@@ -28,7 +28,7 @@ SYMBOLS = [
     "trs_topk_merge", "trs_shard_stage_bytes", "trs_shard_plan_bytes", "trs_shard_plan_tmp_bytes",
     "trs_shard_plan_build", "trs_shard_workspace_bytes", "trs_shard_train_steps", "trs_ipc_export",
     "trs_ipc_open", "trs_ipc_close", "trs_scores_backward", "trs_sort_workspace_bytes", "trs_sorted_auc",
-    "trs_epoch_shuffle", "trs_gather_rows_i64",
+    "trs_epoch_shuffle", "trs_gather_rows_i64", "trs_predict_topk_reuse",
 ]
 
 
@@ -302,7 +302,17 @@ def mlp_train_steps(model: Model, mlp: Mlp, epoch: Epoch, optim: Optim, plan, wo
                                      C.c_void_p(_ptr(loss_out, torch.float32)), _stream()))
 
 
-def predict_topk(model: Model, users, k: int, item_meta=None, item_offset: int = 0):
+class TopkCache:
+    """Keeps the predict workspace -- with the prepared bf16 item operand inside -- between calls.  ``key`` is whatever
+    the caller uses to say "the item tables have not changed" (model.py: tensor versions + the fused runners'
+    update counter); a different key, query count or k rebuilds."""
+
+    def __init__(self):
+        self.ws, self.key = None, None
+
+
+def predict_topk(model: Model, users, k: int, item_meta=None, item_offset: int = 0, cache: Optional[TopkCache] = None,
+                 cache_key=None):
     """Top-k items for each user id in ``users`` against all items of ``model.item``.
     Returns (idx int64 [n, k], score fp32 [n, k], overflow int32 [n])."""
     L = lib()
@@ -317,12 +327,19 @@ def predict_topk(model: Model, users, k: int, item_meta=None, item_offset: int =
     nbytes = L.trs_predict_topk_workspace_bytes(C.byref(model), C.c_int64(n), k)
     if nbytes == 0:
         raise RuntimeError(f"libtrs_b200: {L.trs_last_error().decode()}")
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    _check(L.trs_predict_topk(C.byref(model), C.c_void_p(_ptr(users, torch.int64)), C.c_int64(n),
-                              C.c_void_p(_ptr(item_meta, torch.int64)), k, C.c_int64(item_offset),
-                              C.c_void_p(idx.data_ptr()), C.c_void_p(score.data_ptr()),
-                              C.c_void_p(over.data_ptr()), C.c_void_p(ws.data_ptr()),
-                              C.c_size_t(nbytes), _stream()))
+    key = (cache_key, n, k, int(model.item.emb or 0), nbytes, str(dev))
+    reuse = cache is not None and cache.ws is not None and cache.key == key and cache_key is not None
+    if reuse:
+        ws = cache.ws
+    else:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        if cache is not None:
+            cache.ws, cache.key = ws, key
+    _check(L.trs_predict_topk_reuse(C.byref(model), C.c_void_p(_ptr(users, torch.int64)), C.c_int64(n),
+                                    C.c_void_p(_ptr(item_meta, torch.int64)), k, C.c_int64(item_offset),
+                                    C.c_void_p(idx.data_ptr()), C.c_void_p(score.data_ptr()),
+                                    C.c_void_p(over.data_ptr()), C.c_void_p(ws.data_ptr()),
+                                    C.c_size_t(nbytes), int(reuse), _stream()))
     return idx, score, over
 
 

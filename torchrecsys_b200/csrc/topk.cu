@@ -655,6 +655,14 @@ extern "C" int trs_predict_topk(const trs_model* model, const int64_t* users, in
                                 const int64_t* item_meta, int k, int64_t item_offset, int64_t* out_idx,
                                 float* out_score, int32_t* overflow, void* workspace, size_t workspace_bytes,
                                 trs_stream_t stream) {
+    return trs_predict_topk_reuse(model, users, n_query, item_meta, k, item_offset, out_idx, out_score, overflow,
+                                  workspace, workspace_bytes, 0, stream);
+}
+
+extern "C" int trs_predict_topk_reuse(const trs_model* model, const int64_t* users, int64_t n_query,
+                                      const int64_t* item_meta, int k, int64_t item_offset, int64_t* out_idx,
+                                      float* out_score, int32_t* overflow, void* workspace, size_t workspace_bytes,
+                                      int items_prepared, trs_stream_t stream) {
     int rc = check_topk(model, n_query, k);
     if (rc) return rc;
     if (n_query == 0) return TRS_OK;
@@ -668,13 +676,16 @@ extern "C" int trs_predict_topk(const trs_model* model, const int64_t* users, in
     cudaStream_t st = (cudaStream_t)stream;
     char* W = (char*)workspace;
     const int64_t n_items = model->item.n_rows;
-    TRS_CUDA(cudaMemsetAsync(W + L.vmax2, 0, 256, st));
+    // items_prepared: the workspace still holds the bf16 item operand (and its max norm) of a previous call with the
+    // same item tables and n_query -- the 1.4 GB re-cast of an unchanged 5M x 128 table is skipped
+    if (!items_prepared) TRS_CUDA(cudaMemsetAsync(W + L.vmax2, 0, 256, st));
     TRS_CUDA(cudaMemsetAsync(overflow, 0, (size_t)n_query * 4, st));
     TRS_CUDA(cudaMemsetAsync(W + L.Ub, 0, (size_t)L.user_tiles * TK_BM * L.Kp * 2, st));
     {
         long long blocks = (n_items + 7) / 8;
         const long long cap = (long long)device_props().sm_count * 32;
-        if (model->dim % 4 == 0)
+        if (items_prepared) {
+        } else if (model->dim % 4 == 0)
             topk_prep_items_kernel<true><<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(
                 *model, item_meta, n_items, L.Kp, (bf16*)(W + L.Vb), (unsigned*)(W + L.vmax2));
         else
@@ -705,8 +716,11 @@ extern "C" int trs_predict_topk(const trs_model* model, const int64_t* users, in
     g.overflow = overflow;
     g.progress = (int*)(W + L.progress);
     {
-        const char* w_env = getenv("TRS_TOPK_WINDOW");  // tuning hook
-        g.sync_window = (w_env && atoi(w_env) > 0) ? atoi(w_env) : TK_SYNC_WINDOW;
+        g.sync_window = TK_SYNC_WINDOW;
+#ifdef TRS_DEBUG
+        const char* w_env = getenv("TRS_TOPK_WINDOW");  // tuning hook of debug builds only
+        if (w_env && atoi(w_env) > 0) g.sync_window = atoi(w_env);
+#endif
     }
     TRS_CUDA(cudaMemsetAsync(g.progress, 0xff, (size_t)L.splits * L.user_tiles * 4, st));
     CUtensorMap tv;

@@ -134,6 +134,12 @@ def advance_steps(optimizer, params, b: OptBinding, n_steps: int) -> None:
     b.step0 += n_steps
 
 
+def _bump_version(net) -> None:
+    """The kernels write parameters through raw pointers: torch's tensor version counters do not see it.  Caches keyed
+    on "the model has not changed" (the prepared item operand of predict) read this counter as well."""
+    net._trs_version = getattr(net, "_trs_version", 0) + 1
+
+
 PLAN_FUSED_MAX = 16384  # plan.cu FS_MAX: lookups per (step, id space) the single-CTA plan kernel holds
 
 
@@ -209,6 +215,7 @@ class EpochRunner(_Chunked):
         _lib.train_steps(model, epoch, optim, plan, ws, 0, n_steps, loss)
         self.launches += 1 + plan_launches(model, batch_size, n_steps)
         advance_steps(self.optimizer, self.params, b, n_steps)
+        _bump_version(self.net)
         return loss
 
 
@@ -262,6 +269,7 @@ class MlpEpochRunner(_Chunked):
         if self.net.use_batch_norm:
             for m in self.net.bns:
                 m.num_batches_tracked += 2 * n_steps  # two forward passes per step (model.py:173-183)
+        _bump_version(self.net)
         return loss
 
 
@@ -301,6 +309,7 @@ class AutogradEpochRunner(_Chunked):
                 losses.append(loss.detach())
         finally:
             self.net._trusted_ids = False
+        _bump_version(self.net)
         return torch.stack(losses) if losses else torch.empty(0, device=samples["user"].device)
 
 

@@ -298,7 +298,12 @@ class TorchRecSys(torch.nn.Module):
         if self.use_metadata and "item_meta" not in self._dev_cache:
             self._device_split("train_data")
         meta = self._dev_cache.get("item_meta") if self.use_metadata else None
-        idx, _, over = _lib.predict_topk(self.net.abi_model(), users, top_k, meta)
+        if not hasattr(self, "_topk_cache"):
+            self._topk_cache = _lib.TopkCache()
+        params = list(self.net.parameters())  # unchanged tables -> the prepared bf16 item operand is reused
+        version = (getattr(self.net, "_trs_version", 0),) + tuple((p._version, p.data_ptr()) for p in params)
+        idx, _, over = _lib.predict_topk(self.net.abi_model(), users, top_k, meta, cache=self._topk_cache,
+                                         cache_key=version)
         idx = idx.cpu()
         for q in torch.nonzero(over.cpu()).flatten().tolist():
             idx[q] = self._predict_exact(int(users[q]), top_k, dev)
