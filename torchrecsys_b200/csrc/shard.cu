@@ -107,6 +107,8 @@ route_scatter_kernel(const int64_t* __restrict__ a, const int64_t* __restrict__ 
                      uint32_t world, uint32_t rank, const uint32_t* __restrict__ tile_cnt, int tiles,
                      uint32_t* __restrict__ out_key, uint32_t* __restrict__ out_val, uint32_t* __restrict__ samp,
                      uint32_t* __restrict__ own_cnt, uint32_t* __restrict__ samp_cnt) {
+    // user space (samp != NULL): the rank's samples ARE its owned user lookups in slot order, so the pair's value is
+    // the sample's index in the rank's list (its slot is samp[index]); item space: the value is the slot itself
     __shared__ uint32_t s_w[RT_THREADS / 32];
     __shared__ uint32_t s_base;
     const int64_t step = blockIdx.y;
@@ -165,7 +167,7 @@ route_scatter_kernel(const int64_t* __restrict__ a, const int64_t* __restrict__ 
         if (own) {
             const uint32_t p = run + wbase + __popc(m & ((1u << lane) - 1u));
             out_key[seg + p] = id / world;
-            out_val[seg + p] = (uint32_t)j;
+            out_val[seg + p] = samp ? p : (uint32_t)j;
             if (samp) samp[s0 + p] = (uint32_t)j;
         }
         run += tot;
@@ -222,13 +224,14 @@ dirty_mark_kernel(const int64_t* __restrict__ pos, const int64_t* __restrict__ n
 }
 // A user row looked up exactly ONCE in a step has no other reader or writer in that step (every sample of a user runs
 // on the user row's owner): its sample updates it in phase A.  Marks the sample (SAMP_USER_SINGLE) and the sorted
-// pair (VAL_DONE_IN_A: phase B skips it).  Runs after dirty_mark_kernel (which rewrites the samp entries).
+// pair (VAL_DONE_IN_A: phase B skips it).  Runs after dirty_mark_kernel (which rewrites the samp entries); every
+// sample has one user lookup, so no two threads touch the same entry.
 __global__ void __launch_bounds__(RT_THREADS)
 single_mark_kernel(const uint32_t* __restrict__ ukey, uint32_t* __restrict__ uval, const uint32_t* __restrict__ own_cnt,
-                   const uint32_t* __restrict__ samp_cnt, uint32_t* __restrict__ samp, int B) {
+                   uint32_t* __restrict__ samp, int B) {
     const int64_t step = blockIdx.y;
     const int64_t s0 = step * (int64_t)B;
-    const int n = (int)own_cnt[2 * step], nS = (int)samp_cnt[step];
+    const int n = (int)own_cnt[2 * step];
     const uint32_t* K = ukey + s0;
     uint32_t* P = uval + s0;
     uint32_t* S = samp + s0;
@@ -238,16 +241,9 @@ single_mark_kernel(const uint32_t* __restrict__ ukey, uint32_t* __restrict__ uva
         if (k >= n) continue;
         const uint32_t key = K[k];
         if ((k > 0 && K[k - 1] == key) || (k + 1 < n && K[k + 1] == key)) continue;
-        const uint32_t b = P[k];
-        int lo = 0, hi = nS;  // the rank's samples are its owned user lookups in slot order: find slot b
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if ((S[mid] & 0x07FFFFFFu) < b) lo = mid + 1; else hi = mid;
-        }
-        if (lo < nS && (S[lo] & 0x07FFFFFFu) == b) {
-            atomicOr(S + lo, 1u << 27);
-            P[k] = b | (1u << 31);
-        }
+        const uint32_t idx = P[k];  // the sample's index in the rank's list
+        S[idx] |= 1u << 27;
+        P[k] = idx | (1u << 31);
     }
 }
 
@@ -610,9 +606,11 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                 const uint32_t prev = k > 0 ? __ldg(K + k - 1) : ~key;
                 const uint32_t next = k + 1 < n ? __ldg(K + k + 1) : ~key;
                 const uint32_t v = __ldg(P + k);
+                const bool head = prev != key && !(v & VAL_DONE_IN_A);
+                // item space: the value is the staging slot; user space: the sample's index in the rank's list
+                const uint32_t sl = it ? v : (head ? (__ldg(C.samp + lo_ + (v & 0x1FFFFFFFu)) & SAMP_POS) : 0u);
                 Dd.key[z] = key;
-                Dd.sf[z] = (v & 0x1FFFFFFFu) |
-                           ((prev != key && !(v & VAL_DONE_IN_A) ? 1u : 0u) | (next == key ? 2u : 0u) | (it ? 4u : 0u)) << 29;
+                Dd.sf[z] = (sl & 0x1FFFFFFFu) | ((head ? 1u : 0u) | (next == key ? 2u : 0u) | (it ? 4u : 0u)) << 29;
             }
         }
     };
@@ -956,7 +954,8 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                     const uint32_t* P = it ? C.ival + 2 * lo : C.uval + lo;
                     const float* stage = it ? my_stage_i : my_stage_u;
                     for (int q = k + 1; q < n && __ldg(K + q) == key; ++q) {
-                        const uint32_t j = __ldg(P + q) & 0x1FFFFFFFu;
+                        const uint32_t v = __ldg(P + q) & 0x1FFFFFFFu;
+                        const uint32_t j = it ? v : (__ldg(C.samp + lo + v) & SAMP_POS);
                         const Row<4, IT> r = ld_row(stage + (size_t)j * dim);
 #pragma unroll
                         for (int a = 0; a < IT; ++a)
@@ -1158,8 +1157,8 @@ extern "C" int trs_shard_plan_build(const trs_shard* sh, const trs_epoch* ep, vo
         dirty_bitmap_kernel<<<g2, RT_THREADS, 0, st>>>(ep->pos, ep->neg, n, ep->batch, bitmap, lb, exact);
         dim3 g1((unsigned)(((int64_t)ep->batch + RT_TILE - 1) / RT_TILE), (unsigned)steps);
         dirty_mark_kernel<<<g1, RT_THREADS, 0, st>>>(ep->pos, ep->neg, n, ep->batch, bitmap, lb, exact, samp_cnt, samp);
-        single_mark_kernel<<<g1, RT_THREADS, 0, st>>>((const uint32_t*)(P + L.ukey), (uint32_t*)(P + L.uval), own_cnt, samp_cnt,
-                                                     samp, ep->batch);
+        single_mark_kernel<<<g1, RT_THREADS, 0, st>>>((const uint32_t*)(P + L.ukey), (uint32_t*)(P + L.uval), own_cnt, samp,
+                                                     ep->batch);
     }
     TRS_CUDA(cudaGetLastError());
     return TRS_OK;
