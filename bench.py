@@ -822,7 +822,10 @@ def sharded_bench(args, wl, name):
                 "d2h_bytes_per_step": 4,
                 "note": "each rank's user+positive ids from pinned host memory; negatives are drawn on the device"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": traffic_of(name, K)[0],
+                     "traffic_source": "static: profiles/shard_r2.md (ncu --set full of a 1-rank launch on 4M x 1M tables; "
+                                       "per step, times K; not measured by this run)",
                      "kernel": "trs::shard_train_kernel (one persistent launch per rank, K steps)",
                      "kernel_ms_per_step": kernel_ms / K, "plan_ms_per_step": plan_ms / K,
                      "algorithmic_bytes_per_step": alg / K / G,
