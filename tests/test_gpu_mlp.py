@@ -261,3 +261,59 @@ def test_mlp_without_batch_norm_and_ragged_last_batch(dev):
     got = {k: v.detach().cpu() for k, v in net.state_dict().items()}
     problems = _compare_deltas(got, emu, init, list(init), 3e-2, 0.995, "[emul 3 steps]")
     assert not problems, "\n".join(problems)
+
+
+def test_gradient_error_is_measured_against_the_references_own_amp_run(dev):
+    """The bound on the bf16 tower's gradients is not self-defined: the reference's OWN reduced-precision path --
+    ``use_amp=True``: ``torch.cuda.amp.autocast`` (fp16) + GradScaler, model.py:86-88, 192-195 -- run here on the same
+    B200, the same C3-shaped tower, initial weights and batch, deviates from its fp32 gradients by a measurable
+    relative error; so does a bf16 autocast of it (what the reference's AMP would be with the dtype north_star names).
+    The fused tcgen05 step must be as close to the fp32 gradients as that bf16 autocast run, tensor by tensor (factor
+    1.5 for the different accumulation order), and never further than 2x the fp16 run's error where fp16 does not
+    overflow."""
+    from oracle import torch_port as TP
+    from torchrecsys_b200.collaborative.mlp import MLP
+    from torchrecsys_b200.engine import MlpEpochRunner
+    torch.manual_seed(7)
+    U, I, D, B, hidden = 5000, 3000, 64, 4096, [512, 256, 128]
+    ref = TP.MLPPort(U, I, [], D, hidden=hidden, batch_norm=True)
+    with torch.no_grad():
+        ref.user.weight.normal_(0, 0.5)
+        ref.item.weight.normal_(0, 0.5)
+    init = {k: v.clone() for k, v in ref.state_dict().items()}
+    rng = np.random.default_rng(11)
+    batch = {k: torch.from_numpy(rng.integers(0, n, B)).to(dev) for k, n in (("user", U), ("pos", I), ("neg", I))}
+
+    def port_grads(autocast_dtype):
+        net = TP.MLPPort(U, I, [], D, hidden=hidden, batch_norm=True)
+        net.load_state_dict(init)
+        net = net.to(dev).train()
+        ctx = torch.autocast("cuda", dtype=autocast_dtype) if autocast_dtype is not None else torch.autocast("cuda", enabled=False)
+        with ctx:
+            loss = TP.hinge(net(batch["user"], batch["pos"]), net(batch["user"], batch["neg"]))
+        scale = 1024.0 if autocast_dtype is torch.float16 else 1.0     # GradScaler: scale, backward, unscale
+        (loss * scale).backward()
+        return {k: (p.grad.to_dense() if p.grad.is_sparse else p.grad).float() / scale
+                for k, p in net.named_parameters()}
+
+    g32, g16, gbf = port_grads(None), port_grads(torch.float16), port_grads(torch.bfloat16)
+    net = MLP(U, I, {}, D, use_metadata=False, use_batch_norm=True, hidden_layers=hidden, use_cuda=True)
+    net.load_state_dict(init)
+    net = net.to(dev).train()
+    MlpEpochRunner(net, torch.optim.SGD(net.parameters(), lr=1.0)).run(batch, B)
+    ours = {k: (init[k].to(dev) - p.detach()) for k, p in net.named_parameters()}      # lr = 1: the delta IS the gradient
+
+    def rel(a, b):
+        return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+    lines, bad = [], []
+    for k in g32:
+        if _skip(k):
+            continue
+        e16, ebf, eus = rel(g16[k], g32[k]), rel(gbf[k], g32[k]), rel(ours[k], g32[k])
+        cos = float(torch.nn.functional.cosine_similarity(ours[k].flatten(), g32[k].flatten(), dim=0))
+        lines.append(f"{k:28s} rel. error vs fp32: reference fp16 AMP {e16:.3e}, bf16 autocast {ebf:.3e}, this kernel {eus:.3e} (cos {cos:.5f})")
+        if not (eus <= 1.5 * ebf + 1e-4):
+            bad.append(f"{k}: {eus:.3e} > 1.5 x bf16 autocast {ebf:.3e}")
+    print("\n".join(lines))
+    assert not bad, "\n".join(bad + lines)

@@ -336,12 +336,28 @@ def merge_topk_lists(scores: torch.Tensor, idx: torch.Tensor, k: int, merge: Opt
 def sharded_predict_topk(local_topk: Callable, users: torch.Tensor, k: int, n_items: int, group=None,
                          merge: Optional[Callable] = None):
     """``local_topk(users, k, item_offset) -> (idx [Q, k] global ids, score [Q, k])`` on this rank's item block;
-    returns the merged global top-k on every rank."""
+    returns the merged global top-k on every rank.
+
+    The per-rank candidate lists are exchanged with an all_to_all that sends each user's candidates to ONE merger rank
+    (users split evenly over the ranks): every rank merges Q / G users x G lists instead of all Q users -- G times less
+    merge work and traffic than all-gathering the lists -- and the merged [Q / G, k] results are all-gathered."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, _ = item_block(n_items, rank, world)
     idx, score = local_topk(users, k, lo)
-    all_idx = [torch.empty_like(idx) for _ in range(world)]
-    all_score = [torch.empty_like(score) for _ in range(world)]
-    dist.all_gather(all_idx, idx.contiguous(), group=group)
-    dist.all_gather(all_score, score.contiguous(), group=group)
-    return merge_topk_lists(torch.stack(all_score), torch.stack(all_idx), k, merge)
+    Q = idx.shape[0]
+    if world == 1:
+        return merge_topk_lists(score[None], idx[None], k, merge)
+    Qc = -(-Q // world)                                   # users per merger rank
+    pad = Qc * world - Q
+    if pad:
+        idx = torch.cat([idx, idx.new_full((pad, k), -1)])
+        score = torch.cat([score, score.new_full((pad, k), float("-inf"))])
+    got_idx, got_score = torch.empty_like(idx), torch.empty_like(score)   # [world, Qc, k]: every rank's list for MY users
+    dist.all_to_all_single(got_idx, idx.contiguous(), group=group)
+    dist.all_to_all_single(got_score, score.contiguous(), group=group)
+    m_idx, m_score = merge_topk_lists(got_score.view(world, Qc, k), got_idx.view(world, Qc, k), k, merge)
+    out_idx = torch.empty((world * Qc, k), dtype=m_idx.dtype, device=m_idx.device)
+    out_score = torch.empty((world * Qc, k), dtype=m_score.dtype, device=m_score.device)
+    dist.all_gather_into_tensor(out_idx, m_idx.contiguous(), group=group)
+    dist.all_gather_into_tensor(out_score, m_score.contiguous(), group=group)
+    return out_idx[:Q], out_score[:Q]
