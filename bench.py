@@ -88,6 +88,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the other_workloads sub-results")
     ap.add_argument("--shard-it", type=int, default=0, help="tuning: 16-byte chunks per lane of the sharded kernel (1 or 2)")
+    ap.add_argument("--shard-overlap", type=int, default=None, help="tuning: force the early first pass of phase A on (1) / off (0)")
     ap.add_argument("--emulate-world", type=int, default=0,
                     help="c4_linear on ONE GPU: host a group of this many ranks in one launch (structure check, no NVLink)")
     return ap.parse_args()
@@ -691,6 +692,8 @@ def sharded_bench(args, wl, name):
         dist.init_process_group("nccl", device_id=dev)
     if args.shard_it:
         _lib.lib().trs_debug_shard_chunks_per_lane(args.shard_it)
+    if args.shard_overlap is not None:
+        _lib.lib().trs_debug_shard_overlap(args.shard_overlap)
     G = emu or world                       # ranks of the group
     K, W, B = args.steps, max(args.warmup, 3), wl["batch"]
     Bg = B * G
@@ -717,10 +720,8 @@ def sharded_bench(args, wl, name):
             part = src[rank][lo_step:lo_step + n_steps]
             if not part.is_cuda:
                 part = part.to(dev, non_blocking=True)
-            allr = torch.empty((world,) + tuple(part.shape), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(allr, part)
-        else:
-            allr = torch.stack([src[q][lo_step:lo_step + n_steps].to(dev, non_blocking=True) for q in mine])
+            return tuple(tr.gather_epoch(part))     # ids cross NVLink as int32, widened while reordering
+        allr = torch.stack([src[q][lo_step:lo_step + n_steps].to(dev, non_blocking=True) for q in mine])
         cols = allr.permute(2, 1, 0, 3).contiguous()     # [G, steps, 2, B] -> [2, steps, G, B]
         return cols[0].view(-1), cols[1].view(-1)
 

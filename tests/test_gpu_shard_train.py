@@ -113,6 +113,61 @@ def test_group_sizes_agree_bit_for_bit_and_split_launches_equal_one(dev):
                 assert torch.equal(sd[k], ref[k]), (world, k)
 
 
+def _plan_words(plan, n, B):
+    """The plan's arrays (uint32 words at 256-byte aligned offsets, csrc/shard.cu: shard_plan_layout)."""
+    words = plan.cpu().numpy().view(np.uint32)
+    steps, off, out = -(-n // B), 0, {}
+    for name, cnt in (("samp_cnt", steps), ("own_cnt", 2 * steps), ("samp", n), ("ukey", n), ("uval", n),
+                      ("ikey", 2 * n), ("ival", 2 * n)):
+        out[name] = words[off // 4: off // 4 + cnt]
+        off += (cnt * 4 + 255) // 256 * 256
+    return out
+
+
+@pytest.mark.parametrize("world,n_items", [(1, 3000), (4, 3000), (2, 3_000_000), (8, 3_000_000)])
+def test_plan_flags_never_miss_a_row_the_previous_step_updates(dev, world, n_items):
+    """Phase A runs a sample BEFORE the previous step's owners are done unless the plan flags one of its three rows as
+    updated by that step (bits 28 / 30 / 31 of its samp entry).  A flag may be set needlessly (the filter is hashed for
+    large tables), it must never be missing; bit 27 marks the users with one lookup in the step."""
+    from torchrecsys_b200 import _lib
+    U, B, steps = 4000, 1024, 5
+    rng = np.random.default_rng(world + n_items)
+    n = B * steps - 100                                   # a ragged last step
+    user, pos, neg = _skewed(rng, U, n), _skewed(rng, n_items, n), rng.integers(0, n_items, n)
+    ids = [_to(dev, a) for a in (user, pos, neg)]          # make_epoch takes addresses: the tensors must stay alive
+    epoch = _lib.make_epoch(*ids, None, None, B)
+    needless = total = 0
+    for rank in range(world):
+        sh = _lib.Shard()
+        sh.rank, sh.world, sh.dim, sh.n_users, sh.n_items = rank, world, 64, U, n_items
+        P = _plan_words(_lib.shard_plan_build(sh, epoch, dev), n, B)
+        torch.cuda.synchronize()
+        for s in range(steps):
+            lo, hi = s * B, min(n, (s + 1) * B)
+            mine = np.flatnonzero(user[lo:hi] % world == rank)
+            cnt = int(P["samp_cnt"][s])
+            ent = P["samp"][lo:lo + cnt]
+            b = (ent & 0x07FFFFFF).astype(np.int64)
+            np.testing.assert_array_equal(b, mine)        # the rank's samples, in batch order
+            u, p_, n_ = user[lo + b], pos[lo + b], neg[lo + b]
+            uniq, c = np.unique(user[lo:hi], return_counts=True)
+            single = np.isin(u, uniq[c == 1])
+            np.testing.assert_array_equal((ent >> 27) & 1, single.astype(np.uint32))
+            f_user, f_pos, f_neg = (((ent >> k) & 1).astype(bool) for k in (28, 30, 31))
+            if s == 0:                                     # nothing is known about the step before the plan
+                assert f_user.all() and f_pos.all() and f_neg.all()
+                continue
+            plo = lo - B
+            items_prev = np.union1d(pos[plo:lo], neg[plo:lo])
+            up, cp = np.unique(user[plo:lo], return_counts=True)
+            must = (np.isin(u, up[cp > 1]), np.isin(p_, items_prev), np.isin(n_, items_prev))
+            for flag, need in zip((f_user, f_pos, f_neg), must):
+                assert not (need & ~flag).any()
+                needless += int((flag & ~need).sum())
+                total += len(flag)
+    assert needless <= 0.04 * total
+
+
 def test_sharded_training_equals_the_fused_single_gpu_kernel(dev):
     """Same ids, same init: the peer-mapped path and trs_train_steps (one GPU, whole tables) end in the same
     tables up to the order of duplicate sums."""

@@ -95,6 +95,14 @@ def _worker(rank, port, q):
         ok = all(torch.equal(sd[k], full[k]) for k in full)
         want = torch.tensor([1.0, 2.0]).repeat(I)[:I, None].expand(I, D)
         ok = ok and torch.equal(osd["item.weight"]["sum"], want)
+        # the loaders' id exchange: [steps, columns, B] per rank -> global columns, step-major, rank-major in a step
+        steps, B = 3, 5
+        g = torch.Generator().manual_seed(7)
+        parts = [torch.randint(0, U, (steps, 2, B), generator=g) for _ in range(2)]
+        cols = tr.gather_epoch(parts[rank])
+        both = torch.stack(parts)                                  # [world, steps, 2, B]
+        for j in range(2):
+            ok = ok and cols[j].dtype == torch.int64 and torch.equal(cols[j], both[:, :, j].permute(1, 0, 2).reshape(-1))
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

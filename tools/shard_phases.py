@@ -1,5 +1,6 @@
 """Phase timeline of trs::shard_train_kernel on the C4 shape: per step, when the slowest / average CTA finishes
-phase A, leaves barrier 1, finishes phase B, leaves barrier 2 (globaltimer stamps, trs_debug_shard_trace).
+phase A, leaves barrier 1, finishes phase B, and how long the next phase A waits for the step's end (globaltimer stamps,
+trs_debug_shard_trace).
     python tools/shard_phases.py [--world 1] [--users 50000000] [--items 5000000] [--steps 12] [--it 2]   # one GPU
     torchrun --nproc-per-node N tools/shard_phases.py ...                                                 # real peers"""
 import argparse
@@ -24,6 +25,7 @@ ap.add_argument("--dim", type=int, default=128)
 ap.add_argument("--batch", type=int, default=16384)
 ap.add_argument("--steps", type=int, default=12)
 ap.add_argument("--it", type=int, default=1)
+ap.add_argument("--overlap", type=int, default=-1)
 a = ap.parse_args()
 real = "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1
 local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -35,6 +37,7 @@ if real:
     rank, a.world = dist.get_rank(), dist.get_world_size()
 L = _lib.lib()
 L.trs_debug_shard_chunks_per_lane(a.it)
+L.trs_debug_shard_overlap(a.overlap)
 G, B = a.world, a.batch * a.world
 tr = ShardedLinearTrainer(a.users, a.items, a.dim, global_batch=B, device=dev, emulate_world=None if real else G)
 rng = np.random.default_rng(0)
@@ -53,7 +56,7 @@ tr.train_epoch(*ids, B)
 torch.cuda.synchronize()
 L.trs_debug_shard_trace(None)
 t = buf.cpu().numpy().reshape(n_local, a.steps, cpr, 8).astype(np.float64) / 1e3  # us
-names = ["A done", "bar1 left", "B done", "bar2 left"]
+names = ["A done", "bar1 left", "B done", "arrived at end"]
 if rank == 0:
     print(f"world {G}{' (real peers)' if real else ' (one GPU)'}, {cpr} CTAs per rank, batch/rank {a.batch}, "
           f"{a.it} chunks per lane; microseconds from the step's earliest start")
@@ -69,15 +72,12 @@ for r in range(n_local):
     d = t[r, 2:, :, :]
     step = np.mean(d[1:, :, 0].min(axis=1) - d[:-1, :, 0].min(axis=1))
     who = rank if real else r
-    if False:   # (the split of phase B was removed) | B(user rows) | cross-rank barrier | B(item rows) | cross-rank barrier
-        print(f"rank {who} mean over steps (avg CTA): A {np.mean(d[:, :, 1] - d[:, :, 0]):.1f}  "
-              f"rank-bar {np.mean(d[:, :, 5] - d[:, :, 1]):.1f}  B-user {np.mean(d[:, :, 6] - d[:, :, 5]):.1f}  "
-              f"x-bar1 {np.mean(d[:, :, 2] - d[:, :, 6]):.1f}  B-item {np.mean(d[:, :, 3] - d[:, :, 2]):.1f}  "
-              f"x-bar2 {np.mean(d[:, :, 4] - d[:, :, 3]):.1f}  step {step:.1f}", flush=True)
-    else:
-        print(f"rank {who} mean over steps (avg CTA): A {np.mean(d[:, :, 1] - d[:, :, 0]):.1f}  "
-              f"bar1 {np.mean(d[:, :, 2] - d[:, :, 1]):.1f}  B {np.mean(d[:, :, 3] - d[:, :, 2]):.1f}  "
-              f"bar2 {np.mean(d[:, :, 4] - d[:, :, 3]):.1f}  step {step:.1f}", flush=True)
+    # the wait for the barrier that ends step s sits inside step s + 1's phase A, after its first pass (stamps 5, 6)
+    wait = np.mean(d[1:, :, 6] - d[1:, :, 5])
+    print(f"rank {who} mean over steps (avg CTA): A {np.mean(d[:, :, 1] - d[:, :, 0]):.1f} (first pass "
+          f"{np.mean(d[1:, :, 5] - d[1:, :, 0]):.1f}, wait for the previous step's end {wait:.1f})  "
+          f"bar1 {np.mean(d[:, :, 2] - d[:, :, 1]):.1f}  B {np.mean(d[:, :, 3] - d[:, :, 2]):.1f}  "
+          f"arrive {np.mean(d[:, :, 4] - d[:, :, 3]):.1f}  step {step:.1f}", flush=True)
 if real:
     dist.barrier()
     tr.close()

@@ -180,8 +180,27 @@ route_scatter_kernel(const int64_t* __restrict__ a, const int64_t* __restrict__ 
 // row step s does not touch.  Per step a hashed bitmap of the item rows looked up anywhere in the GLOBAL batch;
 // a sample's lookup whose bit is set in the previous step's bitmap is flagged in its samp entry (bit 30: positive,
 // bit 31: negative) and read after the step barrier instead.  False positives only cost latency.
-__device__ __forceinline__ uint32_t dirty_hash(uint32_t id, int log2_bits, bool exact) {
-    return exact ? id : (id * 2654435761u) >> (32 - log2_bits);
+// A blocked Bloom filter: the hashed id picks ONE 32-bit word and two bits in it (one atomicOr to set, one load to
+// test); at 16 bits per lookup that is ~2 % false positives against 6 % for a single bit.
+struct DirtyProbe { uint32_t word, mask; };
+__device__ __forceinline__ DirtyProbe dirty_probe(uint32_t id, int log2_bits, bool exact) {
+    DirtyProbe p;
+    if (exact) {
+        p.word = id >> 5;
+        p.mask = 1u << (id & 31u);
+    } else {
+        uint32_t h = id * 0x9E3779B1u;
+        h ^= h >> 15;
+        h *= 0x85EBCA77u;
+        h ^= h >> 13;
+        p.word = h >> (37 - log2_bits);
+        p.mask = (1u << (h & 31u)) | (1u << ((h >> 5) & 31u));
+    }
+    return p;
+}
+__device__ __forceinline__ bool dirty_test(const uint32_t* bm, uint32_t id, int log2_bits, bool exact) {
+    const DirtyProbe p = dirty_probe(id, log2_bits, exact);
+    return (bm[p.word] & p.mask) == p.mask;
 }
 __global__ void __launch_bounds__(RT_THREADS)
 dirty_bitmap_kernel(const int64_t* __restrict__ pos, const int64_t* __restrict__ neg, int64_t n_samples, int B,
@@ -194,8 +213,8 @@ dirty_bitmap_kernel(const int64_t* __restrict__ pos, const int64_t* __restrict__
     for (int r = 0; r < RT_ROWS; ++r) {
         const int j = blockIdx.x * RT_TILE + r * RT_THREADS + threadIdx.x;
         if (j < 2 * Bs) {
-            const uint32_t h = dirty_hash(route_id(pos, neg, s0, Bs, j), log2_bits, exact);
-            atomicOr(bm + (h >> 5), 1u << (h & 31u));
+            const DirtyProbe p = dirty_probe(route_id(pos, neg, s0, Bs, j), log2_bits, exact);
+            atomicOr(bm + p.word, p.mask);
         }
     }
 }
@@ -214,9 +233,8 @@ dirty_mark_kernel(const int64_t* __restrict__ pos, const int64_t* __restrict__ n
             const uint32_t b = samp[s0 + k];
             uint32_t fl = 3u;  // the first step of a plan: nothing is known about the step before it
             if (bm) {
-                const uint32_t hp = dirty_hash((uint32_t)pos[s0 + b], log2_bits, exact);
-                const uint32_t hn = dirty_hash((uint32_t)neg[s0 + b], log2_bits, exact);
-                fl = ((bm[hp >> 5] >> (hp & 31u)) & 1u) | (((bm[hn >> 5] >> (hn & 31u)) & 1u) << 1);
+                fl = (dirty_test(bm, (uint32_t)pos[s0 + b], log2_bits, exact) ? 1u : 0u) |
+                     (dirty_test(bm, (uint32_t)neg[s0 + b], log2_bits, exact) ? 2u : 0u);
             }
             samp[s0 + k] = b | (fl << 30);
         }
@@ -226,28 +244,101 @@ dirty_mark_kernel(const int64_t* __restrict__ pos, const int64_t* __restrict__ n
 // on the user row's owner): its sample updates it in phase A.  Marks the sample (SAMP_USER_SINGLE) and the sorted
 // pair (VAL_DONE_IN_A: phase B skips it).  Runs after dirty_mark_kernel (which rewrites the samp entries); every
 // sample has one user lookup, so no two threads touch the same entry.
+// The user rows that are NOT single in a step are updated by its phase B: their (local) rows go into a hashed bitmap
+// per step, and user_dirty_mark_kernel flags the next step's samples that read one of them (SAMP_DIRTY_USER).
 __global__ void __launch_bounds__(RT_THREADS)
 single_mark_kernel(const uint32_t* __restrict__ ukey, uint32_t* __restrict__ uval, const uint32_t* __restrict__ own_cnt,
-                   uint32_t* __restrict__ samp, int B) {
+                   uint32_t* __restrict__ samp, int B, uint32_t* __restrict__ ubitmap, int log2_bits) {
     const int64_t step = blockIdx.y;
     const int64_t s0 = step * (int64_t)B;
     const int n = (int)own_cnt[2 * step];
     const uint32_t* K = ukey + s0;
     uint32_t* P = uval + s0;
     uint32_t* S = samp + s0;
+    uint32_t* bm = ubitmap + ((size_t)step << (log2_bits - 5));
 #pragma unroll
     for (int r = 0; r < RT_ROWS; ++r) {
         const int k = blockIdx.x * RT_TILE + r * RT_THREADS + threadIdx.x;
         if (k >= n) continue;
         const uint32_t key = K[k];
-        if ((k > 0 && K[k - 1] == key) || (k + 1 < n && K[k + 1] == key)) continue;
+        if ((k > 0 && K[k - 1] == key) || (k + 1 < n && K[k + 1] == key)) {
+            const DirtyProbe p = dirty_probe(key, log2_bits, false);
+            atomicOr(bm + p.word, p.mask);
+            continue;
+        }
         const uint32_t idx = P[k];  // the sample's index in the rank's list
         S[idx] |= 1u << 27;
         P[k] = idx | (1u << 31);
     }
 }
 
-// bits of a step's bitmap: 16x the item lookups of a step (6 % false positives), or one bit per item if that is less
+// Phase B then only needs the user pairs that phase A does NOT finish: drop the marked ones (stable, in place, one CTA
+// per step; a chunk is read completely before any of it is overwritten, and pairs only move towards the front).
+__global__ void __launch_bounds__(1024)
+user_compact_kernel(uint32_t* __restrict__ ukey, uint32_t* __restrict__ uval, uint32_t* __restrict__ own_cnt, int B) {
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_run;
+    const int64_t step = blockIdx.x;
+    const int n = (int)own_cnt[2 * step];
+    uint32_t* K = ukey + step * (int64_t)B;
+    uint32_t* P = uval + step * (int64_t)B;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int k = base + (int)threadIdx.x;
+        uint32_t key = 0, val = 0;
+        bool keep = false;
+        if (k < n) {
+            key = K[k];
+            val = P[k];
+            keep = (val & (1u << 31)) == 0u;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_w[warp] = __popc(m);
+        __syncthreads();
+        uint32_t wbase = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 32; ++w) {
+            const uint32_t c = s_w[w];
+            if (w < warp) wbase += c;
+            tot += c;
+        }
+        const uint32_t run = s_run;
+        __syncthreads();
+        if (keep) {
+            const uint32_t p = run + wbase + __popc(m & ((1u << lane) - 1u));
+            K[p] = key;
+            P[p] = val;
+        }
+        if (threadIdx.x == 0) s_run = run + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) own_cnt[2 * step] = s_run;
+}
+
+__global__ void __launch_bounds__(RT_THREADS)
+user_dirty_mark_kernel(const int64_t* __restrict__ user, int B, uint32_t world, const uint32_t* __restrict__ ubitmap,
+                       int log2_bits, const uint32_t* __restrict__ samp_cnt, uint32_t* __restrict__ samp) {
+    const int64_t step = blockIdx.y;
+    const int64_t s0 = step * (int64_t)B;
+    const int n = (int)samp_cnt[step];
+    const uint32_t* bm = step > 0 ? ubitmap + ((size_t)(step - 1) << (log2_bits - 5)) : nullptr;
+#pragma unroll
+    for (int r = 0; r < RT_ROWS; ++r) {
+        const int k = blockIdx.x * RT_TILE + r * RT_THREADS + threadIdx.x;
+        if (k < n) {
+            const uint32_t e = samp[s0 + k];
+            bool d = true;  // the first step of a plan: nothing is known about the step before it
+            if (bm) {
+                d = dirty_test(bm, (uint32_t)user[s0 + (e & 0x07FFFFFFu)] / world, log2_bits, false);
+            }
+            if (d) samp[s0 + k] = e | (1u << 28);
+        }
+    }
+}
+
+// bits of a step's bitmap: 16x the item lookups of a step (~2 % false positives, see dirty_probe), or one bit per item if that is less
 static int dirty_log2_bits(const trs_epoch* ep, int64_t n_items, bool* exact) {
     int lb = 10;
     while (((int64_t)1 << lb) < 32ll * ep->batch && lb < 28) ++lb;
@@ -263,8 +354,10 @@ static int dirty_log2_bits(const trs_epoch* ep, int64_t n_items, bool* exact) {
 // samp entries of the plan: position of the sample in its step | flags
 constexpr uint32_t SAMP_POS = 0x07FFFFFFu;          // position b in the global step (global batch < 2^27)
 constexpr uint32_t SAMP_USER_SINGLE = 1u << 27;     // the user row is looked up once in the step: phase A updates it
+constexpr uint32_t SAMP_DIRTY_USER = 1u << 28;      // the user row had several lookups in the previous step (phase B updates it)
 constexpr uint32_t SAMP_DIRTY_POS = 1u << 30;       // the positive / negative item row is updated by the previous step
 constexpr uint32_t SAMP_DIRTY_NEG = 1u << 31;
+constexpr uint32_t SAMP_DIRTY_ANY = SAMP_DIRTY_USER | SAMP_DIRTY_POS | SAMP_DIRTY_NEG;
 constexpr uint32_t VAL_DONE_IN_A = 1u << 31;        // sorted (row, slot) pair whose row phase A updates itself
 
 // Thread-private 16-byte shared-memory slots per chunk a lane owns: phase A keeps SB samples x {user, positive,
@@ -273,12 +366,14 @@ template <int IT>
 constexpr int shard_slots() { return 12; }
 
 struct ShardCtx {  // everything one (virtual) rank needs; copied to shared memory by each of its CTAs
-    int rank, world, dim, pad;
+    int rank, world, dim;
+    int overlap;  // phase A starts on the samples the previous step does not touch before that step's end barrier
     trs_table user[TRS_MAX_RANKS];
     trs_table item[TRS_MAX_RANKS];
     float* stage_u[TRS_MAX_RANKS];  // [B, dim]   gradient rows of the user lookups, slot = sample position in the step
     float* stage_i[TRS_MAX_RANKS];  // [2B, dim]  positives then negatives
     float* stage_b[TRS_MAX_RANKS];  // [2B]       d item_bias
+    size_t stage_par;               // floats between the two copies of the staging buffers (step parity)
     unsigned* sync[TRS_MAX_RANKS];
     const uint32_t *samp_cnt, *own_cnt, *samp, *ukey, *uval, *ikey, *ival;
     float* loss_part;  // [n_steps][cta_per_rank]
@@ -385,24 +480,28 @@ __device__ __forceinline__ void spin_until(const ShardCtx& C, const unsigned* cn
     }
 }
 
-// every CTA of every rank; e = number of this barrier over the life of the group (1-based)
-__device__ __forceinline__ void cross_rank_barrier(const ShardCtx& C, unsigned e, unsigned cpr,
-                                                   unsigned long long timeout_ns, bool remote_writes) {
+// every CTA of every rank.  Split in two so that work which does not depend on the peers can sit between: arrive (one
+// release fence + a relaxed add to every rank's counter) ...
+__device__ __forceinline__ void cross_arrive(const ShardCtx& C, bool remote_writes) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned* mine = C.sync[C.rank] + 64;
-        const unsigned target = e * cpr * (unsigned)C.world;
         if (C.world > 1) {
             if (remote_writes) fence_acq_rel_sys(); else fence_acq_rel_gpu();
             for (int q = 0; q < C.world; ++q) red_relaxed_sys(C.sync[q] + 64);
-            spin_until(C, mine, target, true, timeout_ns);
-            (void)ld_acquire_sys(mine);
         } else {
             fence_acq_rel_gpu();
-            red_relaxed_gpu(mine);
-            spin_until(C, mine, target, false, timeout_ns);
-            (void)ld_acquire_gpu(mine);
+            red_relaxed_gpu(C.sync[C.rank] + 64);
         }
+    }
+}
+// ... and wait until every CTA of every rank has arrived at barrier number e (1-based over the life of the group)
+__device__ __forceinline__ void cross_wait(const ShardCtx& C, unsigned e, unsigned cpr, unsigned long long timeout_ns) {
+    if (threadIdx.x == 0) {
+        const unsigned* mine = C.sync[C.rank] + 64;
+        const unsigned target = e * cpr * (unsigned)C.world;
+        const bool sys = C.world > 1;
+        spin_until(C, mine, target, sys, timeout_ns);
+        if (sys) (void)ld_acquire_sys(mine); else (void)ld_acquire_gpu(mine);
     }
     __syncthreads();
 }
@@ -551,10 +650,11 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
     const trs_table& tU = C.user[me];
     const trs_table& tI = C.item[me];
     const bool item_lin = tI.lin != nullptr;
-    float* const my_stage_u = C.stage_u[me];
-    float* const my_stage_i = C.stage_i[me];
-    const float* const my_stage_b = C.stage_b[me];
-    unsigned bar_no = 0;   // cross-rank barriers passed in this launch
+    // the staging buffers exist twice (step parity): a rank may already store step s+1's gradient rows into a peer
+    // that is still reading step s's
+    unsigned bar_no = 0;   // cross-rank barriers arrived at in this launch
+    bool wait_pending = false;  // arrived at the barrier that ends a step, not yet waited for it (see phase A)
+    const bool overlap = C.overlap != 0;
 
     // ---- records of a phase-A round: lane gl fetches samples gl, gl + G, ... of the round and splits their ids
     //      into (owner, local row) ONCE (plan + epoch data: immutable, so the NEXT step's first rounds are fetched
@@ -636,6 +736,10 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
         const int nU = (int)C.own_cnt[2 * s], nI = (int)C.own_cnt[2 * s + 1];
         const bool more = si + 1 < n_steps;
         const int nS_next = more ? (int)C.samp_cnt[s + 1] : 0;
+        const size_t po = (s & 1) ? C.stage_par : 0;
+        float* const my_stage_u = C.stage_u[me] + po;
+        float* const my_stage_i = C.stage_i[me] + po;
+        const float* const my_stage_b = C.stage_b[me] + po;
         unsigned long long* tr = C.trace ? C.trace + ((size_t)si * cpr + c) * 8 : nullptr;
         if (tr && threadIdx.x == 0) tr[0] = shard_now_ns();
 
@@ -651,7 +755,11 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)line * 128));
             }
         }
-        float hsum = 0.f;
+        // hinge terms: one per regular-round sample, added up in sample order afterwards (the order in which the two
+        // passes visit them depends on plan flags, the loss must not), then the overflow rounds' in visiting order
+        float hreg[2 * SBA], hover = 0.f;
+#pragma unroll
+        for (int i = 0; i < 2 * SBA; ++i) hreg[i] = 0.f;
         if (PFS && pf_live) {  // rows fetched while the previous step's owners were updating: landed?
             while (!sh_mbar_try_wait(my_bar, pf_parity)) {
             }
@@ -662,17 +770,17 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
         // the global batch reads or writes it, and its owner is this rank) is updated right here from its state rows
         // in slots su_slot + 1 / + 2; every other gradient row goes to its owner's staging buffer.
         auto process = [&](bool valid, uint32_t bf, uint32_t q, uint32_t lu, const Row<4, IT>& xu, const Row<4, IT>& xp,
-                           const Row<4, IT>& xn, float bu, float bip, float bin, int su_slot) {
+                           const Row<4, IT>& xn, float bu, float bip, float bin, int su_slot, float& hinge) {
             const float sp = (group_sum<G>(row_dot_partial(xu, xp)) + bu) + bip;
             const float sn = (group_sum<G>(row_dot_partial(xu, xn)) + bu) + bin;
             const float h = __fadd_rn(__fsub_rn(sn, sp), 1.0f);
             const float g = (h >= 0.f) ? invB : 0.f;
             if (!valid) return;
-            if (gl == 0) hsum += fmaxf(h, 0.f);
+            hinge = fmaxf(h, 0.f);
             const uint32_t b = bf & SAMP_POS;
             const uint32_t qu = q & 15u, qp = (q >> 4) & 15u, qn = (q >> 8) & 15u;
-            float* dp = C.stage_i[qp] + (size_t)b * dim;
-            float* dn = C.stage_i[qn] + (size_t)(Bs + b) * dim;
+            float* dp = C.stage_i[qp] + po + (size_t)b * dim;
+            float* dn = C.stage_i[qn] + po + (size_t)(Bs + b) * dim;
             Row<4, IT> gu;
 #pragma unroll
             for (int a = 0; a < IT; ++a) {
@@ -691,8 +799,8 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                 }
             }
             if (gl == 0) {
-                C.stage_b[qp][b] = -g;
-                C.stage_b[qn][Bs + b] = g;
+                (C.stage_b[qp] + po)[b] = -g;
+                (C.stage_b[qn] + po)[Bs + b] = g;
             }
             if (bf & SAMP_USER_SINGLE) {
                 Row<4, IT> p = xu, s0, s1;
@@ -702,7 +810,7 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                 if (KIND == TRS_OPT_SPARSE_ADAM) s1 = slot_row(su_slot + 2);
                 sh_update_store<KIND, IT>(C.user[qu], (size_t)lu * dim, nch, gl, G, opt, scale, p, s0, s1, gu);
             } else {
-                float* du = C.stage_u[qu] + (size_t)b * dim;
+                float* du = C.stage_u[qu] + po + (size_t)b * dim;
 #pragma unroll
                 for (int a = 0; a < IT; ++a) {
                     const int ch = gl + a * G;
@@ -710,10 +818,25 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                 }
             }
         };
-        for (int rnd = 0;; ++rnd) {
+        // Two passes over the regular rounds.  Pass 0 takes the samples none of whose three rows the previous step's
+        // owners update (plan flags) BEFORE waiting for the barrier that ends the previous step: their rows are final,
+        // and their gradient rows go to the other copy of the staging buffers.  Then the wait, then pass 1 (the flagged
+        // samples) and the overflow rounds.
+        for (int rr = 0;; ++rr) {
+            if (wait_pending && (rr == NREG || !overlap)) {  // every warp of the CTA comes through here once per step
+                if (tr && threadIdx.x == 0) tr[5] = shard_now_ns();
+                cross_wait(C, sync_epoch + bar_no, (unsigned)cpr, timeout_ns);
+                wait_pending = false;
+                if (tr && threadIdx.x == 0) tr[6] = shard_now_ns();
+            }
+            const bool late = rr >= NREG;            // pass 1 / overflow
+            const int rnd = late ? rr - NREG : rr;
             const int o_lo = round_lo(rnd), n_r = round_n(rnd);
             const int k0 = gfirst - goff + o_lo * gstride;
-            if (k0 >= nS) break;  // warp-uniform
+            if (k0 >= nS) {  // warp-uniform
+                if (late) break;
+                continue;
+            }
             const int kb = k0 + goff;
             Rec cur;
             if (rnd < NPR) {
@@ -725,6 +848,13 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
             }
             if (rnd < NREG) {
                 // ---- regular round: item rows in the region, user row + state in slots 3i .. 3i + 2 ----
+                if (late) {  // nothing flagged in the warp's groups: pass 0 did the whole round
+                    if (!overlap) continue;
+                    bool d = false;
+#pragma unroll
+                    for (int z = 0; z < RPL; ++z) d = d || (cur.b[z] != 0xFFFFFFFFu && (cur.b[z] & SAMP_DIRTY_ANY) != 0u);
+                    if (!__any_sync(0xffffffffu, d)) continue;
+                }
                 float bias_r[SBA];  // lane t < 3 holds the width-1 companion of lookup t (user, positive, negative)
 #pragma unroll
                 for (int i = 0; i < SBA; ++i) {
@@ -734,7 +864,7 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                     const uint32_t lp = __shfl_sync(0xffffffffu, cur.lp[i / G], i % G, G);
                     const uint32_t ln = __shfl_sync(0xffffffffu, cur.ln[i / G], i % G, G);
                     bias_r[i] = 0.f;
-                    if (i < n_r && bf != 0xFFFFFFFFu) {
+                    if (i < n_r && bf != 0xFFFFFFFFu && (overlap ? ((bf & SAMP_DIRTY_ANY) != 0u) == late : !late)) {
                         const int ord = o_lo + i;
                         const bool have_p = pf_live && !(bf & SAMP_DIRTY_POS), have_n = pf_live && !(bf & SAMP_DIRTY_NEG);
                         const trs_table& TU = C.user[q & 15u];
@@ -766,7 +896,8 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                     const uint32_t bf = __shfl_sync(0xffffffffu, cur.b[i / G], i % G, G);
                     const uint32_t q = __shfl_sync(0xffffffffu, cur.q[i / G], i % G, G);
                     const uint32_t lu = __shfl_sync(0xffffffffu, cur.lu[i / G], i % G, G);
-                    const bool valid = i < n_r && bf != 0xFFFFFFFFu;
+                    const bool valid = i < n_r && bf != 0xFFFFFFFFu &&
+                                       (overlap ? ((bf & SAMP_DIRTY_ANY) != 0u) == late : !late);
                     Row<4, IT> xu, xp, xn;
                     if (valid) {
                         xu = slot_row(i * 3 + 0);
@@ -779,7 +910,11 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                     const float bu = __shfl_sync(0xffffffffu, bias_r[i], 0, G);
                     const float bip = __shfl_sync(0xffffffffu, bias_r[i], 1, G);
                     const float bin = __shfl_sync(0xffffffffu, bias_r[i], 2, G);
-                    process(valid, bf, q, lu, xu, xp, xn, bu, bip, bin, i * 3);
+                    float hv = 0.f;
+                    process(valid, bf, q, lu, xu, xp, xn, bu, bip, bin, i * 3, hv);
+                    if (valid) {
+                        if (rnd == 0) hreg[i] = hv; else hreg[SBA + i] = hv;
+                    }
                 }
             } else {
                 // ---- overflow round: two samples, all five rows in the thread-private slots 5i .. 5i + 4 ----
@@ -830,7 +965,9 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                     const float bu = __shfl_sync(0xffffffffu, bias_r[i], 0, G);
                     const float bip = __shfl_sync(0xffffffffu, bias_r[i], 1, G);
                     const float bin = __shfl_sync(0xffffffffu, bias_r[i], 2, G);
-                    process(valid, bf, q, lu, xu, xp, xn, bu, bip, bin, i * 5);
+                    float hv = 0.f;
+                    process(valid, bf, q, lu, xu, xp, xn, bu, bip, bin, i * 5, hv);
+                    hover += hv;
                 }
             }
         }
@@ -846,7 +983,10 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
         Desc dB;
         fetch_descs(dB, lo, nU, nI, gfirst, nP);
 
-        hsum = warp_sum(hsum);
+        float hsum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 2 * SBA; ++i) hsum += hreg[i];
+        hsum = warp_sum(gl == 0 ? hsum + hover : 0.f);
         if ((threadIdx.x & 31) == 0) s_loss[threadIdx.x >> 5] = hsum;
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -857,7 +997,8 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
             if (tr) tr[1] = shard_now_ns();
         }
         ++bar_no;
-        cross_rank_barrier(C, sync_epoch + bar_no, (unsigned)cpr, timeout_ns, true);
+        cross_arrive(C, true);
+        cross_wait(C, sync_epoch + bar_no, (unsigned)cpr, timeout_ns);
         if (tr && threadIdx.x == 0) tr[2] = shard_now_ns();
 
         // ------------------------------ phase B ------------------------------------------
@@ -979,10 +1120,13 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
             __syncthreads();
             if (threadIdx.x == 0) tr[3] = shard_now_ns();
         }
+        // the owners' updates are done: arrive, and wait inside the next step's phase A (after its pass 0)
         ++bar_no;
-        cross_rank_barrier(C, sync_epoch + bar_no, (unsigned)cpr, timeout_ns, false);
+        cross_arrive(C, false);
+        wait_pending = true;
         if (tr && threadIdx.x == 0) tr[4] = shard_now_ns();
     }
+    if (wait_pending) cross_wait(C, sync_epoch + bar_no, (unsigned)cpr, timeout_ns);
 
     // per-step hinge sums of this rank, CTAs added in a fixed order
     if (c == 0) {
@@ -1043,6 +1187,7 @@ static cudaError_t launch_shard(const ShardCtx* ctx0, const ShardCtx* ctxs, int 
 // chunks per lane halve the per-row bookkeeping instructions; measured equal at one rank, trs_debug_shard_chunks_per_lane.)
 static int g_shard_prefer_it = 1;
 static unsigned long long* g_shard_trace = nullptr;
+static int g_shard_overlap = -1;
 
 static bool pick_shard_shape(int dim, int* G, int* IT) {
     if (dim <= 0 || dim % 4 || dim > 512) return false;
@@ -1074,7 +1219,7 @@ using namespace trs;
 
 extern "C" size_t trs_shard_stage_bytes(int dim, int global_batch) {
     if (dim <= 0 || global_batch <= 0) return 0;
-    return shard_stage_layout(dim, global_batch).total;
+    return 2 * shard_stage_layout(dim, global_batch).total;   // two copies, used by even / odd steps
 }
 
 extern "C" size_t trs_shard_plan_bytes(const trs_epoch* ep) {
@@ -1090,13 +1235,13 @@ static int route_tiles(const trs_epoch* ep) { return (int)((2ll * ep->batch + RT
 static size_t dirty_bitmap_bytes(const trs_epoch* ep) {
     bool exact;
     const int lb = dirty_log2_bits(ep, (int64_t)1 << 40, &exact);  // the hashed size: an exact bitmap is never larger
-    return (((size_t)n_steps_of(ep) << lb) / 8 + 255) / 256 * 256;
+    return (((size_t)n_steps_of(ep) << lb) / 8 + 255) / 256 * 256;   // one for the item rows, one for the user rows
 }
 
 extern "C" size_t trs_shard_plan_tmp_bytes(const trs_epoch* ep) {
     if (!ep || ep->batch <= 0) return 0;
     const size_t tile_cnt = ((size_t)n_steps_of(ep) * route_tiles(ep) * sizeof(uint32_t) + 255) / 256 * 256;
-    return shard_tmp_pairs_bytes(ep) + tile_cnt + (hist_bytes(ep) + 255) / 256 * 256 + dirty_bitmap_bytes(ep);
+    return shard_tmp_pairs_bytes(ep) + tile_cnt + (hist_bytes(ep) + 255) / 256 * 256 + 2 * dirty_bitmap_bytes(ep);
 }
 
 extern "C" int trs_shard_plan_build(const trs_shard* sh, const trs_epoch* ep, void* plan, size_t plan_bytes,
@@ -1157,8 +1302,15 @@ extern "C" int trs_shard_plan_build(const trs_shard* sh, const trs_epoch* ep, vo
         dirty_bitmap_kernel<<<g2, RT_THREADS, 0, st>>>(ep->pos, ep->neg, n, ep->batch, bitmap, lb, exact);
         dim3 g1((unsigned)(((int64_t)ep->batch + RT_TILE - 1) / RT_TILE), (unsigned)steps);
         dirty_mark_kernel<<<g1, RT_THREADS, 0, st>>>(ep->pos, ep->neg, n, ep->batch, bitmap, lb, exact, samp_cnt, samp);
+        bool ex_unused;
+        const int lbu = dirty_log2_bits(ep, (int64_t)1 << 40, &ex_unused);  // always hashed
+        uint32_t* ubitmap = (uint32_t*)((char*)bitmap + dirty_bitmap_bytes(ep));
+        TRS_CUDA(cudaMemsetAsync(ubitmap, 0, ((size_t)steps << lbu) / 8, st));
         single_mark_kernel<<<g1, RT_THREADS, 0, st>>>((const uint32_t*)(P + L.ukey), (uint32_t*)(P + L.uval), own_cnt, samp,
-                                                     ep->batch);
+                                                     ep->batch, ubitmap, lbu);
+        user_dirty_mark_kernel<<<g1, RT_THREADS, 0, st>>>(ep->user, ep->batch, W, ubitmap, lbu, samp_cnt, samp);
+        user_compact_kernel<<<(unsigned)steps, 1024, 0, st>>>((uint32_t*)(P + L.ukey), (uint32_t*)(P + L.uval), own_cnt,
+                                                             ep->batch);
     }
     TRS_CUDA(cudaGetLastError());
     return TRS_OK;
@@ -1211,6 +1363,9 @@ extern "C" int trs_shard_train_steps(const trs_shard* shards, int n_local, const
         c.rank = sh.rank;
         c.world = sh.world;
         c.dim = sh.dim;
+        c.stage_par = SL.total / sizeof(float);
+        // on one GPU the barrier that ends a step costs about what the second pass does; across GPUs it is worth hiding
+        c.overlap = g_shard_overlap < 0 ? (sh.world > 1 ? 1 : 0) : g_shard_overlap;
         for (int q = 0; q < sh.world; ++q) {
             TRS_REQUIRE(sh.user[q].emb && sh.item[q].emb && sh.stage[q] && sh.sync[q], "rank %d: peer %d is not mapped",
                         sh.rank, q);
@@ -1280,6 +1435,8 @@ extern "C" void trs_debug_shard_chunks_per_lane(int it) { g_shard_prefer_it = it
 // debug hook: device buffer of n_local * n_steps * CTAs-per-rank * 8 uint64 that the next launches fill with phase
 // time stamps (tools/shard_phases.py); NULL switches it off
 extern "C" void trs_debug_shard_trace(void* buf) { g_shard_trace = (unsigned long long*)buf; }
+// tuning hook (results do not depend on it): 1 / 0 forces the early first pass of phase A on / off, -1 = automatic
+extern "C" void trs_debug_shard_overlap(int mode) { g_shard_overlap = mode < 0 ? -1 : (mode ? 1 : 0); }
 
 
 // ---- CUDA IPC plumbing ---------------------------------------------------------------------------------------

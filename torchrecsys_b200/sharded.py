@@ -235,23 +235,38 @@ class ShardedLinearTrainer:
     def plan_launches(self) -> int:
         """CUDA kernels one trs_shard_plan_build launches for one rank (bench.py's gpu_launches)."""
         passes = lambda rows: max(1, -(-max(1, (max(rows, 2) - 1).bit_length()) // 8))
-        return 2 * (2 + passes(-(-self.n_users // self.world)) + passes(-(-self.n_items // self.world)))
+        # per id space: count + scatter + 2 per radix pass; then the item filter, the three flag kernels, the compaction
+        return 2 * (2 + passes(-(-self.n_users // self.world)) + passes(-(-self.n_items // self.world))) + 5
 
     def check_status(self) -> None:
         if int(self.status.item()) != 0:
             raise RuntimeError("row-sharded training: a peer rank did not reach a step barrier within "
                                f"{self.timeout_ms} ms; the tables are in an undefined state")
 
+    def gather_epoch(self, local: torch.Tensor) -> List[torch.Tensor]:
+        """The loaders' exchange: ``local`` is THIS rank's [n_steps, k, B] int64 ids (k columns: user, positive, ...);
+        returns the k columns of the GLOBAL epoch, int64 [n_steps * world * B], step-major and rank-major inside a
+        step -- what ``train_epoch`` takes.  One NCCL all-gather; ids travel as int32 when every table has fewer
+        than 2^31 rows (half the NVLink bytes) and are widened by the same pass that reorders them."""
+        n_steps, k, B = local.shape
+        W = self.world
+        if len(self.local_ranks) == W:
+            if W != 1:
+                raise ValueError("gather_epoch with emulated ranks: stack the ranks' outputs yourself")
+            return [local[:, j].reshape(-1) for j in range(k)]
+        narrow = max(self.n_users, self.n_items) < 2 ** 31
+        part = local.to(torch.int32) if narrow else local.contiguous()
+        allr = torch.empty((W * n_steps, k, B), dtype=part.dtype, device=part.device)
+        dist.all_gather_into_tensor(allr, part, group=self.group)
+        cols = torch.empty((k, n_steps, W, B), dtype=torch.int64, device=part.device)
+        cols.copy_(allr.view(W, n_steps, k, B).permute(2, 1, 0, 3))
+        return [cols[j].view(-1) for j in range(k)]
+
     def train_step(self, user: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
         """Convenience: THIS rank's samples of one step; the global batch is the all-gather over ranks (rank-major).
         Returns the global batch-mean hinge (device scalar)."""
         if len(self.local_ranks) < self.world:
-            parts = []
-            for t in (user, pos, neg):
-                out = torch.empty(self.world * t.shape[0], dtype=t.dtype, device=t.device)
-                dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
-                parts.append(out)
-            user, pos, neg = parts
+            user, pos, neg = self.gather_epoch(torch.stack([user, pos, neg]).unsqueeze(0))
         return self.train_epoch(user, pos, neg, user.shape[0])[0]
 
     # ---- checkpoints: the reference's single-process layout (state_dict keys of collaborative/linear.py) --------
