@@ -426,6 +426,28 @@ __device__ __forceinline__ void sh_cp_async_wait(int n) {
     }
 }
 
+// L2 policies: a staged gradient row is written in phase A and read once in phase B of the same step -- it should
+// stay in L2 in between (evict_last) and leave right after (evict_first), while the table rows stream through.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_v4_hint(float* p, const float4& v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void sh_cp_async16_hint(void* smem, const void* gmem, uint64_t pol) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "l"(pol) : "memory");
+}
+
 template <int IT>
 constexpr int shard_threads() { return IT <= 2 ? 512 : 256; }
 template <int IT>
@@ -647,6 +669,14 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
         }
     };
     auto ld_row = [&](const float* base) { return load_row_cg<4, G, IT>(base, nch, gl); };
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
+    auto copy_row_drop = [&](int j, const float* base) {  // a row nobody reads again: out of L2 first
+#pragma unroll
+        for (int a = 0; a < IT; ++a) {
+            const int ch = gl + a * G;
+            if (ch < nch) sh_cp_async16_hint(slot(j, a), base + (size_t)ch * 4, pol_drop);
+        }
+    };
     const trs_table& tU = C.user[me];
     const trs_table& tI = C.item[me];
     const bool item_lin = tI.lin != nullptr;
@@ -794,8 +824,8 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                         gp[e] = -g * xu.c[a][e];
                         gn[e] = g * xu.c[a][e];
                     }
-                    gp.st(dp + (size_t)ch * 4);
-                    gn.st(dn + (size_t)ch * 4);
+                    st_v4_hint(dp + (size_t)ch * 4, gp.v, pol_keep);
+                    st_v4_hint(dn + (size_t)ch * 4, gn.v, pol_keep);
                 }
             }
             if (gl == 0) {
@@ -814,7 +844,7 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
 #pragma unroll
                 for (int a = 0; a < IT; ++a) {
                     const int ch = gl + a * G;
-                    if (ch < nch) gu.c[a].st(du + (size_t)ch * 4);
+                    if (ch < nch) st_v4_hint(du + (size_t)ch * 4, gu.c[a].v, pol_keep);
                 }
             }
         };
@@ -1053,7 +1083,7 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                     const bool it = (sf >> 31) != 0u;
                     const trs_table& t = it ? tI : tU;
                     const size_t roff = (size_t)key * dim;
-                    copy_row(i * 4 + 0, (it ? my_stage_i : my_stage_u) + (size_t)sl * dim);
+                    copy_row_drop(i * 4 + 0, (it ? my_stage_i : my_stage_u) + (size_t)sl * dim);
                     copy_row(i * 4 + 1, t.emb + roff);
                     if (KIND != TRS_OPT_SGD) copy_row(i * 4 + 2, t.emb_s0 + roff);
                     if (KIND == TRS_OPT_SPARSE_ADAM) copy_row(i * 4 + 3, t.emb_s1 + roff);
