@@ -340,9 +340,12 @@ typedef struct {
 /* `epoch` below is always the GLOBAL epoch: the ids of every rank's samples in loader order, identical on all
  * ranks (an all-gather of the loader output, once per epoch); epoch->batch is the GLOBAL batch.  Metadata is not
  * supported on this path. */
+/* Two copies of [global_batch, dim] + [2 * global_batch, dim] + [2 * global_batch] floats: even and odd steps use
+ * different copies, so a rank may store step s+1's gradient rows into a peer that is still reading step s's. */
 size_t trs_shard_stage_bytes(int dim, int global_batch);
-/* The rank's plan: which samples it runs (user % world == rank) and, per step, the (local row, slot) pairs of the
- * lookups it OWNS, stably sorted by row. */
+/* The rank's plan: which samples it runs (user % world == rank) with their flags (user row looked up once in the
+ * step; user / positive / negative row updated by the step before), and, per step, the (local row, slot) pairs of
+ * the lookups it OWNS and still has to apply after the samples ran, stably sorted by row. */
 size_t trs_shard_plan_bytes(const trs_epoch* epoch);
 size_t trs_shard_plan_tmp_bytes(const trs_epoch* epoch);
 int trs_shard_plan_build(const trs_shard* shard, const trs_epoch* epoch, void* plan, size_t plan_bytes, void* tmp,
