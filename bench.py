@@ -766,7 +766,17 @@ def sharded_bench(args, wl, name):
     rep_h = {q: t[W:].repeat(r_in, 1, 1).pin_memory() for q, t in ids_h.items()}
     loss_host = torch.empty(r_in * K, dtype=torch.float32).pin_memory()
     resident_block = lambda: block(rep_d, 0, r_in * K)[0]
-    e2e_block = lambda: block(rep_h, 0, r_in * K, loss_host=loss_host)[0]
+    if emu:
+        e2e_block = lambda: block(rep_h, 0, r_in * K, loss_host=loss_host)[0]
+    else:   # the trainer's own host-fed epoch: chunks copied on a side stream while the previous chunk trains
+        def draw(gp, first):
+            neg, _ = _lib.philox_negatives(1234, seen[0] + first, gp, wl["n_items"])
+            return neg
+
+        def e2e_block():
+            loss = tr.train_epoch_host(rep_h[rank], draw, loss_host)
+            seen[0] += r_in * K * Bg
+            return loss
     resident_block()
     e2e_block()
     launches0 = tr.launches
@@ -821,7 +831,9 @@ def sharded_bench(args, wl, name):
                                 "memorises its few samples, the hinge goes to 0; the work per step does not change"},
         "e2e": {"value": R * K * Bg / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": 16 * B,
                 "d2h_bytes_per_step": 4,
-                "note": "each rank's user+positive ids from pinned host memory; negatives are drawn on the device"},
+                "note": "ShardedLinearTrainer.train_epoch_host: each rank's user+positive ids from pinned host memory in "
+                        "chunks of >= 64 steps, chunk i+1 copied on a side stream while chunk i trains; negatives are "
+                        "drawn on the device; per-step losses back to pinned host memory"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": traffic_of(name, K)[0],

@@ -168,6 +168,34 @@ def test_plan_flags_never_miss_a_row_the_previous_step_updates(dev, world, n_ite
     assert needless <= 0.04 * total
 
 
+def test_host_fed_epoch_in_chunks_equals_one_resident_epoch(dev):
+    """train_epoch_host copies chunk i+1 on a side stream while chunk i trains: same tables, same losses as one
+    train_epoch over device-resident ids (chunks are split launches; negatives keyed by the global sample index)."""
+    from torchrecsys_b200 import _lib
+    U, I, D, B, steps = 3000, 800, 32, 256, 150
+    rng = np.random.default_rng(11)
+    params = _full_params(rng, U, I, D)
+    ids_host = torch.from_numpy(np.stack([_skewed(rng, U, steps * B).reshape(steps, B),
+                                          _skewed(rng, I, steps * B).reshape(steps, B)], 1)).pin_memory()
+    draw = lambda pos, first: _lib.philox_negatives(99, first, pos, I)[0]
+    a = _trainer(dev, 1, U, I, D, B, "adagrad", 0.05, params)
+    loss_host = torch.zeros(steps).pin_memory()
+    la = a.train_epoch_host(ids_host, draw, loss_host, chunk_steps=64)      # 8 + 32 + 64 + 46 steps
+    a.check_status()
+    b = _trainer(dev, 1, U, I, D, B, "adagrad", 0.05, params)
+    user, pos = ids_host[:, 0].reshape(-1).to(dev), ids_host[:, 1].reshape(-1).to(dev)
+    lb = b.train_epoch(user, pos, draw(pos, 0), B)
+    torch.cuda.synchronize()
+    assert torch.equal(la, lb) and torch.equal(loss_host, lb.cpu())
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    # and again: the buffers of the first call are reused
+    la2 = a.train_epoch_host(ids_host, draw, None, chunk_steps=64)
+    lb2 = b.train_epoch(user, pos, draw(pos, 0), B)
+    assert torch.equal(la2, lb2)
+
+
 def test_sharded_training_equals_the_fused_single_gpu_kernel(dev):
     """Same ids, same init: the peer-mapped path and trs_train_steps (one GPU, whole tables) end in the same
     tables up to the order of duplicate sums."""

@@ -130,6 +130,7 @@ class ShardedLinearTrainer:
         self._plan_tmp = None
         self._ws = None
         self._inv_counts = None
+        self._h2d = None          # train_epoch_host: two device id buffers + the copy stream
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.launches = 0
 
@@ -180,7 +181,7 @@ class ShardedLinearTrainer:
 
     # ---- training -----------------------------------------------------------------------------------
     def train_epoch(self, user: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, global_batch: Optional[int] = None,
-                    check: bool = True, timing: bool = False) -> torch.Tensor:
+                    check: bool = True, timing: bool = False, _scales: Optional[torch.Tensor] = None) -> torch.Tensor:
         """user / pos / neg: the GLOBAL epoch (int64 device tensors, identical on every rank), step s = samples
         [s*B, (s+1)*B) with B = ``global_batch``.  Returns the per-step batch-mean hinge losses (device, [n_steps]) --
         what ``loss.item()`` returns at model.py:200.  ``check=False`` skips the status read-back (no host sync);
@@ -203,8 +204,7 @@ class ShardedLinearTrainer:
             ev[0].record()
         for r, sh in zip(self.local_ranks, shards):
             self._plans[r] = _lib.shard_plan_build(sh, epoch, self.device, self._plans.get(r), self._plan_tmp)
-        scales = torch.tensor(step_scales(self.binding, n_steps), dtype=torch.float64).to(torch.float32)
-        scales = scales.to(self.device, non_blocking=True)
+        scales = self._step_scales(n_steps) if _scales is None else _scales
         b = self.binding
         optim = _lib.Optim(b.kind, 0, b.beta1, b.beta2, b.eps, scales.data_ptr())
         sums = torch.zeros((len(self.local_ranks), n_steps), dtype=torch.float32, device=self.device)
@@ -224,13 +224,20 @@ class ShardedLinearTrainer:
         if len(self.local_ranks) < self.world:
             dist.all_reduce(total, group=self.group)
         key = (n, B)
-        if self._inv_counts is None or self._inv_counts[0] != key:  # 1 / samples per step, cached per epoch shape
-            c = torch.full((n_steps,), 1.0 / B, dtype=torch.float64)
-            c[-1] = 1.0 / (n - (n_steps - 1) * B)
-            self._inv_counts = (key, c.to(torch.float32).to(self.device))
+        if self._inv_counts is None or self._inv_counts[0] != key:  # 1 / samples per step, cached per epoch shape;
+            last = 1.0 / (n - (n_steps - 1) * B)                    # built on the device: no copy that would wait
+            c = torch.full((n_steps,), 1.0 / B, dtype=torch.float64, device=self.device)   # for the running kernel
+            if n % B:
+                c[-1:].fill_(last)                                  # (c[-1] = x would go through a host tensor)
+            self._inv_counts = (key, c.to(torch.float32))
         if check:
             self.check_status()
         return total * self._inv_counts[1]
+
+    def _step_scales(self, n_steps: int) -> torch.Tensor:
+        """trs_optim.step_scale of the next ``n_steps`` steps on the device (python doubles, as torch computes them)."""
+        scales = torch.tensor(step_scales(self.binding, n_steps), dtype=torch.float64).to(torch.float32)
+        return scales.pin_memory().to(self.device, non_blocking=True)   # pinned: the copy does not wait for the stream
 
     def plan_launches(self) -> int:
         """CUDA kernels one trs_shard_plan_build launches for one rank (bench.py's gpu_launches)."""
@@ -261,6 +268,66 @@ class ShardedLinearTrainer:
         cols = torch.empty((k, n_steps, W, B), dtype=torch.int64, device=part.device)
         cols.copy_(allr.view(W, n_steps, k, B).permute(2, 1, 0, 3))
         return [cols[j].view(-1) for j in range(k)]
+
+    def train_epoch_host(self, ids_host: torch.Tensor, draw_negatives: Callable[[torch.Tensor, int], torch.Tensor],
+                         loss_host: Optional[torch.Tensor] = None, chunk_steps: Optional[int] = None) -> torch.Tensor:
+        """A whole epoch straight from THIS rank's loader output in (pinned) host memory: ``ids_host`` is int64
+        [n_steps, 2, B] (user, positive).  The epoch is cut into chunks of steps; chunk i+1 is copied to the device on a
+        side stream (two device buffers) while chunk i trains, so the host-to-device copy leaves the critical path
+        (chunks grow from ``chunk_steps / 32`` to ``chunk_steps`` steps: only the short first copy is exposed).
+        Per chunk: id exchange (``gather_epoch``), ``draw_negatives(positives_global, first_global_sample)`` (device
+        int64, e.g. the Philox kernel), plan, one persistent launch.  Per-step losses are also copied into ``loss_host``
+        (pinned) if given.  No host synchronisation; call ``check_status()`` afterwards."""
+        if self.bases is None:
+            raise RuntimeError("torchrecsys_b200 has no CPU fallback: row-sharded training needs CUDA devices")
+        if len(self.local_ranks) != 1:
+            raise ValueError("train_epoch_host drives one rank per process")
+        n_steps, k, B = ids_host.shape
+        if n_steps == 0:
+            return torch.empty(0, device=self.device)
+        Bg = B * self.world
+        chunk_steps = int(chunk_steps or min(2048, max(64, -(-n_steps // 2))))
+        bounds, size = [0], max(8, chunk_steps // 32)   # a short first chunk (its copy is the one nothing hides), then
+        while bounds[-1] < n_steps:                      # four times longer each time (a copy takes < 10 % of the time
+            bounds.append(min(n_steps, bounds[-1] + size))   # its steps take to train) up to chunk_steps: every chunk
+            size = min(chunk_steps, 4 * size)                # costs ~0.2 ms of plan / launch ramp on the device
+        if self._h2d is None or tuple(self._h2d[0][0].shape) != (chunk_steps, k, B):
+            self._h2d = ([torch.empty((chunk_steps, k, B), dtype=torch.int64, device=self.device) for _ in range(2)],
+                         torch.cuda.Stream(self.device))
+        bufs, side = self._h2d
+        main = torch.cuda.current_stream(self.device)
+        side.wait_stream(main)                    # the buffers may still feed the previous call's last chunks
+        free = [None, None]                       # event: the chunk that last used the buffer has trained
+
+        def stage(i):
+            lo, hi = bounds[i], bounds[i + 1]
+            buf = bufs[i % 2][:hi - lo]
+            with torch.cuda.stream(side):
+                if free[i % 2] is not None:
+                    side.wait_event(free[i % 2])
+                buf.copy_(ids_host[lo:hi], non_blocking=True)
+                landed = torch.cuda.Event()
+                landed.record(side)
+            return buf, landed
+
+        # every step's optimizer scalar up front: a pinned allocation inside the loop would wait for the running kernel
+        scales = self._step_scales(n_steps)
+        losses = []
+        nxt = stage(0)
+        for i in range(len(bounds) - 1):
+            buf, landed = nxt
+            if i + 2 < len(bounds):
+                nxt = stage(i + 1)                # queued before this chunk's work: the copy engine starts right away
+            main.wait_event(landed)
+            cols = self.gather_epoch(buf)
+            neg = draw_negatives(cols[1], bounds[i] * Bg)
+            loss = self.train_epoch(cols[0], cols[1], neg, Bg, check=False, _scales=scales[bounds[i]:bounds[i + 1]])
+            if loss_host is not None:
+                loss_host[bounds[i]:bounds[i + 1]].copy_(loss, non_blocking=True)
+            free[i % 2] = torch.cuda.Event()
+            free[i % 2].record(main)
+            losses.append(loss)
+        return losses[0] if len(losses) == 1 else torch.cat(losses)
 
     def train_step(self, user: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
         """Convenience: THIS rank's samples of one step; the global batch is the all-gather over ranks (rank-major).
