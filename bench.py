@@ -88,6 +88,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the other_workloads sub-results")
     ap.add_argument("--shard-it", type=int, default=0, help="tuning: 16-byte chunks per lane of the sharded kernel (1 or 2)")
+    ap.add_argument("--shard-remote-hint", type=int, default=None, help="tuning: L2 policy on stores into peer memory (1) or local only (0)")
     ap.add_argument("--shard-overlap", type=int, default=None, help="tuning: force the early first pass of phase A on (1) / off (0)")
     ap.add_argument("--emulate-world", type=int, default=0,
                     help="c4_linear on ONE GPU: host a group of this many ranks in one launch (structure check, no NVLink)")
@@ -694,6 +695,8 @@ def sharded_bench(args, wl, name):
         _lib.lib().trs_debug_shard_chunks_per_lane(args.shard_it)
     if args.shard_overlap is not None:
         _lib.lib().trs_debug_shard_overlap(args.shard_overlap)
+    if args.shard_remote_hint is not None:
+        _lib.lib().trs_debug_shard_remote_hint(args.shard_remote_hint)
     G = emu or world                       # ranks of the group
     K, W, B = args.steps, max(args.warmup, 3), wl["batch"]
     Bg = B * G
@@ -780,12 +783,20 @@ def sharded_bench(args, wl, name):
     resident_block()
     e2e_block()
     launches0 = tr.launches
+    # the timed region runs REGIONS times back to back (each: barrier + sync, n_launch epochs, sync + barrier); the
+    # line reports the MEDIAN region (max over ranks per region first) and lists all of them in config.region_ms --
+    # one region is a single ~100 ms launch, and a stray host / allocator hiccup on any rank would otherwise be the number
+    REGIONS = 3
+    ms_all, e2e_all = [], []
     with ClockSampler(local) as clocks:
-        ms, loss = timed(resident_block, n_launch)
-    launches = (tr.launches - launches0) // n_launch + 1
+        for _ in range(REGIONS):
+            ms_i, loss = timed(resident_block, n_launch)
+            ms_all.append(ms_i)
+    launches = (tr.launches - launches0) // (n_launch * REGIONS) + 1
     tr.check_status()
     mean_loss = float(loss.mean().item())
-    e2e_ms, _ = timed(e2e_block, n_launch)
+    for _ in range(REGIONS):
+        e2e_all.append(timed(e2e_block, n_launch)[0])
     # the persistent kernel (and the plan) alone
     sync_all()
     _, (gu, gp, neg) = block(ids_d, W, K, timing=True)
@@ -793,10 +804,12 @@ def sharded_bench(args, wl, name):
     tr.check_status()
     p0, p1, k0, k1 = tr.events
     kernel_ms, plan_ms = k0.elapsed_time(k1), p0.elapsed_time(p1)
-    times = torch.tensor([ms, e2e_ms, kernel_ms, plan_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor(ms_all + e2e_all + [kernel_ms, plan_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, kernel_ms, plan_ms = (float(x) for x in times.cpu())
+    times = [float(x) for x in times.cpu()]
+    ms_all, e2e_all, (kernel_ms, plan_ms) = times[:REGIONS], times[REGIONS:2 * REGIONS], times[2 * REGIONS:]
+    ms, e2e_ms = sorted(ms_all)[REGIONS // 2], sorted(e2e_all)[REGIONS // 2]
 
     S_ = {"sgd": 0, "adagrad": 1, "sparse_adam": 2}[wl["opt"]]
     alg = algorithmic_bytes(wl, gu, gp, neg, K, Bg, S_)        # of the GLOBAL batch; every rank owns 1/G of the rows
@@ -815,6 +828,9 @@ def sharded_bench(args, wl, name):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["desc"], "name": name, "batch_per_gpu": B, "global_batch": Bg, "optimizer": wl["opt"],
                    "repeats": R, "steps_per_launch": r_in * K, "launches": n_launch,
+                   "timed_regions": REGIONS, "region_ms": [round(x, 3) for x in ms_all],
+                   "e2e_region_ms": [round(x, 3) for x in e2e_all],
+                   "region_note": "value / e2e are the MEDIAN of the timed regions listed here (each max over ranks)",
                    "parallelism": (f"user / item tables ROW-SHARDED over {G} ranks (row % {G}); samples run on their "
                                    "user row's owner; item rows read from and gradient rows stored into the owner's "
                                    "HBM over NVLink by one persistent kernel per rank (CUDA-IPC mapped shards, flag "

@@ -684,7 +684,8 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
     // that is still reading step s's
     unsigned bar_no = 0;   // cross-rank barriers arrived at in this launch
     bool wait_pending = false;  // arrived at the barrier that ends a step, not yet waited for it (see phase A)
-    const bool overlap = C.overlap != 0;
+    const bool overlap = (C.overlap & 1) != 0;
+    const bool hint_remote = (C.overlap & 2) != 0;   // L2 policy also on stores into peer memory
 
     // ---- records of a phase-A round: lane gl fetches samples gl, gl + G, ... of the round and splits their ids
     //      into (owner, local row) ONCE (plan + epoch data: immutable, so the NEXT step's first rounds are fetched
@@ -824,8 +825,10 @@ shard_train_kernel(const __grid_constant__ ShardCtx ctx0, const ShardCtx* __rest
                         gp[e] = -g * xu.c[a][e];
                         gn[e] = g * xu.c[a][e];
                     }
-                    st_v4_hint(dp + (size_t)ch * 4, gp.v, pol_keep);
-                    st_v4_hint(dn + (size_t)ch * 4, gn.v, pol_keep);
+                    if (hint_remote || (int)qp == me) st_v4_hint(dp + (size_t)ch * 4, gp.v, pol_keep);
+                    else gp.st(dp + (size_t)ch * 4);
+                    if (hint_remote || (int)qn == me) st_v4_hint(dn + (size_t)ch * 4, gn.v, pol_keep);
+                    else gn.st(dn + (size_t)ch * 4);
                 }
             }
             if (gl == 0) {
@@ -1218,6 +1221,7 @@ static cudaError_t launch_shard(const ShardCtx* ctx0, const ShardCtx* ctxs, int 
 static int g_shard_prefer_it = 1;
 static unsigned long long* g_shard_trace = nullptr;
 static int g_shard_overlap = -1;
+static int g_shard_remote_hint = 1;
 
 static bool pick_shard_shape(int dim, int* G, int* IT) {
     if (dim <= 0 || dim % 4 || dim > 512) return false;
@@ -1395,7 +1399,7 @@ extern "C" int trs_shard_train_steps(const trs_shard* shards, int n_local, const
         c.dim = sh.dim;
         c.stage_par = SL.total / sizeof(float);
         // on one GPU the barrier that ends a step costs about what the second pass does; across GPUs it is worth hiding
-        c.overlap = g_shard_overlap < 0 ? (sh.world > 1 ? 1 : 0) : g_shard_overlap;
+        c.overlap = (g_shard_overlap < 0 ? (sh.world > 1 ? 1 : 0) : g_shard_overlap) | (g_shard_remote_hint ? 2 : 0);
         for (int q = 0; q < sh.world; ++q) {
             TRS_REQUIRE(sh.user[q].emb && sh.item[q].emb && sh.stage[q] && sh.sync[q], "rank %d: peer %d is not mapped",
                         sh.rank, q);
@@ -1467,6 +1471,8 @@ extern "C" void trs_debug_shard_chunks_per_lane(int it) { g_shard_prefer_it = it
 extern "C" void trs_debug_shard_trace(void* buf) { g_shard_trace = (unsigned long long*)buf; }
 // tuning hook (results do not depend on it): 1 / 0 forces the early first pass of phase A on / off, -1 = automatic
 extern "C" void trs_debug_shard_overlap(int mode) { g_shard_overlap = mode < 0 ? -1 : (mode ? 1 : 0); }
+// tuning hook: the evict_last policy on gradient rows stored into PEER memory (1, default) or only on local ones (0)
+extern "C" void trs_debug_shard_remote_hint(int on) { g_shard_remote_hint = on ? 1 : 0; }
 
 
 // ---- CUDA IPC plumbing ---------------------------------------------------------------------------------------
