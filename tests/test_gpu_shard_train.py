@@ -180,7 +180,7 @@ def test_host_fed_epoch_in_chunks_equals_one_resident_epoch(dev):
     draw = lambda pos, first: _lib.philox_negatives(99, first, pos, I)[0]
     a = _trainer(dev, 1, U, I, D, B, "adagrad", 0.05, params)
     loss_host = torch.zeros(steps).pin_memory()
-    la = a.train_epoch_host(ids_host, draw, loss_host, chunk_steps=64)      # 8 + 32 + 64 + 46 steps
+    la = a.train_epoch_host(ids_host, draw, loss_host, chunk_steps=64)      # 10 + 40 + 64 + 36 steps
     a.check_status()
     b = _trainer(dev, 1, U, I, D, B, "adagrad", 0.05, params)
     user, pos = ids_host[:, 0].reshape(-1).to(dev), ids_host[:, 1].reshape(-1).to(dev)

@@ -274,7 +274,7 @@ class ShardedLinearTrainer:
         """A whole epoch straight from THIS rank's loader output in (pinned) host memory: ``ids_host`` is int64
         [n_steps, 2, B] (user, positive).  The epoch is cut into chunks of steps; chunk i+1 is copied to the device on a
         side stream (two device buffers) while chunk i trains, so the host-to-device copy leaves the critical path
-        (chunks grow from ``chunk_steps / 32`` to ``chunk_steps`` steps: only the short first copy is exposed).
+        (chunks grow from a sixteenth of the epoch to ``chunk_steps`` steps: only the short first copy is exposed).
         Per chunk: id exchange (``gather_epoch``), ``draw_negatives(positives_global, first_global_sample)`` (device
         int64, e.g. the Philox kernel), plan, one persistent launch.  Per-step losses are also copied into ``loss_host``
         (pinned) if given.  No host synchronisation; call ``check_status()`` afterwards."""
@@ -286,11 +286,14 @@ class ShardedLinearTrainer:
         if n_steps == 0:
             return torch.empty(0, device=self.device)
         Bg = B * self.world
-        chunk_steps = int(chunk_steps or min(2048, max(64, -(-n_steps // 2))))
-        bounds, size = [0], max(8, chunk_steps // 32)   # a short first chunk (its copy is the one nothing hides), then
-        while bounds[-1] < n_steps:                      # four times longer each time (a copy takes < 10 % of the time
-            bounds.append(min(n_steps, bounds[-1] + size))   # its steps take to train) up to chunk_steps: every chunk
-            size = min(chunk_steps, 4 * size)                # costs ~0.2 ms of plan / launch ramp on the device
+        # A short first chunk (its copy is the one nothing hides), then four times longer each time (copying a step's ids
+        # takes 10-20 % of the time the step takes to train) up to chunk_steps: n/16, n/4, the rest for an epoch of up to
+        # ~3000 steps.  Few chunks: each costs 0.2 ms (one GPU) to ~1 ms (eight) of exchange / plan / launch ramp.
+        chunk_steps = int(chunk_steps or min(2048, max(64, -(-11 * n_steps // 16))))
+        bounds, size = [0], max(8, min(chunk_steps, -(-n_steps // 16)))
+        while bounds[-1] < n_steps:
+            bounds.append(min(n_steps, bounds[-1] + size))
+            size = min(chunk_steps, 4 * size)
         if self._h2d is None or tuple(self._h2d[0][0].shape) != (chunk_steps, k, B):
             self._h2d = ([torch.empty((chunk_steps, k, B), dtype=torch.int64, device=self.device) for _ in range(2)],
                          torch.cuda.Stream(self.device))
