@@ -222,3 +222,20 @@ def test_plan_launch_count_follows_the_batch_size():
     m = NS(n_meta=1, net=_lib.NET_FM, user=NS(n_rows=1_000_000), item=NS(n_rows=200_000), meta=[NS(n_rows=100)])
     assert engine.plan_launches(m, 8192, 200) == 1            # one CTA per (step, id space)
     assert engine.plan_launches(m, 16384, 200) == 2 * (3 + 3 + 1) + 2 + 1 + 2  # tiled sort + items + flags
+
+
+def test_batchnorm_refuses_a_training_batch_of_one_row_like_torch():
+    """torch.nn.BatchNorm1d raises on a [1, C] batch in train mode (what the reference's MLP would hit on a short last
+    batch); the fused MLP runner refuses the epoch with torch's message instead of normalising one row by itself."""
+    from torchrecsys_b200.engine import MlpEpochRunner
+    bn = torch.nn.BatchNorm1d(8).train()
+    with pytest.raises(ValueError) as torch_err:
+        bn(torch.zeros(1, 8))
+    with pytest.raises(ValueError) as ours:
+        MlpEpochRunner.check_batchnorm_rows(1025, 512, 8)
+    assert str(ours.value) == str(torch_err.value)
+    with pytest.raises(ValueError):
+        MlpEpochRunner.check_batchnorm_rows(7, 1, 8)
+    MlpEpochRunner.check_batchnorm_rows(1024, 512, 8)      # full batches
+    MlpEpochRunner.check_batchnorm_rows(1026, 512, 8)      # a last batch of two rows is fine
+    MlpEpochRunner.check_batchnorm_rows(0, 512, 8)

@@ -242,10 +242,20 @@ class MlpEpochRunner(_Chunked):
         """The dense gradients of the LAST step run (read-only view of the step's workspace)."""
         return self.grads
 
+    @staticmethod
+    def check_batchnorm_rows(n: int, batch_size: int, width: int) -> None:
+        """torch's BatchNorm1d refuses a training batch of one row (torch: nn/functional.py _verify_batch_size); so does
+        the reference, at the step that meets it.  Here the epoch is one launch: refuse it up front."""
+        if n > 0 and (batch_size == 1 or n % batch_size == 1):
+            raise ValueError("Expected more than 1 value per channel when training, got input size "
+                             f"torch.Size([1, {width}])")
+
     def _run(self, samples: Dict[str, torch.Tensor], batch_size: int) -> torch.Tensor:
         b = self.binding
         dev = samples["user"].device
         key = b.keys[0]
+        if self.net.use_batch_norm:
+            self.check_batchnorm_rows(samples["user"].shape[0], batch_size, self.net.hidden_layers[0])
         model = self.net.abi_model(self.optimizer.state, b.keys)
         mlp = self.net.abi_mlp(self.grads, self.optimizer.state if key else None, key)
         epoch = _lib.make_epoch(samples["user"], samples["pos"], samples["neg"],
