@@ -219,6 +219,38 @@ def test_sharded_training_equals_the_fused_single_gpu_kernel(dev):
         np.testing.assert_allclose(sd[k].cpu().numpy(), v.cpu().numpy(), rtol=2e-3, atol=2e-4, err_msg=k)
 
 
+def test_a_fitted_model_moves_onto_shards_and_back(dev):
+    """fit (fused kernel, torch SparseAdam) -> from_model -> a sharded epoch -> to_model -> fit again, against the fused
+    kernel running all three epochs: the optimizer's moments and step count travel both ways."""
+    import copy
+    from torchrecsys_b200.collaborative.linear import Linear
+    from torchrecsys_b200.engine import EpochRunner
+    from torchrecsys_b200.sharded import ShardedLinearTrainer
+    U, I, D, B, steps = 3000, 700, 64, 512, 4
+    rng = np.random.default_rng(21)
+    n = B * steps
+    epochs = [{k: _to(dev, rng.integers(0, m, n)) for k, m in (("user", U), ("pos", I), ("neg", I))} for _ in range(3)]
+    torch.manual_seed(5)
+    net_a = Linear(U, I, {}, D, use_metadata=False, use_cuda=True).to(dev)
+    net_b = copy.deepcopy(net_a)
+    opt_a = torch.optim.SparseAdam(list(net_a.parameters()), lr=0.02)
+    opt_b = torch.optim.SparseAdam(list(net_b.parameters()), lr=0.02)
+    for e in epochs:                                                   # a: the fused kernel all the way
+        EpochRunner(net_a, opt_a).run(e, B)
+    EpochRunner(net_b, opt_b).run(epochs[0], B)                        # b: fused, sharded over 2 ranks, fused
+    tr = ShardedLinearTrainer.from_model(net_b, opt_b, B, device=dev, emulate_world=2)
+    assert tr.binding.step0 == steps
+    tr.train_epoch(epochs[1]["user"], epochs[1]["pos"], epochs[1]["neg"], B)
+    tr.to_model(net_b, opt_b)
+    assert opt_b.state[net_b.user.weight]["step"] == 2 * steps
+    EpochRunner(net_b, opt_b).run(epochs[2], B)
+    for (k, p), (_, q) in zip(net_a.named_parameters(), net_b.named_parameters()):
+        np.testing.assert_allclose(q.detach().cpu().numpy(), p.detach().cpu().numpy(), rtol=2e-3, atol=2e-4, err_msg=k)
+        for name in ("exp_avg", "exp_avg_sq"):
+            np.testing.assert_allclose(opt_b.state[q][name].cpu().numpy(), opt_a.state[p][name].cpu().numpy(),
+                                       rtol=2e-3, atol=1e-6, err_msg=f"{k} {name}")
+
+
 def test_checkpoint_moves_between_group_sizes_and_the_single_gpu_model(dev):
     """state_dict() / optimizer_state_dict() are in the reference's single-process layout: train on 2 ranks, reload on
     3 ranks (parameters AND SparseAdam moments), continue -- equals 4 uninterrupted steps on 1 rank."""

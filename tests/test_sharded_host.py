@@ -120,3 +120,60 @@ def test_checkpoint_gather_over_a_gloo_group_of_two():
         assert p.exitcode == 0
     got = dict(q.get(timeout=5) for _ in range(2))
     assert got == {0: True, 1: True}
+
+
+@pytest.mark.parametrize("opt_name", ["SparseAdam", "Adagrad", "SGD"])
+def test_bridge_from_a_linear_model_and_its_torch_optimizer_and_back(opt_name):
+    """from_model shards TorchRecSys(net_type='linear').net together with the state of the torch optimizer bound to it
+    (hyper-parameters, moments, step count); to_model hands everything back in torch's own conventions, so that a torch
+    step taken afterwards equals the step the original pair would have taken."""
+    from torchrecsys_b200.collaborative.linear import Linear
+    U, I, D = 61, 29, 8
+    torch.manual_seed(3)
+
+    def make():
+        net = Linear(U, I, {}, D, use_metadata=False, use_cuda=False)
+        params = list(net.parameters())
+        opt = {"SparseAdam": lambda: torch.optim.SparseAdam(params, lr=0.05, betas=(0.8, 0.95), eps=1e-7),
+               "Adagrad": lambda: torch.optim.Adagrad(params, lr=0.05, lr_decay=0.01, eps=1e-9),
+               "SGD": lambda: torch.optim.SGD(params, lr=0.05)}[opt_name]()
+        return net, opt
+
+    def torch_step(net, opt, seed):
+        g = torch.Generator().manual_seed(seed)
+        opt.zero_grad()
+        for p in net.parameters():                       # a sparse gradient on a few rows, as nn.Embedding(sparse=True) gives
+            rows = torch.randint(0, p.shape[0], (7,), generator=g)
+            p.grad = torch.sparse_coo_tensor(rows[None], torch.randn(7, p.shape[1], generator=g), p.shape).coalesce()
+        opt.step()
+
+    net, opt = make()
+    for s in range(3):
+        torch_step(net, opt, s)
+    tr = ShardedLinearTrainer.from_model(net, opt, global_batch=32, device="cpu", emulate_world=3)
+    assert tr.kind == {"SparseAdam": "sparse_adam", "Adagrad": "adagrad", "SGD": "sgd"}[opt_name]
+    b = tr.binding
+    assert b.lr == 0.05 and b.step0 == (0 if opt_name == "SGD" else 3)
+    if opt_name == "SparseAdam":
+        assert (b.beta1, b.beta2, b.eps) == (0.8, 0.95, 1e-7)
+    if opt_name == "Adagrad":
+        assert (b.lr_decay, b.eps) == (0.01, 1e-9)
+    for r in range(3):
+        assert torch.equal(tr.tables[r]["item"][0], net.item.weight.detach()[r::3])
+    net2, opt2 = make()
+    tr.to_model(net2, opt2)
+    for (k, p), (_, q) in zip(net.named_parameters(), net2.named_parameters()):
+        assert torch.equal(p, q), k
+        for name, v in opt.state[p].items():
+            w = opt2.state[q][name]
+            assert type(v) is type(w) and (torch.equal(v, w) if torch.is_tensor(v) else v == w), (k, name)
+    torch_step(net, opt, 99)
+    torch_step(net2, opt2, 99)
+    for (k, p), (_, q) in zip(net.named_parameters(), net2.named_parameters()):
+        assert torch.equal(p, q), k
+    # not shardable: metadata tables, optimizers without a row-wise update
+    with pytest.raises(ValueError):
+        ShardedLinearTrainer.from_model(Linear(U, I, {"c": 5}, D, use_metadata=True), opt, 32, device="cpu", emulate_world=2)
+    with pytest.raises(NotImplementedError):
+        ShardedLinearTrainer.from_model(net, torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9), 32, device="cpu",
+                                        emulate_world=2)

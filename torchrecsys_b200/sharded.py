@@ -396,6 +396,72 @@ class ShardedLinearTrainer:
                 torch.cuda.synchronize(self.device)
             dist.barrier(group=self.group)  # peers read these rows: nobody trains before everyone has loaded
 
+    # ---- the bridge to TorchRecSys(net_type='linear'): shard a model + its torch optimizer, and hand them back ------
+    @classmethod
+    def from_model(cls, net: torch.nn.Module, optimizer: torch.optim.Optimizer, global_batch: int, device=None,
+                   group=None, emulate_world: Optional[int] = None, timeout_ms: int = 20000) -> "ShardedLinearTrainer":
+        """``net`` is a ``Linear`` scorer without metadata (``TorchRecSys(...).net``), ``optimizer`` the torch optimizer
+        bound to its parameters (SparseAdam / Adam, Adagrad, plain SGD -- the ones with a row-wise kernel, read the way
+        ``engine.bind_optimizer`` reads them).  Tables, optimizer state and step count move onto the shards; training
+        continues exactly where ``fit`` would (same update arithmetic: tested bit-for-bit against the fused kernel)."""
+        sd = {k: v.detach() for k, v in net.state_dict().items()}
+        extra = set(sd) - {"user.weight", "item.weight", "user_bias.weight", "item_bias.weight"}
+        if extra or getattr(net, "use_metadata", False):
+            raise ValueError(f"row-sharded training covers the Linear scorer without metadata (got {sorted(extra)})")
+        name = type(optimizer).__name__
+        g = optimizer.param_groups[0]
+        if any(any(pg.get(k) != g.get(k) for k in ("lr", "betas", "eps", "lr_decay")) for pg in optimizer.param_groups):
+            raise NotImplementedError("the row-wise update needs identical hyper-parameters in every param group")
+        if name in ("SparseAdam", "Adam"):
+            if g.get("weight_decay") or g.get("amsgrad") or g.get("maximize"):
+                raise NotImplementedError(f"{name}: weight_decay / amsgrad / maximize are not supported on sparse tables")
+            kw = dict(optimizer="sparse_adam", lr=g["lr"], betas=tuple(g["betas"]), eps=g["eps"])
+        elif name == "Adagrad":
+            if g.get("weight_decay") or g.get("maximize"):
+                raise NotImplementedError("Adagrad: weight_decay is not compatible with sparse gradients (as in torch)")
+            kw = dict(optimizer="adagrad", lr=g["lr"], eps=g["eps"], lr_decay=g.get("lr_decay", 0.0))
+        elif name == "SGD":
+            if g.get("momentum") or g.get("weight_decay") or g.get("nesterov") or g.get("maximize"):
+                raise NotImplementedError("SGD: momentum / weight_decay / nesterov are not row-sparse")
+            kw = dict(optimizer="sgd", lr=g["lr"])
+        else:
+            raise NotImplementedError(f"optimizer {name} has no row-wise update; use SparseAdam, Adagrad or plain SGD")
+        n_users, dim = sd["user.weight"].shape
+        tr = cls(n_users, sd["item.weight"].shape[0], dim, global_batch, device=device, group=group,
+                 emulate_world=emulate_world, timeout_ms=timeout_ms, **kw)
+        state = None
+        named = dict(net.named_parameters())
+        if all(len(optimizer.state.get(named[k], {})) for k in sd) and _STATE_KEYS[tr.kind]:
+            state = {}
+            for k in sd:
+                st = optimizer.state[named[k]]
+                step = st.get("step", 0)
+                state[k] = {"step": int(step.item()) if torch.is_tensor(step) else int(step)}
+                for sname in _STATE_KEYS[tr.kind]:
+                    state[k][sname] = st[sname].detach()
+        tr.load_state_dict(sd, state)
+        return tr
+
+    def to_model(self, net: torch.nn.Module, optimizer: Optional[torch.optim.Optimizer] = None) -> None:
+        """Gather the shards back into ``net`` (and the optimizer's per-parameter state into ``optimizer``, in torch's own
+        names and step convention) -- for ``evaluate`` / ``predict`` / ``torch.save`` on one device.  Collective: every
+        rank of the group calls it and ends up with the full model."""
+        sd = self.state_dict()
+        with torch.no_grad():
+            for k, p in net.named_parameters():
+                p.copy_(sd[k].to(p.device))
+        if hasattr(net, "_trs_version"):
+            net._trs_version += 1
+        if optimizer is None or not _STATE_KEYS[self.kind]:
+            return
+        osd = self.optimizer_state_dict()
+        tensor_step = type(optimizer).__name__ != "SparseAdam"     # torch keeps an int there for SparseAdam only
+        for k, p in net.named_parameters():
+            st = optimizer.state[p]
+            st["step"] = torch.tensor(float(self.binding.step0)) if tensor_step else int(self.binding.step0)
+            for sname in _STATE_KEYS[self.kind]:
+                st[sname] = osd[k][sname].to(p.device).view_as(p).clone()
+
     def gather_full(self, name: str) -> Tuple[torch.Tensor, torch.Tensor]:
         sd = self.state_dict()
         return sd[f"{name}.weight"], sd[f"{name}_bias.weight"]
