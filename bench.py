@@ -768,7 +768,7 @@ def sharded_bench(args, wl, name):
     rep_d = {q: t[W:].repeat(r_in, 1, 1) for q, t in ids_d.items()}
     rep_h = {q: t[W:].repeat(r_in, 1, 1).pin_memory() for q, t in ids_h.items()}
     loss_host = torch.empty(r_in * K, dtype=torch.float32).pin_memory()
-    resident_block = lambda: block(rep_d, 0, r_in * K)[0]
+    resident_block = lambda: block(rep_d, 0, r_in * K, timing=True)[0]   # events around the plan and the kernel
     if emu:
         e2e_block = lambda: block(rep_h, 0, r_in * K, loss_host=loss_host)[0]
     else:   # the trainer's own host-fed epoch: chunks copied on a side stream while the previous chunk trains
@@ -787,29 +787,33 @@ def sharded_bench(args, wl, name):
     # line reports the MEDIAN region (max over ranks per region first) and lists all of them in config.region_ms --
     # one region is a single ~100 ms launch, and a stray host / allocator hiccup on any rank would otherwise be the number
     REGIONS = 3
-    ms_all, e2e_all = [], []
+    ms_all, e2e_all, kern_all, plan_all = [], [], [], []
     with ClockSampler(local) as clocks:
         for _ in range(REGIONS):
             ms_i, loss = timed(resident_block, n_launch)
             ms_all.append(ms_i)
+            p0, p1, k0, k1 = tr.events           # the region's last launch of r_in x K steps, scaled to the K-step block
+            kern_all.append(k0.elapsed_time(k1) / r_in)
+            plan_all.append(p0.elapsed_time(p1) / r_in)
     launches = (tr.launches - launches0) // (n_launch * REGIONS) + 1
     tr.check_status()
     mean_loss = float(loss.mean().item())
     for _ in range(REGIONS):
         e2e_all.append(timed(e2e_block, n_launch)[0])
-    # the persistent kernel (and the plan) alone
+    # the ids of one K-step block (for the algorithmic bytes); the kernel's time is the one measured INSIDE the timed
+    # regions above (CUDA events around the persistent launch of the median region)
     sync_all()
-    _, (gu, gp, neg) = block(ids_d, W, K, timing=True)
+    _, (gu, gp, neg) = block(ids_d, W, K)
     sync_all()
     tr.check_status()
-    p0, p1, k0, k1 = tr.events
-    kernel_ms, plan_ms = k0.elapsed_time(k1), p0.elapsed_time(p1)
-    times = torch.tensor(ms_all + e2e_all + [kernel_ms, plan_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor(ms_all + e2e_all + kern_all + plan_all, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     times = [float(x) for x in times.cpu()]
-    ms_all, e2e_all, (kernel_ms, plan_ms) = times[:REGIONS], times[REGIONS:2 * REGIONS], times[2 * REGIONS:]
-    ms, e2e_ms = sorted(ms_all)[REGIONS // 2], sorted(e2e_all)[REGIONS // 2]
+    ms_all, e2e_all, kern_all, plan_all = (times[i * REGIONS:(i + 1) * REGIONS] for i in range(4))
+    mid = sorted(range(REGIONS), key=lambda i: ms_all[i])[REGIONS // 2]
+    ms, e2e_ms = ms_all[mid], sorted(e2e_all)[REGIONS // 2]
+    kernel_ms, plan_ms = kern_all[mid], plan_all[mid]          # per K steps
 
     S_ = {"sgd": 0, "adagrad": 1, "sparse_adam": 2}[wl["opt"]]
     alg = algorithmic_bytes(wl, gu, gp, neg, K, Bg, S_)        # of the GLOBAL batch; every rank owns 1/G of the rows
@@ -855,7 +859,9 @@ def sharded_bench(args, wl, name):
                      "traffic": traffic_of(name, K)[0],
                      "traffic_source": "static: profiles/shard_r2.md (ncu --set full of a 1-rank launch on 4M x 1M tables; "
                                        "per step, times K; not measured by this run)",
-                     "kernel": "trs::shard_train_kernel (one persistent launch per rank, K steps)",
+                     "kernel": "trs::shard_train_kernel (one persistent launch per rank)",
+                     "kernel_time_source": "CUDA events around the persistent launch INSIDE the median timed region "
+                                           "(steps_per_launch steps), max over ranks",
                      "kernel_ms_per_step": kernel_ms / K, "plan_ms_per_step": plan_ms / K,
                      "algorithmic_bytes_per_step": alg / K / G,
                      "whole_step_frac": alg / G / (ms / R * 1e-3) / 1e9 / peak,
