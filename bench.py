@@ -615,8 +615,9 @@ def predict_bench(args, wl, name, K=None, W=None):
         "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": wl["desc"], "name": name, "users_per_step": B, "top_k": k,
-                   "parallelism": (f"item table in {world} contiguous blocks, local top-k per rank, all-gather + "
-                                   "k-way merge (the same users on every rank)") if world > 1 else "single GPU",
+                   "parallelism": (f"item table in {world} contiguous blocks, local top-k per rank (the same users on "
+                                   "every rank), a user's candidate lists go to ONE merger rank (all_to_all), k-way merge "
+                                   "of its share of the users there, results all-gathered") if world > 1 else "single GPU",
                    "l2": "inputs larger than L2: bf16 item operand 1.44 GB streamed per user wave",
                    "timed_region": "user operand preparation + tcgen05 score/top-k kernel + exact fp32 re-scoring, every "
                                    "step; the bf16 item operand is prepared once while the tables are unchanged (first "

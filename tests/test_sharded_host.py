@@ -177,3 +177,15 @@ def test_bridge_from_a_linear_model_and_its_torch_optimizer_and_back(opt_name):
     with pytest.raises(NotImplementedError):
         ShardedLinearTrainer.from_model(net, torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9), 32, device="cpu",
                                         emulate_world=2)
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 64, 150, 500, 1420, 5000, 100_000])
+def test_host_fed_epochs_are_cut_into_a_few_growing_chunks(n):
+    cap, b = ShardedLinearTrainer.host_chunks(n)
+    sizes = np.diff(b)
+    assert b[0] == 0 and b[-1] == n and (sizes > 0).all() and sizes.max() <= cap <= 2048
+    assert sizes[0] <= max(8, -(-n // 16))                      # the exposed first copy is short
+    assert all(sizes[i + 1] <= 4 * sizes[i] for i in range(len(sizes) - 1))   # each copy hides behind the chunk before
+    assert len(sizes) <= 3 + n // 2048 + 1                      # and the epoch is not shredded
+    cap, b = ShardedLinearTrainer.host_chunks(150, 64)
+    assert (cap, b) == (64, [0, 10, 50, 114, 150])

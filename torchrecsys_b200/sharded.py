@@ -269,6 +269,19 @@ class ShardedLinearTrainer:
         cols.copy_(allr.view(W, n_steps, k, B).permute(2, 1, 0, 3))
         return [cols[j].view(-1) for j in range(k)]
 
+    @staticmethod
+    def host_chunks(n_steps: int, chunk_steps: Optional[int] = None) -> Tuple[int, List[int]]:
+        """Chunk boundaries of a host-fed epoch: (largest chunk, [0, ..., n_steps]).  A short first chunk (its copy is
+        the one nothing hides), then four times longer each time (copying a step's ids takes 10-20 % of the time the step
+        takes to train) up to ``chunk_steps``: n/16, n/4, the rest for an epoch of up to ~3000 steps.  Few chunks: each
+        costs 0.2 ms (one GPU) to ~1 ms (eight) of exchange / plan / launch ramp."""
+        chunk_steps = int(chunk_steps or min(2048, max(64, -(-11 * n_steps // 16))))
+        bounds, size = [0], max(8, min(chunk_steps, -(-n_steps // 16)))
+        while bounds[-1] < n_steps:
+            bounds.append(min(n_steps, bounds[-1] + size))
+            size = min(chunk_steps, 4 * size)
+        return chunk_steps, bounds
+
     def train_epoch_host(self, ids_host: torch.Tensor, draw_negatives: Callable[[torch.Tensor, int], torch.Tensor],
                          loss_host: Optional[torch.Tensor] = None, chunk_steps: Optional[int] = None) -> torch.Tensor:
         """A whole epoch straight from THIS rank's loader output in (pinned) host memory: ``ids_host`` is int64
@@ -286,14 +299,7 @@ class ShardedLinearTrainer:
         if n_steps == 0:
             return torch.empty(0, device=self.device)
         Bg = B * self.world
-        # A short first chunk (its copy is the one nothing hides), then four times longer each time (copying a step's ids
-        # takes 10-20 % of the time the step takes to train) up to chunk_steps: n/16, n/4, the rest for an epoch of up to
-        # ~3000 steps.  Few chunks: each costs 0.2 ms (one GPU) to ~1 ms (eight) of exchange / plan / launch ramp.
-        chunk_steps = int(chunk_steps or min(2048, max(64, -(-11 * n_steps // 16))))
-        bounds, size = [0], max(8, min(chunk_steps, -(-n_steps // 16)))
-        while bounds[-1] < n_steps:
-            bounds.append(min(n_steps, bounds[-1] + size))
-            size = min(chunk_steps, 4 * size)
+        chunk_steps, bounds = self.host_chunks(n_steps, chunk_steps)
         if self._h2d is None or tuple(self._h2d[0][0].shape) != (chunk_steps, k, B):
             self._h2d = ([torch.empty((chunk_steps, k, B), dtype=torch.int64, device=self.device) for _ in range(2)],
                          torch.cuda.Stream(self.device))
