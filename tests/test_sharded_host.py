@@ -189,3 +189,45 @@ def test_host_fed_epochs_are_cut_into_a_few_growing_chunks(n):
     assert len(sizes) <= 3 + n // 2048 + 1                      # and the epoch is not shredded
     cap, b = ShardedLinearTrainer.host_chunks(150, 64)
     assert (cap, b) == (64, [0, 10, 50, 114, 150])
+
+
+def test_host_fed_epoch_control_flow_with_stub_streams(monkeypatch):
+    """The chunk loop of train_epoch_host with the device pieces stubbed out (streams / events as no-ops, the training
+    call recorded): every step is handed over exactly once and in order, negatives are keyed by the global sample index
+    of the chunk's first sample, each chunk gets ITS slice of the optimizer scalars, losses land in the host buffer."""
+    import contextlib
+
+    class _Stub:
+        def wait_stream(self, s): pass
+        def wait_event(self, e): pass
+        def record(self, s=None): pass
+
+    monkeypatch.setattr(torch.cuda, "Stream", lambda *a, **k: _Stub())
+    monkeypatch.setattr(torch.cuda, "Event", lambda *a, **k: _Stub())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _Stub())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    B, steps = 4, 150
+    tr = ShardedLinearTrainer(50, 20, 8, global_batch=B, device="cpu", emulate_world=1)
+    tr.bases = {0: 0}                                           # pretend the arena is mapped
+    calls = []
+
+    def fake_train_epoch(user, pos, neg, batch, check=True, timing=False, _scales=None):
+        n = user.shape[0] // batch
+        calls.append((user.clone(), pos.clone(), neg.clone(), _scales.clone(), check))
+        tr.binding.step0 += n
+        return user.view(n, batch).float().mean(1)
+
+    tr.train_epoch = fake_train_epoch
+    tr._step_scales = lambda n: torch.arange(n, dtype=torch.float32)
+    ids = torch.arange(steps * 2 * B).view(steps, 2, B)
+    loss_host = torch.zeros(steps)
+    out = tr.train_epoch_host(ids, lambda pos, first: pos + first, loss_host, chunk_steps=64)
+    _, bounds = ShardedLinearTrainer.host_chunks(steps, 64)
+    assert len(calls) == len(bounds) - 1 and not any(c[4] for c in calls)
+    assert torch.equal(torch.cat([c[0] for c in calls]), ids[:, 0].reshape(-1))
+    assert torch.equal(torch.cat([c[1] for c in calls]), ids[:, 1].reshape(-1))
+    assert torch.equal(torch.cat([c[3] for c in calls]), torch.arange(steps, dtype=torch.float32))
+    for c, lo in zip(calls, bounds):
+        assert torch.equal(c[2], c[1] + lo * B)                 # first global sample of the chunk
+    want = ids[:, 0].float().mean(1)
+    assert torch.equal(out, want) and torch.equal(loss_host, want) and tr.binding.step0 == steps
