@@ -8,15 +8,24 @@
 //
 //   phase A  the samples PLACED on this rank (those whose user row it owns: user rows never cross NVLink; the
 //            step's global batch is the same set of samples whichever rank runs which).  A row group (dim/4
-//            lanes) per sample; the rows of up to 8 samples per group are in flight at once (cp.async straight
-//            from the owner's HBM -- local or peer -- into thread-private shared-memory slots).  Both scores,
-//            the hinge with g = [h >= 0] / B_global, and each lookup's gradient row goes straight into its
-//            OWNER's staging buffer at slot = the lookup's position in the global batch (remote store).
-//   cross-rank barrier: per rank a grid barrier, then its last CTA posts the barrier number into every peer's
-//            flag words (st.release.sys after __threadfence_system) and everybody waits for W flags locally.
-//   phase B  every owner walks the (local row, slot) pairs of the lookups it owns -- stably sorted by row: the
-//            plan, built once per epoch -- sums the staged rows of a row in slot order (what coalesce() gives,
-//            deterministic), applies SGD / Adagrad / SparseAdam to parameter + state rows of ITS shard.
+//            lanes) per sample.  The two item rows of a group's first 7 samples sit in a per-group region of shared
+//            memory that bulk async copies (cp.async.bulk + one mbarrier per group) fill A STEP AHEAD, straight from
+//            the owner's HBM -- local or peer -- while the owners update; rows the previous step updates (plan
+//            flag) are fetched after the barrier instead.  User rows (+ optimizer state) come by cp.async into
+//            thread-private slots, four samples at a time.  Both scores, the hinge with g = [h >= 0] / B_global; a
+//            user row looked up once in the step is updated in place, every other gradient row goes straight into
+//            its OWNER's staging buffer at slot = the lookup's position in the global batch (remote store, L2
+//            policy evict_last: the owner reads it once, with evict_first).
+//            With W > 1 phase A runs in two passes: the samples none of whose rows the previous step updates run
+//            BEFORE the rank waits for the barrier that ends that step (the staging buffers exist twice, for even
+//            and odd steps), the flagged ones after it.
+//   cross-rank barrier: a monotonic arrival counter per rank -- one release fence (system scope after stores into
+//            peer memory), a relaxed add to every rank's counter, relaxed polling of the own counter, one acquire
+//            load.  The barrier after phase B is split into arrive (there) and wait (inside the next phase A).
+//   phase B  every owner walks the (local row, slot) pairs of the lookups it owns and phase A did not finish --
+//            stably sorted by row: the plan, built once per epoch -- sums the staged rows of a row in slot order
+//            (what coalesce() gives, deterministic, independent of W), applies SGD / Adagrad / SparseAdam to
+//            parameter + state rows of ITS shard.
 //   cross-rank barrier (updates visible before the next step's reads).
 //
 // HBM per step and rank: each owned touched row's parameter + state read once and written once, the staged
