@@ -103,6 +103,23 @@ def _worker(rank, port, q):
         both = torch.stack(parts)                                  # [world, steps, 2, B]
         for j in range(2):
             ok = ok and cols[j].dtype == torch.int64 and torch.equal(cols[j], both[:, :, j].permute(1, 0, 2).reshape(-1))
+        # a fitted model moves onto the two ranks and back (to_model gathers over the group: both ranks get everything)
+        from torchrecsys_b200.collaborative.linear import Linear
+        torch.manual_seed(11)
+        net = Linear(U, I, {}, D, use_metadata=False, use_cuda=False)
+        opt = torch.optim.Adagrad(net.parameters(), lr=0.1)
+        for p in net.parameters():
+            opt.state[p]["sum"].uniform_(0.0, 1.0)
+            opt.state[p]["step"] += 5
+        tr2 = ShardedLinearTrainer.from_model(net, opt, global_batch=16, device="cpu")
+        ok = ok and tr2.binding.step0 == 5 and torch.equal(tr2.tables[rank]["user"][0], net.user.weight.detach()[rank::2])
+        ok = ok and torch.equal(tr2.state[rank]["item"][0][0], opt.state[net.item.weight]["sum"][rank::2])
+        net2 = Linear(U, I, {}, D, use_metadata=False, use_cuda=False)
+        opt2 = torch.optim.Adagrad(net2.parameters(), lr=0.1)
+        tr2.to_model(net2, opt2)
+        for (k, a), (_, b) in zip(net.named_parameters(), net2.named_parameters()):
+            ok = ok and torch.equal(a, b) and torch.equal(opt.state[a]["sum"], opt2.state[b]["sum"])
+            ok = ok and float(opt2.state[b]["step"]) == 5.0
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
